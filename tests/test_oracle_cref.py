@@ -1,0 +1,78 @@
+"""C oracle (oracle/cpu_ref.c) vs the Python big-int arbiter (oracle/oracle.py). CPU only."""
+import numpy as np
+import pytest
+
+from oracle import cref as C
+from oracle import oracle as O
+
+GENS = {
+    "bls12_377_g1": O.G1_GEN,
+    "bls12_377_g2": O.G2_GEN,
+}
+
+
+def _bw6_point(curve, rng):
+    """random curve point (not necessarily in the r-torsion; irrelevant to MSM parity)."""
+    while True:
+        x = rng.below(O.Q761)
+        y = O.sqrt_mod((x * x * x + curve.b) % O.Q761, O.Q761)
+        if y is not None:
+            return (x, y)
+
+
+def gen_for(name, rng):
+    if name in GENS:
+        return GENS[name]
+    return _bw6_point(O.CURVES[name], rng)
+
+
+@pytest.mark.parametrize("name", list(O.CURVES))
+def test_scalar_mul_and_codecs(name):
+    L = C.LAYOUTS[name]
+    rng = O.SplitMix64(1)
+    g = gen_for(name, rng)
+    for k in (0, 1, 2, 3, rng.below(L.curve.scalar_mod), L.curve.scalar_mod - 1):
+        got = L.jacobian_to_affine(C.scalar_mul(L, g, k))
+        assert got == L.curve.pmul(g, k), (name, k)
+
+
+@pytest.mark.parametrize("name", list(O.CURVES))
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 100])
+def test_msm_matches_python_pippenger_and_naive(name, n):
+    L = C.LAYOUTS[name]
+    rng = O.SplitMix64(1000 + n)
+    g = gen_for(name, rng)
+    ks = [rng.below(L.curve.scalar_mod) for _ in range(n)]
+    packed = C.fixed_base_batch(L, g, ks)
+    pts = L.affine_from_records(packed)
+    scalars = [rng.below(L.curve.scalar_mod) for _ in range(n)]
+    if n >= 31:
+        scalars[0] = 0                       # skipped
+        scalars[1] = 1                       # unit-scalar fast path
+        scalars[2] = L.curve.scalar_mod - 1
+        pts[4] = pts[3]                      # duplicate bases (P + P inside a bucket)
+        scalars[4] = scalars[3]
+        pts[6] = L.curve.pneg(pts[5])        # P + (-P) inside a bucket
+        scalars[6] = scalars[5]
+        pts[7] = None                        # infinity base
+    bases = L.affine_records(pts)
+    want = L.curve.msm_naive(pts, scalars)
+    got = L.jacobian_to_affine(C.msm(L, bases, L.scalars_array(scalars), threads=4))
+    assert got == want
+    if n <= 33:
+        assert O.msm_pippenger(L.curve, pts, scalars) == want
+    # packed layout (no flag byte) must agree as well
+    got2 = L.jacobian_to_affine(C.msm(L, L.affine_records(pts, L.packed_stride), L.scalars_array(scalars), threads=1))
+    assert got2 == want
+
+
+def test_window_rule_matches_arkworks_table():
+    # n=2^16->13, 2^20->15, 2^22->17, 2^24->18, 4096->10, 20->3
+    assert [O.msm_window_bits(n) for n in (1 << 16, 1 << 20, 1 << 22, 1 << 24, 4096, 20)] == [13, 15, 17, 18, 10, 3]
+
+
+def test_batch_exponent_bytes():
+    # batch.rs:23-28: n = 4096 -> 18 bytes (144-bit exponents); capped at 31
+    assert O.batch_exponent_bytes(4096) == 18
+    assert O.batch_exponent_bytes(20) == 17
+    assert O.batch_exponent_bytes(1 << 200) == 31
