@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Headline benchmark: BLS12-377 G1 MSM, n = 2^20 pairs per GPU (BASELINE.json metric
+"G1 MSM Mscalar-muls/s (BLS12-377, n=2^20) at 1/2/4/8 GPU").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: arkworks-algorithm C port
+
+One "step" = one MSM over one batch of synthetic (base, scalar) pairs.  At N GPUs every
+rank owns a contiguous chunk of 2^20 pairs of one N*2^20-pair MSM (weak scaling): local
+bucket MSM -> NCCL all-gather of the 144-byte partial Jacobian points -> local sum kernel
+(NCCL cannot reduce elliptic-curve points).
+
+Printed JSON (rank 0, one line):
+  value     pairs/s (in Mpairs/s) with inputs already resident in HBM, CUDA-event timed,
+            max over ranks, barrier + synchronize on both sides
+  e2e       the same metric through the host-pointer C-ABI call b200_msm(): pinned host
+            buffers in arkworks layout -> H2D -> pack -> MSM -> D2H of the result
+  roofline  dominant kernel (k_bucket_accumulate) vs the measured HBM peak; the path is
+            integer-ALU-bound so the fraction is small by construction
+  cpu_baseline  the C oracle (arkworks-algorithm port) on the box's host cores, same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LOG2_N = 20
+CURVE = "bls12_377_g1"
+BYTES_PER_PAIR = 128            # 32 B scalar + 2 x 48 B affine coordinates
+SEED = 0x5DBE62598D313D76       # first 8 bytes of the reference's test seed (hash_to_curve/mod.rs:290-293)
+METRIC = "G1 MSM Mscalar-muls/s (BLS12-377, n=2^20)"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def uniform_scalars(n: int, seed: int) -> np.ndarray:
+    """n uniform 252-bit scalars (< r) as uint64 [n, 4]; numpy PCG64 seeded from SEED."""
+    rng = np.random.default_rng(seed)
+    arr = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + \
+        rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    arr[:, 3] &= np.uint64((1 << 60) - 1)
+    return arr
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the arkworks-algorithm C port (oracle/cpu_ref.c), window-parallel threads
+# ----------------------------------------------------------------------------------------
+def cpu_inputs(n: int):
+    """Bases for the CPU arm: 1024 distinct oracle points tiled to n (an MSM's cost does not
+    depend on the base values); scalars uniform."""
+    from oracle import cref as C
+    from oracle import oracle as O
+    L = C.LAYOUTS[CURVE]
+    rng = O.SplitMix64(SEED)
+    packed = C.fixed_base_batch(L, O.G1_GEN, [rng.below(O.R) for _ in range(1024)])
+    bases = C.with_flags(L, np.tile(packed, (max(1, n // 1024), 1))[:n])
+    return L, bases, uniform_scalars(n, SEED & 0xFFFFFFFF)
+
+
+def cpu_msm_rate(n: int, reps: int, threads: int):
+    from oracle import cref as C
+    L, bases, sc = cpu_inputs(n)
+    C.msm(L, bases[:1024], sc[:1024], threads=threads)           # warm the library
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        C.msm(L, bases, sc, threads=threads)
+    dt = (time.perf_counter() - t0) / reps
+    return n / dt, dt, C.msm_window_tasks(L, n)
+
+
+def pick_cpu_sample(threads: int, budget_s: float = 6.0):
+    """Largest n = 2^k <= 2^20 whose single MSM fits the time budget on this host."""
+    rate, _, _ = cpu_msm_rate(1 << 13, 1, threads)
+    k = LOG2_N
+    while k > 13 and (1 << k) / (rate * 1.6) > budget_s:          # larger n runs ~1.6x faster per pair
+        k -= 1
+    return k
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    k = pick_cpu_sample(cores)
+    n = 1 << k
+    from oracle import cref as C
+    L, bases, sc = cpu_inputs(n)
+    tasks = C.msm_window_tasks(L, n)
+    threads = min(cores, tasks)
+    for _ in range(args.warmup):
+        C.msm(L, bases, sc, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        C.msm(L, bases, sc, threads=threads)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt / 1e6
+    sample = f"n=2^{k} pairs per step (full workload is 2^{LOG2_N}), {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (377-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": f"BLS12-377 G1 Pippenger MSM on host cores, arkworks window rule, n=2^{k}",
+                   "note": "arkworks-algorithm C port (oracle/cpu_ref.c), not the arkworks binary: no Rust toolchain"},
+        "cpu_baseline": {"value": val, "unit": "Mpairs/s", "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores": cores, "window_tasks": tasks},
+        "e2e": {"value": val, "unit": "Mpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from celo_bls_snark_rs_b200 import engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E.init(local)
+    cid = E.BLS12_377_G1
+    n = 1 << args.log2n
+    stream = torch.cuda.Stream(device=dev)          # an explicit stream: kernels, NCCL and the timing events share it
+    torch.cuda.set_stream(stream)
+    sp = stream.cuda_stream
+    assert sp != 0
+
+    # ---- synthetic inputs, resident in HBM: bases = k_i * G on the GPU, two rotating input sets ----
+    gen_x = 0x008848DEFE740A67C8FC6225BF87FF5485951E2CAA9D41BB188282C8BD37CB5CD5481512FFCD394EEAB9B16EB21BE9EF
+    gen_y = 0x01914A69C5102EFF1F674F5D30AFEEC4BD7FB348CA3E52D96D182AD44FB82305C2FE3D3634A9591AFD82DE55559C8EA6
+    p377 = 0x01AE3A4617C510EAC63B05C06CA1493B1A22D9F300F5138F1EF3622FBA094800170B5D44300000008508C00000000001
+    mont = lambda v: (v << 384) % p377
+    gen = np.frombuffer(mont(gen_x).to_bytes(48, "little") + mont(gen_y).to_bytes(48, "little"), dtype=np.uint8)
+    d_gen = torch.from_numpy(gen.copy()).to(dev)
+    sets = []
+    for s in range(2):
+        ks = uniform_scalars(n, (SEED + 1000 * rank + s) & 0xFFFFFFFF)
+        sc = uniform_scalars(n, (SEED + 77 + 1000 * rank + s) & 0xFFFFFFFF)
+        d_ks = torch.from_numpy(ks.view(np.int64)).to(dev)
+        d_bases = torch.empty((n, 96), dtype=torch.uint8, device=dev)
+        E.fixed_base_mul_device(cid, d_gen.data_ptr(), d_ks.data_ptr(), n, d_bases.data_ptr(), sp)
+        d_sc = torch.from_numpy(sc.view(np.int64)).to(dev)
+        sets.append((d_bases, d_sc, sc))
+    torch.cuda.synchronize()
+
+    d_part = torch.zeros(144, dtype=torch.uint8, device=dev)
+    d_all = torch.zeros(world * 144, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(144, dtype=torch.uint8, device=dev)
+
+    def step(i):
+        d_bases, d_sc, _ = sets[i & 1]
+        E.msm_device(cid, d_bases.data_ptr(), d_sc.data_ptr(), n, d_part.data_ptr(), sp)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_part)
+            E.sum_jacobian_device(cid, d_all.data_ptr(), world, d_res.data_ptr(), sp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    E.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = E.launch_count() - launches0 + (args.steps if world > 1 else 0)     # + NCCL all-gather kernels
+    acc_ms, acc_launches, acc_pairs = E.profile_read()
+    E.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-pointer C-ABI (pinned arkworks-layout buffers) ----
+    h_bases = torch.zeros((n, 104), dtype=torch.uint8).pin_memory()
+    h_bases[:, :96].copy_(sets[0][0].cpu())
+    h_sc = torch.from_numpy(sets[0][2].view(np.int64)).pin_memory()
+    out = np.zeros(144, dtype=np.uint8)
+
+    def e2e_step():
+        E.msm_host_ptrs(cid, h_bases.data_ptr(), 104, h_sc.data_ptr(), n, out)
+        if world > 1:
+            d_part.copy_(torch.from_numpy(out), non_blocking=False)
+            dist.all_gather_into_tensor(d_all, d_part)
+            E.sum_jacobian_device(cid, d_all.data_ptr(), world, d_res.data_ptr(), sp)
+            return d_res.cpu()
+        return out
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        total_pairs = n * world * args.steps
+        value = total_pairs / (ms / 1e3) / 1e6
+        e2e_val = total_pairs / (e2e_ms / 1e3) / 1e6
+        peak, peak_src = measured_peak_gbs()
+        kernel_ms = acc_ms / max(acc_launches, 1)
+        achieved = (acc_pairs / max(acc_launches, 1)) * BYTES_PER_PAIR / (kernel_ms / 1e3) / 1e9 if acc_launches else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("k_bucket_accumulate_bytes_per_launch")
+            except Exception:
+                traffic = None
+        c, w, nb = E.msm_plan(cid, n)
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (377-bit Montgomery, integer pipe)", "data": "synthetic",
+            "config": {"workload": f"BLS12-377 G1 Pippenger MSM, n=2^{args.log2n} pairs per GPU, uniform 252-bit scalars, "
+                                   "bases k_i*G generated on device", "pairs_per_gpu": n, "window_bits": c, "windows": w,
+                       "buckets_per_window": nb, "parallelism": f"chunk-sharded x{world} + all-gather of 144 B partials",
+                       "l2": "two rotating input sets; inputs (128 MiB) + workspace (>160 MiB) exceed the 126 MB L2"},
+            "e2e": {"value": e2e_val, "unit": "Mpairs/s", "h2d_bytes_per_step": n * (104 + 32),
+                    "d2h_bytes_per_step": 144, "ms_per_step": e2e_ms / args.steps,
+                    "api": "b200_msm (host pointers, pinned arkworks-layout records)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_bucket_accumulate", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "kernel_share_of_step": kernel_ms / (ms / args.steps) if ms else None,
+                         "algorithmic_bytes_per_launch": n * BYTES_PER_PAIR,
+                         "note": "integer-ALU-bound path (about 160 377-bit Montgomery products per pair): "
+                                 "the HBM fraction is small by construction; see DESIGN.md"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            k = pick_cpu_sample(cores)
+            from oracle import cref as C
+            tasks = C.msm_window_tasks(C.LAYOUTS[CURVE], 1 << k)
+            threads = min(cores, tasks)
+            rate, dt, _ = cpu_msm_rate(1 << k, 1, threads)
+            line["cpu_baseline"] = {"value": rate / 1e6, "unit": "Mpairs/s", "cores": threads, "kind": "port",
+                                    "sample": f"one MSM of n=2^{k} pairs ({dt:.2f} s), arkworks window rule, "
+                                              f"{threads} threads over {tasks} windows", "host_cores": cores}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=LOG2_N)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,183 @@
+// Definitions of the per-curve host entry points (kernel launches).  Included by inst_*.cu only.
+#pragma once
+#include "engine.cuh"
+
+namespace b200 {
+
+template <class C> struct CurveTraits;
+template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; };
+template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; };
+
+// Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
+// keeping enough buckets in flight to fill 148 SMs.
+template <class C>
+static MsmPlan make_plan(size_t n) {
+    MsmPlan best{};
+    double best_cost = 1e300;
+    for (int c = 4; c <= 20; c++) {
+        int windows = (C::SCALAR_BITS + 1 + c - 1) / c;
+        double nb = (double)(1u << (c - 1));
+        // 10.5 ~ mixed add, 2*14 running-sum adds + ~20 for the segment scalar-mul / tree share
+        double cost = windows * ((double)n * 10.5 + nb * 48.0);
+        // starve penalty: fewer bucket-threads than the machine holds means idle SMs
+        double threads = windows * nb;
+        if (threads < 148.0 * 384.0) cost *= 1.0 + 0.35 * (148.0 * 384.0 / threads - 1.0);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best.c = c;
+            best.windows = windows;
+            best.nb = 1u << (c - 1);
+        }
+    }
+    best.n = (uint32_t)n;
+    best.seg_len = best.nb >= 4096 ? 16 : (best.nb >= 64 ? 8 : (int)std::min<uint32_t>(best.nb, 4u));
+    best.segs = best.nb / best.seg_len;
+    return best;
+}
+
+template <class C>
+int msm_device(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
+    using F = typename C::F;
+    using T = CurveTraits<C>;
+    if (n == 0) {
+        Jacobian<F> *o = reinterpret_cast<Jacobian<F> *>(d_out);
+        k_sum_jacobian<F><<<1, 1, 0, st>>>(nullptr, 0, o);
+        LAUNCH_CHECK();
+        return B200_OK;
+    }
+    if (n > (size_t)1 << 26) return fail(B200_ERR_ARG, "n = %zu exceeds the 2^26 per-call limit", n);
+    MsmPlan p = make_plan<C>(n);
+    size_t total = (size_t)p.windows * p.nb;
+    uint32_t tiles = (uint32_t)ceil_div(total, SCAN_TILE);
+    int rc;
+    if ((rc = E.counts.reserve(total * 4)) || (rc = E.offsets.reserve((total + 1) * 4)) ||
+        (rc = E.cursor.reserve(total * 4)) || (rc = E.tile_sums.reserve((size_t)tiles * 4)) ||
+        (rc = E.bins.reserve(2 * SIZE_BINS * 4)) || (rc = E.order.reserve(total * 4)) ||
+        (rc = E.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = E.buckets.reserve(total * sizeof(XYZZ<F>))) ||
+        (rc = E.partials.reserve((size_t)p.windows * p.segs * sizeof(XYZZ<F>))) ||
+        (rc = E.window_sums.reserve((size_t)p.windows * sizeof(XYZZ<F>))))
+        return rc;
+
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+
+    const uint32_t *sc = reinterpret_cast<const uint32_t *>(d_scalars);
+    uint32_t *counts = E.counts.as<uint32_t>(), *offsets = E.offsets.as<uint32_t>(), *cursor = E.cursor.as<uint32_t>();
+    uint32_t *bins = E.bins.as<uint32_t>();
+    CUDA_TRY(cudaMemsetAsync(counts, 0, total * 4, st));
+    CUDA_TRY(cudaMemsetAsync(bins, 0, 2 * SIZE_BINS * 4, st));
+
+    int nblk = ceil_div(n, 256);
+    k_digit_hist<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, counts);
+    LAUNCH_CHECK();
+    k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)total, E.tile_sums.as<uint32_t>());
+    LAUNCH_CHECK();
+    k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(E.tile_sums.as<uint32_t>(), tiles);
+    LAUNCH_CHECK();
+    k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)total, E.tile_sums.as<uint32_t>(), offsets, cursor);
+    LAUNCH_CHECK();
+    k_digit_scatter<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, cursor, E.sorted.as<uint32_t>());
+    LAUNCH_CHECK();
+    k_size_hist<<<std::min(ceil_div(total, 256), E.sm_count * 4), 256, 0, st>>>(counts, (uint32_t)total, bins);
+    LAUNCH_CHECK();
+    k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins, bins + SIZE_BINS);
+    LAUNCH_CHECK();
+    k_size_scatter<<<ceil_div(total, 256), 256, 0, st>>>(counts, (uint32_t)total, bins + SIZE_BINS,
+                                                         E.order.as<uint32_t>());
+    LAUNCH_CHECK();
+
+    bool prof = E.profile && E.prof_used < Engine::PROF_SLOTS;
+    if (prof) CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used], st));
+    k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
+        <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
+            reinterpret_cast<const Affine<F> *>(d_bases), E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(),
+            (uint32_t)total, E.buckets.as<XYZZ<F>>());
+    LAUNCH_CHECK();
+    if (prof) {
+        CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));
+        E.prof_used++;
+        E.prof_units += n;
+    }
+
+    uint32_t red_threads = (uint32_t)p.windows * p.segs;
+    k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
+        E.buckets.as<XYZZ<F>>(), p, E.partials.as<XYZZ<F>>());
+    LAUNCH_CHECK();
+    constexpr int WS_THREADS = 64;
+    size_t ws_smem = WS_THREADS * sizeof(XYZZ<F>);
+    k_window_sum<F, WS_THREADS><<<p.windows, WS_THREADS, ws_smem, st>>>(E.partials.as<XYZZ<F>>(), p,
+                                                                        E.window_sums.as<XYZZ<F>>());
+    LAUNCH_CHECK();
+    k_window_combine<F><<<1, 32, 0, st>>>(E.window_sums.as<XYZZ<F>>(), p, reinterpret_cast<Jacobian<F> *>(d_out));
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaEventRecord(E.done, st));
+    E.has_pending = true;
+    return B200_OK;
+}
+
+template <class C>
+int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st) {
+    using F = typename C::F;
+    k_sum_jacobian<F><<<1, 1, 0, st>>>(reinterpret_cast<const Jacobian<F> *>(pts), (uint32_t)count,
+                                       reinterpret_cast<Jacobian<F> *>(out));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <class C>
+int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st) {
+    using F = typename C::F;
+    if (n == 0) return B200_OK;
+    int rc = E.buckets.reserve(n * sizeof(XYZZ<F>));
+    if (rc) return rc;
+    constexpr int TH = 64;
+    k_fixed_base_mul<F, C::SCALAR_WORDS, TH><<<ceil_div(n, TH), TH, 0, st>>>(
+        reinterpret_cast<const Affine<F> *>(base), reinterpret_cast<const uint32_t *>(scalars), (uint32_t)n,
+        E.buckets.as<XYZZ<F>>());
+    LAUNCH_CHECK();
+    k_xyzz_to_affine<F, TH><<<ceil_div(n, TH), TH, 0, st>>>(E.buckets.as<XYZZ<F>>(), (uint32_t)n,
+                                                            reinterpret_cast<Affine<F> *>(out));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <class C>
+int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st) {
+    using F = typename C::F;
+    if (n == 0) return B200_OK;
+    constexpr int TH = 64, BATCH = 8;
+    k_jacobian_to_affine<F, TH, BATCH><<<ceil_div(ceil_div(n, BATCH), TH), TH, 0, st>>>(
+        reinterpret_cast<const Jacobian<F> *>(jac), (uint32_t)n, reinterpret_cast<Affine<F> *>(out));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <class C>
+int plan_query(size_t n, int *c, int *w, uint32_t *nb) {
+    MsmPlan p = make_plan<C>(n);
+    if (c) *c = p.c;
+    if (w) *w = p.windows;
+    if (nb) *nb = p.nb;
+    return B200_OK;
+}
+
+
+template <class C>
+int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStream_t st) {
+    using F = typename C::F;
+    if (n == 0) return B200_OK;
+    k_field_op<F><<<ceil_div(n, 64), 64, 0, st>>>(op, reinterpret_cast<const F *>(a), reinterpret_cast<const F *>(b),
+                                                  (uint32_t)n, reinterpret_cast<F *>(out));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+#define B200_INSTANTIATE(C)                                                                                       \
+    template int msm_device<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);               \
+    template int sum_jacobian<C>(const void *, size_t, void *, cudaStream_t);                                     \
+    template int fixed_base_mul<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);           \
+    template int batch_to_affine<C>(const void *, size_t, void *, cudaStream_t);                                  \
+    template int plan_query<C>(size_t, int *, int *, uint32_t *);                                                 \
+    template int field_op<C>(int, const void *, const void *, size_t, void *, cudaStream_t);
+
+}  // namespace b200

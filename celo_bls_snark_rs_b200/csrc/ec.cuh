@@ -1,0 +1,211 @@
+// Short-Weierstrass group law (a = 0: BLS12-377 G1/G2, BW6-761 G1/G2) for sm_100a.
+//
+// Device replacement for ark-ec 0.1.0 short_weierstrass_jacobian as used by
+// VariableBaseMSM (crates/bls-crypto/src/bls/signature.rs:85, public.rs:61).
+// Buckets are kept in extended Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ,
+// ZZ^3 = ZZZ^2): the mixed addition is 8M + 2S against 7M + 4S for Jacobian and has
+// no field doubling chains.  The tail (window combine) and everything that crosses
+// the C-ABI is plain Jacobian (X/Z^2, Y/Z^3), arkworks' GroupProjective.
+// All exceptional cases (infinity operands, P + P, P + (-P)) are handled exactly:
+// duplicate bases are the common case for this caller, not a corner case
+// (crates/epoch-snark/src/api/prover.rs:154-157 pads with the generator).
+#pragma once
+#include "fp.cuh"
+
+namespace b200 {
+
+// everything except the mixed add of the accumulate kernel is off the hot path: out of line
+#define B200_COLD __device__ __noinline__
+
+// ---------------- Fq2 = Fq[u] / (u^2 + 5) over BLS12-377 Fq -------------------------
+template <class B>
+struct Fp2 {
+    B c0, c1;
+    B200_DEV static Fp2 zero() { return {B::zero(), B::zero()}; }
+    B200_DEV static Fp2 one() { return {B::one(), B::zero()}; }
+    B200_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    B200_DEV bool operator==(const Fp2 &o) const { return c0 == o.c0 && c1 == o.c1; }
+    B200_DEV friend Fp2 operator+(const Fp2 &a, const Fp2 &b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
+    B200_DEV friend Fp2 operator-(const Fp2 &a, const Fp2 &b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
+    B200_DEV Fp2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+    B200_DEV Fp2 neg() const { return {c0.neg(), c1.neg()}; }
+    B200_DEV Fp2 cneg(bool f) const { return {c0.cneg(f), c1.cneg(f)}; }
+    B200_DEV static B mul5(const B &a) {
+        B t = a.dbl().dbl();
+        return t + a;
+    }
+    // Karatsuba: 3 base multiplications; u^2 = -5.  Out of line (one shared body of ~1.2k
+    // instructions per product, like the 24-limb field) to bound code size.
+    __device__ __noinline__ static Fp2 mul_outline(Fp2 a, Fp2 b) {
+        B v0 = a.c0 * b.c0;
+        B v1 = a.c1 * b.c1;
+        B t = (a.c0 + a.c1) * (b.c0 + b.c1);
+        return {v0 - mul5(v1), t - v0 - v1};
+    }
+    // (a0 + a1 u)^2 = a0^2 - 5 a1^2 + 2 a0 a1 u
+    __device__ __noinline__ static Fp2 sqr_outline(Fp2 a) {
+        B v0 = a.c0.sqr();
+        B v1 = a.c1.sqr();
+        B t = a.c0 * a.c1;
+        return {v0 - mul5(v1), t.dbl()};
+    }
+    // (arguments by value: see the note at Fp::mul_outline)
+    B200_DEV friend Fp2 operator*(const Fp2 &a, const Fp2 &b) { return mul_outline(a, b); }
+    B200_DEV Fp2 sqr() const { return sqr_outline(*this); }
+};
+
+// ---------------- points --------------------------------------------------------------
+template <class F>
+struct alignas(16) Affine {                                     // finite point; (0, 0) encodes infinity
+    F x, y;
+    B200_DEV bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+
+template <class F>
+struct alignas(16) Jacobian {
+    F x, y, z;
+    B200_DEV static Jacobian inf() { return {F::one(), F::one(), F::zero()}; }
+    B200_DEV bool is_inf() const { return z.is_zero(); }
+
+    // Out-of-line bodies take and return points BY VALUE (see the note at Fp::mul_outline).
+    // dbl-2009-l (2M + 5S)
+    B200_COLD static Jacobian dbl_outline(Jacobian p) {
+        if (p.is_inf()) return p;
+        F a = p.x.sqr();
+        F b = p.y.sqr();
+        F c = b.sqr();
+        F d = ((p.x + b).sqr() - a - c).dbl();
+        F e = a.dbl() + a;
+        F f = e.sqr();
+        Jacobian r;
+        r.z = (p.z * p.y).dbl();
+        r.x = f - d.dbl();
+        r.y = e * (d - r.x) - c.dbl().dbl().dbl();
+        return r;
+    }
+    B200_DEV void dbl() { *this = dbl_outline(*this); }
+    // add-2007-bl (11M + 5S)
+    B200_COLD static Jacobian add_outline(Jacobian p, Jacobian q) {
+        if (q.is_inf()) return p;
+        if (p.is_inf()) return q;
+        F z1z1 = p.z.sqr();
+        F z2z2 = q.z.sqr();
+        F u1 = p.x * z2z2;
+        F u2 = q.x * z1z1;
+        F s1 = p.y * q.z * z2z2;
+        F s2 = q.y * p.z * z1z1;
+        if (u1 == u2) {
+            if (s1 == s2) return dbl_outline(p);
+            return inf();
+        }
+        F h = u2 - u1;
+        F i = h.dbl().sqr();
+        F j = h * i;
+        F r = (s2 - s1).dbl();
+        F v = u1 * i;
+        Jacobian o;
+        o.x = r.sqr() - j - v.dbl();
+        o.y = r * (v - o.x) - (s1 * j).dbl();
+        o.z = ((p.z + q.z).sqr() - z1z1 - z2z2) * h;
+        return o;
+    }
+    B200_DEV void add(const Jacobian &q) { *this = add_outline(*this, q); }
+};
+
+template <class F>
+struct alignas(16) XYZZ {
+    F x, y, zz, zzz;
+    B200_DEV static XYZZ inf() { return {F::zero(), F::zero(), F::zero(), F::zero()}; }
+    B200_DEV bool is_inf() const { return zz.is_zero(); }
+
+    // mdbl-2008-s-1: 2 * (affine point)
+    B200_COLD static XYZZ dbl_affine(F px, F py) {
+        F u = py.dbl();
+        F v = u.sqr();
+        F w = u * v;
+        F s = px * v;
+        F xx = px.sqr();
+        F m = xx.dbl() + xx;
+        XYZZ r;
+        r.x = m.sqr() - s.dbl();
+        r.y = m * (s - r.x) - w * py;
+        r.zz = v;
+        r.zzz = w;
+        return r;
+    }
+    // dbl-2008-s-1
+    B200_COLD static XYZZ dbl_outline(XYZZ p) {
+        if (p.is_inf()) return p;
+        F u = p.y.dbl();
+        F v = u.sqr();
+        F w = u * v;
+        F s = p.x * v;
+        F xx = p.x.sqr();
+        F m = xx.dbl() + xx;
+        XYZZ r;
+        r.x = m.sqr() - s.dbl();
+        r.y = m * (s - r.x) - w * p.y;
+        r.zz = v * p.zz;
+        r.zzz = w * p.zzz;
+        return r;
+    }
+    B200_DEV void dbl() { *this = dbl_outline(*this); }
+    // madd-2008-s (8M + 2S): this += (px, py), a finite affine point
+    B200_DEV void madd(const F &px, const F &py) {
+        if (is_inf()) {
+            x = px;
+            y = py;
+            zz = F::one();
+            zzz = F::one();
+            return;
+        }
+        F p = px * zz - x;
+        F r = py * zzz - y;
+        if (p.is_zero()) {
+            if (r.is_zero()) *this = dbl_affine(px, py);   // P + P
+            else *this = inf();                            // P + (-P)
+            return;
+        }
+        F pp = p.sqr();
+        F ppp = p * pp;
+        F q = x * pp;
+        F x3 = r.sqr() - ppp - q.dbl();
+        y = r * (q - x3) - y * ppp;
+        x = x3;
+        zz = zz * pp;
+        zzz = zzz * ppp;
+    }
+    // add-2008-s (12M + 2S)
+    B200_COLD static XYZZ add_outline(XYZZ a, XYZZ o) {
+        if (o.is_inf()) return a;
+        if (a.is_inf()) return o;
+        F u1 = a.x * o.zz;
+        F u2 = o.x * a.zz;
+        F s1 = a.y * o.zzz;
+        F s2 = o.y * a.zzz;
+        F p = u2 - u1;
+        F r = s2 - s1;
+        if (p.is_zero()) {
+            if (r.is_zero()) return dbl_outline(a);
+            return inf();
+        }
+        F pp = p.sqr();
+        F ppp = p * pp;
+        F q = u1 * pp;
+        XYZZ t;
+        t.x = r.sqr() - ppp - q.dbl();
+        t.y = r * (q - t.x) - s1 * ppp;
+        t.zz = a.zz * o.zz * pp;
+        t.zzz = a.zzz * o.zzz * ppp;
+        return t;
+    }
+    B200_DEV void add(const XYZZ &o) { *this = add_outline(*this, o); }
+    // (X, Y, ZZ, ZZZ) -> Jacobian (X*ZZ, Y*ZZZ, ZZ)
+    B200_COLD static Jacobian<F> to_jacobian_outline(XYZZ p) {
+        if (p.is_inf()) return Jacobian<F>::inf();
+        return {p.x * p.zz, p.y * p.zzz, p.zz};
+    }
+    B200_DEV Jacobian<F> to_jacobian() const { return to_jacobian_outline(*this); }
+};
+
+}  // namespace b200

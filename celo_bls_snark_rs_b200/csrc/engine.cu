@@ -1,0 +1,259 @@
+// The extern "C" surface declared in include/b200_bls.h.
+// No CPU compute path exists in this library: every entry point either launches the CUDA
+// kernels of msm.cuh or returns an error.
+#include "engine.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static Engine *g_engine = nullptr;
+static std::mutex g_engine_mu;
+
+struct CurveInfo {
+    size_t coord_bytes;   // one coordinate
+    size_t scalar_bytes;
+    size_t jac_bytes;
+};
+static bool curve_info(int curve, CurveInfo &ci) {
+    switch (curve) {
+    case B200_BLS12_377_G1: ci = {48, 32, 144}; return true;
+    case B200_BLS12_377_G2: ci = {96, 32, 288}; return true;
+    case B200_BW6_761_G1:
+    case B200_BW6_761_G2: ci = {96, 48, 288}; return true;
+    default: return false;
+    }
+}
+
+#define DISPATCH_CURVE(curve, FN, ...)                                                     \
+    ((curve) == B200_BLS12_377_G1   ? FN<G1_377>(__VA_ARGS__)                              \
+     : (curve) == B200_BLS12_377_G2 ? FN<G2_377>(__VA_ARGS__)                              \
+                                    : FN<G_761>(__VA_ARGS__))
+
+static int pack_bases(Engine &E, const void *src_dev, size_t stride, size_t n, const CurveInfo &ci, void *dst,
+                      cudaStream_t st) {
+    if (n == 0) return B200_OK;
+    size_t xy = 2 * ci.coord_bytes;
+    if (stride % 8 || stride < xy) return fail(B200_ERR_ARG, "bad base stride %zu", stride);
+    k_pack_bases<<<ceil_div(n, 256), 256, 0, st>>>(reinterpret_cast<const uint64_t *>(src_dev), (uint32_t)n,
+                                                   (uint32_t)(stride / 8), (uint32_t)(xy / 8), stride > xy ? 1 : 0,
+                                                   reinterpret_cast<uint64_t *>(dst));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char *b200_last_error(void) { return g_err.c_str(); }
+uint64_t b200_launch_count(void) { return g_launches.load(); }
+
+int b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B200_ERR_CUDA, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) return fail(B200_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    if (g_engine && g_engine->device == device) return B200_OK;
+    if (g_engine) return fail(B200_ERR_STATE, "engine already bound to device %d; call b200_shutdown first", g_engine->device);
+    CUDA_TRY(cudaSetDevice(device));
+    Engine *E = new Engine();
+    E->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete E;
+        return fail(B200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+    E->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&E->done, cudaEventDisableTiming));
+    g_engine = E;
+    return B200_OK;
+}
+
+void b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    if (!g_engine) return;
+    Engine *E = g_engine;
+    cudaSetDevice(E->device);
+    cudaStreamSynchronize(E->stream);
+    for (Buffer *b : {&E->counts, &E->offsets, &E->cursor, &E->tile_sums, &E->bins, &E->order, &E->sorted, &E->buckets,
+                      &E->partials, &E->window_sums, &E->h2d_bases, &E->packed_bases, &E->scalars, &E->result})
+        b->release();
+    for (auto &ev : E->prof_ev)
+        if (ev) cudaEventDestroy(ev);
+    cudaEventDestroy(E->done);
+    cudaStreamDestroy(E->stream);
+    delete E;
+    g_engine = nullptr;
+}
+
+#define REQUIRE_ENGINE()                                                              \
+    Engine *Ep = g_engine;                                                            \
+    if (!Ep) return fail(B200_ERR_STATE, "b200_init has not been called");            \
+    Engine &E = *Ep;                                                                  \
+    std::lock_guard<std::mutex> lk(E.mu);                                             \
+    CUDA_TRY(cudaSetDevice(E.device))
+
+int b200_msm_device(int curve, const void *d_bases_packed, const void *d_scalars, size_t n, void *d_out_jacobian,
+                    void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!d_out_jacobian || (n && (!d_bases_packed || !d_scalars))) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    return DISPATCH_CURVE(curve, msm_device, E, d_bases_packed, d_scalars, n, d_out_jacobian, st);
+}
+
+int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, int src_on_device, void *d_dst_packed,
+                           void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n && (!src || !d_dst_packed)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    const void *dsrc = src;
+    if (!src_on_device && n) {
+        int rc = E.h2d_bases.reserve(n * stride);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, src, n * stride, cudaMemcpyHostToDevice, st));
+        dsrc = E.h2d_bases.p;
+    }
+    return pack_bases(E, dsrc, stride, n, ci, d_dst_packed, st);
+}
+
+int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out_jacobian || (n && (!bases || !scalars))) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = E.stream;
+    int rc;
+    if ((rc = E.result.reserve(ci.jac_bytes))) return rc;
+    if (n) {
+        size_t xy = 2 * ci.coord_bytes;
+        if ((rc = E.scalars.reserve(n * ci.scalar_bytes)) || (rc = E.packed_bases.reserve(n * xy))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(E.scalars.p, scalars, n * ci.scalar_bytes, cudaMemcpyHostToDevice, st));
+        if (stride == xy) {
+            CUDA_TRY(cudaMemcpyAsync(E.packed_bases.p, bases, n * xy, cudaMemcpyHostToDevice, st));
+        } else {
+            if ((rc = E.h2d_bases.reserve(n * stride))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bases, n * stride, cudaMemcpyHostToDevice, st));
+            if ((rc = pack_bases(E, E.h2d_bases.p, stride, n, ci, E.packed_bases.p, st))) return rc;
+        }
+    }
+    rc = DISPATCH_CURVE(curve, msm_device, E, E.packed_bases.p, E.scalars.p, n, E.result.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_jacobian, E.result.p, ci.jac_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_msm_bls12_377_g1(const void *b, const uint64_t *s, size_t n, void *o) { return b200_msm(B200_BLS12_377_G1, b, 104, s, n, o); }
+int b200_msm_bls12_377_g2(const void *b, const uint64_t *s, size_t n, void *o) { return b200_msm(B200_BLS12_377_G2, b, 200, s, n, o); }
+int b200_msm_bw6_761_g1(const void *b, const uint64_t *s, size_t n, void *o) { return b200_msm(B200_BW6_761_G1, b, 200, s, n, o); }
+int b200_msm_bw6_761_g2(const void *b, const uint64_t *s, size_t n, void *o) { return b200_msm(B200_BW6_761_G2, b, 200, s, n, o); }
+
+int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void *d_out, void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!d_out || (count && !d_points)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    return DISPATCH_CURVE(curve, sum_jacobian, d_points, count, d_out, st);
+}
+
+int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void *d_scalars, size_t n,
+                               void *d_out_packed, void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n && (!d_base_packed || !d_scalars || !d_out_packed)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    int rc = DISPATCH_CURVE(curve, fixed_base_mul, E, d_base_packed, d_scalars, n, d_out_packed, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(E.done, st));
+    E.has_pending = true;
+    return B200_OK;
+}
+
+int b200_batch_to_affine_device(int curve, const void *d_jacobian, size_t n, void *d_out_packed, void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (n && (!d_jacobian || !d_out_packed)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    return DISPATCH_CURVE(curve, batch_to_affine, d_jacobian, n, d_out_packed, st);
+}
+
+int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (op < 0 || op > 6) return fail(B200_ERR_ARG, "unknown field op %d", op);
+    if (n && (!d_a || !d_b || !d_out)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    return DISPATCH_CURVE(curve, field_op, op, d_a, d_b, n, d_out, st);
+}
+
+int b200_profile_enable(int on) {
+    REQUIRE_ENGINE();
+    if (on && !E.prof_ev[0])
+        for (auto &ev : E.prof_ev) CUDA_TRY(cudaEventCreate(&ev));
+    E.profile = on != 0;
+    E.prof_used = 0;
+    E.prof_units = 0;
+    return B200_OK;
+}
+
+int b200_profile_read(double *accumulate_ms, int *launches, uint64_t *pairs) {
+    REQUIRE_ENGINE();
+    double ms = 0;
+    for (int i = 0; i < E.prof_used; i++) {
+        CUDA_TRY(cudaEventSynchronize(E.prof_ev[2 * i + 1]));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, E.prof_ev[2 * i], E.prof_ev[2 * i + 1]));
+        ms += t;
+    }
+    if (accumulate_ms) *accumulate_ms = ms;
+    if (launches) *launches = E.prof_used;
+    if (pairs) *pairs = E.prof_units;
+    E.prof_used = 0;
+    E.prof_units = 0;
+    return B200_OK;
+}
+
+int b200_sync(void *stream) {
+    Engine *Ep = g_engine;
+    if (!Ep) return fail(B200_ERR_STATE, "b200_init has not been called");
+    CUDA_TRY(cudaSetDevice(Ep->device));
+    CUDA_TRY(cudaStreamSynchronize(stream ? (cudaStream_t)stream : Ep->stream));
+    return B200_OK;
+}
+
+int b200_msm_plan(int curve, size_t n, int *window_bits, int *windows, uint32_t *buckets_per_window) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    return DISPATCH_CURVE(curve, plan_query, n, window_bits, windows, buckets_per_window);
+}
+
+}  // extern "C"

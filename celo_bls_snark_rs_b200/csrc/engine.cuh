@@ -1,0 +1,84 @@
+// Shared host-side declarations of the engine (see engine.cu for the C-ABI).
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/b200_bls.h"
+#include "msm.cuh"
+
+namespace b200 {
+
+int fail(int code, const char *fmt, ...);
+void count_launch();
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) return fail(B200_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));      \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                                   \
+    do {                                                                                                 \
+        count_launch();                                                                                  \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess) return fail(B200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e_));  \
+    } while (0)
+
+struct Buffer {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4;
+        CUDA_TRY(cudaMalloc(&p, want));
+        cap = want;
+        return B200_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Engine {
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;      // completion of the last MSM (orders workspace reuse across streams)
+    bool has_pending = false;
+    std::mutex mu;
+    // workspace (grow-only)
+    Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums;
+    // staging for the host-pointer API
+    Buffer h2d_bases, packed_bases, scalars, result;
+    // optional timing of the dominant kernel (b200_profile_*): event pairs around k_bucket_accumulate
+    bool profile = false;
+    static constexpr int PROF_SLOTS = 256;
+    cudaEvent_t prof_ev[2 * PROF_SLOTS] = {};
+    int prof_used = 0;
+    uint64_t prof_units = 0;         // scalar-point pairs covered by the recorded launches
+};
+
+
+
+inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
+
+// per-curve entry points; each is instantiated in its own translation unit (inst_*.cu)
+template <class C> int msm_device(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
+template <class C> int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st);
+template <class C> int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st);
+template <class C> int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st);
+template <class C> int plan_query(size_t n, int *c, int *w, uint32_t *nb);
+template <class C> int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,231 @@
+// Prime-field arithmetic for sm_100a: Montgomery residues on 32-bit limbs held in
+// registers, carry chains written as PTX mad.lo.cc / madc.hi.cc pairs that ptxas
+// fuses into IMAD.WIDE.U32 with predicate carries.
+//
+// Replaces (on the device) ark-ff 0.1.0 Fp384 / Fp768 as reached from
+// crates/bls-crypto/src/bls/signature.rs:85 and public.rs:61; the memory format is
+// arkworks' own (Montgomery, R = 2^384 / 2^768, little-endian limbs) so device
+// buffers are bit-compatible with what the Rust side holds.
+//
+// Multiplication is a row-interleaved (CIOS-style) Montgomery product with the
+// partial products split into an "even" and an "odd" accumulator (each N limbs,
+// the odd one offset by one limb).  A wide product a[j]*b lands on limbs (j, j+1),
+// so products of even j chain through one accumulator without overlapping and
+// products of odd j through the other.  Dividing by 2^32 after each row is free:
+// the two accumulators swap roles (see mont_row()).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "params_gen.cuh"
+
+namespace b200 {
+
+#define B200_DEV __device__ __forceinline__
+
+// ---- carry-chain primitives (all volatile: the CC flag links consecutive asm statements) ----
+B200_DEV void add_cc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+B200_DEV void addc_cc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+B200_DEV void addc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+B200_DEV void sub_cc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+B200_DEV void subc_cc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+B200_DEV void subc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
+
+// (lo, hi) = a * b
+B200_DEV void mul_wide(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// (lo, hi) += a * b, starting a chain (carry out in CC)
+B200_DEV void mad_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (lo, hi) += a * b + CC, continuing a chain
+B200_DEV void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (lo, hi) = a * b + (c_lo, c_hi) + CC, continuing a chain
+B200_DEV void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b, uint32_t c_lo, uint32_t c_hi) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                 : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(c_lo), "r"(c_hi));
+}
+// top of the shifted chain: (lo, hi) = a * b + CC ; hi cannot overflow
+B200_DEV void madc_wide_top(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+
+template <class P>
+struct Fp {
+    static constexpr int N = P::N;
+    uint32_t l[N];
+
+    B200_DEV static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    B200_DEV static Fp one() {                     // Montgomery form of 1
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    __device__ __noinline__ static uint32_t pm2_word(int w) {   // runtime-indexed p - 2
+        uint32_t r = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) r = (i == w) ? P::pm2(i) : r;
+        return r;
+    }
+    B200_DEV static Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = P::r2(i);
+        return r;
+    }
+    B200_DEV bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= l[i];
+        return o == 0;
+    }
+    B200_DEV bool operator==(const Fp &b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) o |= l[i] ^ b.l[i];
+        return o == 0;
+    }
+
+    // r in [0, 2p) -> [0, p)
+    B200_DEV void reduce_once() {
+        uint32_t t[N], borrow;
+        sub_cc(t[0], l[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) subc_cc(t[i], l[i], P::mod(i));
+        subc(borrow, 0, 0);                        // 0xffffffff iff l < p
+#pragma unroll
+        for (int i = 0; i < N; i++) l[i] = borrow ? l[i] : t[i];
+    }
+
+    B200_DEV friend Fp operator+(const Fp &a, const Fp &b) {
+        Fp r;                                      // a + b < 2p < 2^(32N): no carry out
+        add_cc(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], a.l[i], b.l[i]);
+        addc(r.l[N - 1], a.l[N - 1], b.l[N - 1]);
+        r.reduce_once();
+        return r;
+    }
+    B200_DEV friend Fp operator-(const Fp &a, const Fp &b) {
+        Fp r;
+        uint32_t borrow;
+        sub_cc(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) subc_cc(r.l[i], a.l[i], b.l[i]);
+        subc(borrow, 0, 0);                        // all-ones iff a < b
+        add_cc(r.l[0], r.l[0], P::mod(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], r.l[i], P::mod(i) & borrow);
+        addc(r.l[N - 1], r.l[N - 1], P::mod(N - 1) & borrow);
+        return r;
+    }
+    B200_DEV Fp neg() const { return zero() - *this; }      // 0 - 0 stays 0 (no borrow, no +p)
+    B200_DEV Fp cneg(bool flag) const {            // flag ? -x : x
+        Fp n = neg(), r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = flag ? n.l[i] : l[i];
+        return r;
+    }
+    // a^(p-2) (Fermat); inv(0) = 0.  Cold path: kept out of line and rolled.
+    B200_DEV Fp inv() const { return inv_outline(*this); }
+    __device__ __noinline__ static Fp inv_outline(Fp base) {
+        Fp acc = one();
+#pragma unroll 1
+        for (int w = 0; w < N; w++) {
+            uint32_t e = pm2_word(w);
+#pragma unroll 1
+            for (int b = 0; b < 32; b++) {
+                if ((e >> b) & 1u) acc = acc * base;
+                base = base.sqr();
+            }
+        }
+        return acc;
+    }
+    B200_DEV Fp dbl() const { return *this + *this; }
+
+    // one row of the interleaved product: (even, odd) += a * bi + m * p, then / 2^32 by role swap.
+    // On entry (non-first rows) `even` is the previous row's odd accumulator and `odd` the
+    // previous even one, whose limb 0 is zero: odd >> 64 re-aligns it one limb above `even`,
+    // and its limb 1 is folded into even[0] with the carry entering the odd chain.
+    template <bool FIRST>
+    B200_DEV static void mont_row(uint32_t (&even)[N], uint32_t (&odd)[N], const uint32_t (&a)[N], uint32_t bi) {
+        if (FIRST) {
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                mul_wide(odd[j], odd[j + 1], a[j + 1], bi);
+                mul_wide(even[j], even[j + 1], a[j], bi);
+            }
+        } else {
+            add_cc(even[0], even[0], odd[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) madc_wide_cc(odd[j], odd[j + 1], a[j + 1], bi, odd[j + 2], odd[j + 3]);
+            madc_wide_top(odd[N - 2], odd[N - 1], a[N - 1], bi);
+            mad_wide_cc(even[0], even[1], a[0], bi);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) madc_wide_cc(even[j], even[j + 1], a[j], bi);
+            addc(odd[N - 1], odd[N - 1], 0);
+        }
+        uint32_t m = even[0] * P::INV;
+        mad_wide_cc(odd[0], odd[1], P::mod(1), m);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(odd[j], odd[j + 1], P::mod(j + 1), m);
+        mad_wide_cc(even[0], even[1], P::mod(0), m);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(even[j], even[j + 1], P::mod(j), m);
+        addc(odd[N - 1], odd[N - 1], 0);
+    }
+
+    B200_DEV static Fp mul_inline(const Fp &a, const Fp &b) {
+        uint32_t even[N], odd[N];
+        mont_row<true>(even, odd, a.l, b.l[0]);
+        mont_row<false>(odd, even, a.l, b.l[1]);
+#pragma unroll
+        for (int i = 2; i < N; i += 2) {
+            mont_row<false>(even, odd, a.l, b.l[i]);
+            mont_row<false>(odd, even, a.l, b.l[i + 1]);
+        }
+        // the last row left odd[0] == 0: value = even + (odd >> 32), i.e. r[k] = even[k] + odd[k + 1]
+        Fp r;
+        add_cc(r.l[0], even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], even[i], odd[i + 1]);
+        addc(r.l[N - 1], even[N - 1], 0);
+        r.reduce_once();
+        return r;
+    }
+    // by value on purpose: pointer-taking out-of-line helpers were observed to be miscompiled
+    // (caller passed one stack slot for all three pointers); value semantics cannot alias.
+    __device__ __noinline__ static Fp mul_outline(Fp a, Fp b) { return mul_inline(a, b); }
+    // N = 12 (BLS12-377): fully inlined, ~300 IMAD.WIDE.  N = 24 (BW6-761) is ~1200
+    // instructions per product: one shared out-of-line body keeps code size (and the
+    // instruction cache) sane; the call overhead is ~4% of the body.
+    B200_DEV friend Fp operator*(const Fp &a, const Fp &b) {
+        if constexpr (N <= 12) {
+            return mul_inline(a, b);
+        } else {
+            return mul_outline(a, b);
+        }
+    }
+    B200_DEV Fp sqr() const { return *this * *this; }
+
+    B200_DEV Fp to_mont() const { return *this * r2(); }
+    B200_DEV Fp from_mont() const {
+        Fp o = zero();
+        o.l[0] = 1;
+        return *this * o;
+    }
+};
+
+using Fq377 = Fp<Fq377Params>;
+using Fq761 = Fp<Fq761Params>;
+
+}  // namespace b200

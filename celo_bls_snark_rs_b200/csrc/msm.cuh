@@ -1,0 +1,445 @@
+// Pippenger bucket MSM for sm_100a -- kernels.
+//
+// Device replacement for ark-ec 0.1.0 VariableBaseMSM::multi_scalar_mul as called at
+//   crates/bls-crypto/src/bls/signature.rs:85   (BLS12-377 G1)
+//   crates/bls-crypto/src/bls/public.rs:61      (BLS12-377 G2)
+//   crates/epoch-snark/src/api/prover.rs:78,112 (Groth16 MSMs, BW6-761 / BLS12-377)
+// The result is the same group element; the schedule is B200-first and deliberately
+// not arkworks' (which parallelises over ~17 windows only):
+//
+//   1. k_digit_hist      signed-digit recoding of every scalar (c-bit windows, digits in
+//                        [-2^(c-1), 2^(c-1)]) + per-(window, bucket) histogram
+//   2. k_scan_*          exclusive scan of the histogram -> bucket offsets
+//   3. k_digit_scatter   counting-sort scatter of (point index | sign) by bucket
+//   4. k_size_*          buckets ordered by population so the lanes of a warp run equally long
+//   5. k_bucket_accumulate  one thread per bucket, XYZZ accumulator in registers, affine
+//                        bases gathered from the (L2-resident) packed base array with
+//                        128-bit loads, next point prefetched while the current one is added
+//   6. k_bucket_reduce   segment running sums (sum_b b*B_b) -> one partial per segment
+//   7. k_window_sum      per-window tree sum of the partials
+//   8. k_window_combine  Horner over the windows (c doublings each), Jacobian out
+#pragma once
+#include "ec.cuh"
+
+namespace b200 {
+
+struct G1_377 {
+    using F = Fq377;
+    static constexpr int SCALAR_WORDS = 8;          // 32-bit words per scalar in memory (BigInteger256)
+    static constexpr int SCALAR_BITS = 253;
+};
+struct G2_377 {
+    using F = Fp2<Fq377>;
+    static constexpr int SCALAR_WORDS = 8;
+    static constexpr int SCALAR_BITS = 253;
+};
+struct G_761 {                                      // BW6-761 G1 and G2 (both over Fq, a = 0)
+    using F = Fq761;
+    static constexpr int SCALAR_WORDS = 12;         // BigInteger384
+    static constexpr int SCALAR_BITS = 377;
+};
+
+struct MsmPlan {
+    uint32_t n;
+    int c;                 // window bits
+    int windows;           // ceil((SCALAR_BITS + 1) / c)
+    uint32_t nb;           // buckets per window = 2^(c-1)
+    int seg_len;           // buckets per reduce segment
+    uint32_t segs;         // segments per window = nb / seg_len
+};
+
+// signed window digit of the scalar at s (global memory, canonical little-endian words)
+template <int SW>
+B200_DEV int signed_digit(const uint32_t *__restrict__ s, int w, int c, int &carry) {
+    int start = w * c, k = start >> 5, off = start & 31;
+    uint64_t lo = k < SW ? __ldg(s + k) : 0u;
+    uint64_t hi = k + 1 < SW ? __ldg(s + k + 1) : 0u;
+    int d = (int)((uint32_t)(((hi << 32) | lo) >> off) & ((1u << c) - 1u)) + carry;
+    carry = d > (1 << (c - 1));
+    return carry ? d - (1 << c) : d;
+}
+
+template <int SW>
+__global__ void __launch_bounds__(256) k_digit_hist(const uint32_t *__restrict__ scalars, MsmPlan p,
+                                                    uint32_t *__restrict__ counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint32_t *s = scalars + (size_t)i * SW;
+    int carry = 0;
+    for (int w = 0; w < p.windows; w++) {
+        int d = signed_digit<SW>(s, w, p.c, carry);
+        if (d) atomicAdd(&counts[(size_t)w * p.nb + (uint32_t)(abs(d) - 1)], 1u);
+    }
+}
+
+template <int SW>
+__global__ void __launch_bounds__(256) k_digit_scatter(const uint32_t *__restrict__ scalars, MsmPlan p,
+                                                       uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const uint32_t *s = scalars + (size_t)i * SW;
+    int carry = 0;
+    for (int w = 0; w < p.windows; w++) {
+        int d = signed_digit<SW>(s, w, p.c, carry);
+        if (d) {
+            uint32_t pos = atomicAdd(&cursor[(size_t)w * p.nb + (uint32_t)(abs(d) - 1)], 1u);
+            sorted[pos] = i | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// ---- exclusive scan over `total` counters: 3 phases, SCAN_TILE elements per block --------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+B200_DEV uint32_t block_exclusive_scan(uint32_t v, uint32_t *smem /*[33]*/, uint32_t &block_total) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t ws = lane < nwarps ? smem[lane] : 0u;
+        uint32_t wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        smem[lane] = wi - ws;                       // exclusive warp offsets
+        if (lane == 31) smem[32] = wi;
+    }
+    __syncthreads();
+    uint32_t r = smem[warp] + incl - v;
+    block_total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t *__restrict__ counts, uint32_t total,
+                                                                  uint32_t *__restrict__ tile_sums) {
+    __shared__ uint32_t sm[33];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD, s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) s += base + k < total ? counts[base + k] : 0u;
+    uint32_t tot;
+    block_exclusive_scan(s, sm, tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// single block: in-place exclusive scan of the tile sums (any count)
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(uint32_t *__restrict__ tile_sums, uint32_t tiles) {
+    __shared__ uint32_t sm[33];
+    uint32_t running = 0;
+    for (uint32_t b = 0; b < tiles; b += SCAN_THREADS) {
+        uint32_t i = b + threadIdx.x;
+        uint32_t v = i < tiles ? tile_sums[i] : 0u, tot;
+        uint32_t e = block_exclusive_scan(v, sm, tot);
+        if (i < tiles) tile_sums[i] = running + e;
+        running += tot;
+    }
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t *__restrict__ counts, uint32_t total,
+                                                              const uint32_t *__restrict__ tile_sums,
+                                                              uint32_t *__restrict__ offsets /*[total + 1]*/,
+                                                              uint32_t *__restrict__ cursor /*[total]*/) {
+    __shared__ uint32_t sm[33];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        v[k] = base + k < total ? counts[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t tot;
+    uint32_t e = block_exclusive_scan(s, sm, tot) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        if (base + k < total) {
+            offsets[base + k] = e;
+            cursor[base + k] = e;
+        }
+        e += v[k];
+        if (base + k + 1 == total) offsets[total] = e;
+    }
+}
+
+// ---- order buckets by population (descending) so warps are uniformly loaded ---------------
+constexpr int SIZE_BINS = 1024;
+
+static __global__ void __launch_bounds__(256) k_size_hist(const uint32_t *__restrict__ counts, uint32_t total,
+                                                   uint32_t *__restrict__ bin_counts) {
+    __shared__ uint32_t h[SIZE_BINS];
+    for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        atomicAdd(&h[min(counts[i], (uint32_t)SIZE_BINS - 1)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&bin_counts[i], h[i]);
+}
+
+// one block of SIZE_BINS threads: bin_cursor[b] = number of buckets in strictly larger bins
+static __global__ void __launch_bounds__(SIZE_BINS) k_size_scan(const uint32_t *__restrict__ bin_counts,
+                                                         uint32_t *__restrict__ bin_cursor) {
+    __shared__ uint32_t sm[33];
+    int rev = SIZE_BINS - 1 - threadIdx.x;          // thread 0 owns the largest bin
+    uint32_t tot;
+    uint32_t e = block_exclusive_scan(bin_counts[rev], sm, tot);
+    bin_cursor[rev] = e;
+}
+
+static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__restrict__ counts, uint32_t total,
+                                                      uint32_t *__restrict__ bin_cursor, uint32_t *__restrict__ order) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint32_t bin = min(counts[i], (uint32_t)SIZE_BINS - 1);
+    // warp-aggregated cursor bump: one atomic per distinct bin per warp
+    uint32_t peers = __match_any_sync(__activemask(), bin);
+    int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    order[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+
+// ---- bucket accumulation: the dominant kernel ---------------------------------------------
+template <class F>
+B200_DEV Affine<F> load_affine(const Affine<F> *__restrict__ bases, uint32_t idx) {
+    static_assert(sizeof(Affine<F>) % 16 == 0, "packed affine records are 16-byte multiples");
+    constexpr int V = sizeof(Affine<F>) / 16;
+    Affine<F> r;
+    const uint4 *src = reinterpret_cast<const uint4 *>(bases + idx);
+    uint4 *dst = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+    for (int k = 0; k < V; k++) dst[k] = __ldg(src + k);
+    return r;
+}
+
+template <class F, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+k_bucket_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                    const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
+                    XYZZ<F> *__restrict__ buckets) {
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    if (t >= total_buckets) return;
+    uint32_t id = order[t];
+    uint32_t k = offsets[id], end = offsets[id + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (k < end) {
+        uint32_t e = __ldg(sorted + k);
+        Affine<F> pt = load_affine(bases, e & 0x7fffffffu);
+        for (;;) {
+            ++k;
+            uint32_t e_next = 0;
+            Affine<F> pt_next;
+            bool more = k < end;
+            if (more) {                             // prefetch while the current point is added
+                e_next = __ldg(sorted + k);
+                pt_next = load_affine(bases, e_next & 0x7fffffffu);
+            }
+            if (!pt.is_inf()) acc.madd(pt.x, pt.y.cneg(e >> 31));
+            if (!more) break;
+            e = e_next;
+            pt = pt_next;
+        }
+    }
+    buckets[id] = acc;
+}
+
+// ---- bucket reduction ----------------------------------------------------------------------
+// k * p for small k (double-and-add, MSB first)
+template <class F>
+B200_DEV XYZZ<F> small_mul(const XYZZ<F> &p, uint32_t k) {
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int b = 31 - __clz(k | 1u); b >= 0; b--) {
+        r.dbl();
+        if ((k >> b) & 1u) r.add(p);
+    }
+    return r;
+}
+
+// thread (w, seg): partial = sum_{j < L} (seg*L + j + 1) * B[w][seg*L + j]
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZ<F> *__restrict__ buckets, MsmPlan p,
+                                                           XYZZ<F> *__restrict__ partials) {
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    uint32_t total = (uint32_t)p.windows * p.segs;
+    if (t >= total) return;
+    uint32_t w = t / p.segs, seg = t % p.segs;
+    const XYZZ<F> *b = buckets + (size_t)w * p.nb + (size_t)seg * p.seg_len;
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+    for (int j = p.seg_len - 1; j >= 0; j--) {
+        run.add(b[j]);
+        acc.add(run);
+    }
+    if (seg) acc.add(small_mul(run, seg * (uint32_t)p.seg_len));
+    partials[t] = acc;
+}
+
+// block w: window_sums[w] = sum of the window's partials
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZ<F> *__restrict__ partials, MsmPlan p,
+                                                        XYZZ<F> *__restrict__ window_sums) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smem_raw);
+    const XYZZ<F> *src = partials + (size_t)blockIdx.x * p.segs;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = threadIdx.x; i < p.segs; i += THREADS) acc.add(src[i]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            acc.add(sm[threadIdx.x + s]);
+            sm[threadIdx.x] = acc;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) window_sums[blockIdx.x] = acc;
+}
+
+// one thread: Horner over the windows, high to low
+template <class F>
+__global__ void k_window_combine(const XYZZ<F> *__restrict__ window_sums, MsmPlan p, Jacobian<F> *__restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    Jacobian<F> total = Jacobian<F>::inf();
+    for (int w = p.windows - 1; w >= 0; w--) {
+        total.add(window_sums[w].to_jacobian());
+        if (w)
+            for (int k = 0; k < p.c; k++) total.dbl();
+    }
+    *out = total;
+}
+
+// ---- layout conversion: arkworks GroupAffine records -> packed (x | y), infinity -> (0, 0) ----
+// 8-byte granularity (arkworks records are only 8-byte aligned: 104 / 200 byte stride).
+static __global__ void __launch_bounds__(256) k_pack_bases(const uint64_t *__restrict__ src, uint32_t n, uint32_t stride_words,
+                                                    uint32_t coord_words2 /* words of x|y */, int has_flag,
+                                                    uint64_t *__restrict__ dst) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t *s = src + (size_t)i * stride_words;
+    uint64_t *d = dst + (size_t)i * coord_words2;
+    bool inf = has_flag && (s[coord_words2] & 0xffu);
+    for (uint32_t k = 0; k < coord_words2; k++) d[k] = inf ? 0ull : s[k];
+}
+
+// out = sum of `count` Jacobian points (multi-GPU partial combine; tiny)
+template <class F>
+__global__ void k_sum_jacobian(const Jacobian<F> *__restrict__ pts, uint32_t count, Jacobian<F> *__restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    Jacobian<F> total = Jacobian<F>::inf();
+    for (uint32_t i = 0; i < count; i++) total.add(pts[i]);
+    *out = total;
+}
+
+// out[i] = scalars[i] * base (double-and-add); used to synthesise benchmark / test bases on device
+template <class F, int SW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fixed_base_mul(const Affine<F> *__restrict__ base,
+                                                            const uint32_t *__restrict__ scalars, uint32_t n,
+                                                            XYZZ<F> *__restrict__ out) {
+    uint32_t i = blockIdx.x * THREADS + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> g = load_affine(base, 0);
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int w = SW - 1; w >= 0; w--) {
+        uint32_t word = __ldg(scalars + (size_t)i * SW + w);
+        for (int b = 31; b >= 0; b--) {
+            r.dbl();
+            if ((word >> b) & 1u) r.madd(g.x, g.y);
+        }
+    }
+    out[i] = r;
+}
+
+}  // namespace b200
+
+namespace b200 {
+
+// ---- projective -> affine -------------------------------------------------------------------
+template <class F> struct FieldInv;
+template <class P> struct FieldInv<Fp<P>> {
+    B200_DEV static Fp<P> inv(const Fp<P> &a) { return a.inv(); }
+};
+template <class B> struct FieldInv<Fp2<B>> {
+    // 1/(a0 + a1 u) = (a0 - a1 u) / (a0^2 + 5 a1^2)
+    B200_DEV static Fp2<B> inv(const Fp2<B> &a) {
+        B n = (a.c0.sqr() + Fp2<B>::mul5(a.c1.sqr())).inv();
+        return {a.c0 * n, (a.c1 * n).neg()};
+    }
+};
+
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_xyzz_to_affine(const XYZZ<F> *__restrict__ in, uint32_t n,
+                                                            Affine<F> *__restrict__ out) {
+    uint32_t i = blockIdx.x * THREADS + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> p = in[i];
+    Affine<F> r = {F::zero(), F::zero()};
+    if (!p.is_inf()) {
+        F iv = FieldInv<F>::inv(p.zz * p.zzz);      // 1/ZZ = iv * ZZZ, 1/ZZZ = iv * ZZ
+        r.x = p.x * (iv * p.zzz);
+        r.y = p.y * (iv * p.zz);
+    }
+    out[i] = r;
+}
+
+// One inversion per thread, shared by BATCH consecutive points (Montgomery's trick):
+// the device form of batch_normalization_into_affine (signature.rs:82, public.rs:58).
+template <class F, int THREADS, int BATCH>
+__global__ void __launch_bounds__(THREADS) k_jacobian_to_affine(const Jacobian<F> *__restrict__ in, uint32_t n,
+                                                                Affine<F> *__restrict__ out) {
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    uint32_t first = t * BATCH;
+    if (first >= n) return;
+    uint32_t cnt = min((uint32_t)BATCH, n - first);
+    F prefix[BATCH];                                // prefix[k] = prod of non-zero z[0..k]
+    F run = F::one();
+    for (uint32_t k = 0; k < cnt; k++) {
+        F z = in[first + k].z;
+        if (!z.is_zero()) run = run * z;
+        prefix[k] = run;
+    }
+    F iv = FieldInv<F>::inv(run);
+    for (int k = (int)cnt - 1; k >= 0; k--) {
+        Jacobian<F> p = in[first + k];
+        Affine<F> r = {F::zero(), F::zero()};
+        if (!p.z.is_zero()) {
+            F zi = k ? iv * prefix[k - 1] : iv;      // 1 / z_k
+            iv = iv * p.z;
+            F zi2 = zi.sqr();
+            r.x = p.x * zi2;
+            r.y = p.y * (zi2 * zi);
+        }
+        out[first + k] = r;
+    }
+}
+
+// ---- element-wise field ops (parity tests of the field layer against the oracle) -------------
+enum FieldOp { FOP_ADD = 0, FOP_SUB = 1, FOP_MUL = 2, FOP_SQR = 3, FOP_INV = 4, FOP_NEG = 5, FOP_DBL = 6 };
+
+template <class F>
+__global__ void __launch_bounds__(64) k_field_op(int op, const F *__restrict__ a, const F *__restrict__ b, uint32_t n,
+                                                 F *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = a[i], y = b[i], r;
+    switch (op) {
+    case FOP_ADD: r = x + y; break;
+    case FOP_SUB: r = x - y; break;
+    case FOP_MUL: r = x * y; break;
+    case FOP_SQR: r = x.sqr(); break;
+    case FOP_INV: r = FieldInv<F>::inv(x); break;
+    case FOP_NEG: r = x.neg(); break;
+    default: r = x.dbl(); break;
+    }
+    out[i] = r;
+}
+
+}  // namespace b200

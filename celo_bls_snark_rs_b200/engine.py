@@ -1,0 +1,158 @@
+"""ctypes binding of libb200bls.so (include/b200_bls.h) -- the only compute path.
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is
+usable, every entry point raises.  torch is used by callers for device memory and
+streams only; this module passes raw device pointers across the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200bls.so")
+
+BLS12_377_G1, BLS12_377_G2, BW6_761_G1, BW6_761_G2 = 0, 1, 2, 3
+CURVE_IDS = {"bls12_377_g1": 0, "bls12_377_g2": 1, "bw6_761_g1": 2, "bw6_761_g2": 3}
+
+# bytes of one coordinate / one scalar / one Jacobian point, and the arkworks GroupAffine stride
+COORD_BYTES = {0: 48, 1: 96, 2: 96, 3: 96}
+SCALAR_BYTES = {0: 32, 1: 32, 2: 48, 3: 48}
+JAC_BYTES = {0: 144, 1: 288, 2: 288, 3: 288}
+ARK_STRIDE = {0: 104, 1: 200, 2: 200, 3: 200}
+PACKED_STRIDE = {k: 2 * v for k, v in COORD_BYTES.items()}
+
+EXPORTS = [
+    "b200_init", "b200_shutdown", "b200_last_error", "b200_msm", "b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2",
+    "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device",
+    "b200_sum_jacobian_device", "b200_fixed_base_mul_device", "b200_batch_to_affine_device", "b200_sync",
+    "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
+    "b200_field_op_device",
+]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Loads the CUDA library.  Raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(f"{LIB_PATH} is missing: run `python -m celo_bls_snark_rs_b200.build` (no CPU fallback exists)")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.b200_init.argtypes = [i32]
+    lib.b200_last_error.restype = ctypes.c_char_p
+    lib.b200_msm.argtypes = [i32, vp, sz, vp, sz, vp]
+    for name in ("b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2", "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2"):
+        getattr(lib, name).argtypes = [vp, vp, sz, vp]
+    lib.b200_msm_device.argtypes = [i32, vp, vp, sz, vp, vp]
+    lib.b200_pack_bases_device.argtypes = [i32, vp, sz, sz, i32, vp, vp]
+    lib.b200_sum_jacobian_device.argtypes = [i32, vp, sz, vp, vp]
+    lib.b200_fixed_base_mul_device.argtypes = [i32, vp, vp, sz, vp, vp]
+    lib.b200_batch_to_affine_device.argtypes = [i32, vp, sz, vp, vp]
+    lib.b200_field_op_device.argtypes = [i32, i32, vp, vp, sz, vp, vp]
+    lib.b200_sync.argtypes = [vp]
+    lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
+    lib.b200_launch_count.restype = ctypes.c_uint64
+    lib.b200_profile_enable.argtypes = [i32]
+    lib.b200_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i32),
+                                      ctypes.POINTER(ctypes.c_uint64)]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise B200Error(f"b200 error {rc}: {load().b200_last_error().decode()}")
+
+
+def init(device: int = -1):
+    _check(load().b200_init(device))
+
+
+def shutdown():
+    load().b200_shutdown()
+
+
+def launch_count() -> int:
+    return int(load().b200_launch_count())
+
+
+def msm_plan(curve: int, n: int):
+    c, w, nb = ctypes.c_int(), ctypes.c_int(), ctypes.c_uint32()
+    _check(load().b200_msm_plan(curve, n, ctypes.byref(c), ctypes.byref(w), ctypes.byref(nb)))
+    return c.value, w.value, nb.value
+
+
+def _hptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def msm(curve: int, bases: np.ndarray, scalars: np.ndarray, n: Optional[int] = None) -> bytes:
+    """Host-pointer MSM (b200_msm).  bases: uint8 [n, stride] (arkworks or packed
+    records); scalars: uint64 [n, limbs].  Returns the Jacobian result bytes."""
+    bases = np.ascontiguousarray(bases)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    if n is None:
+        n = min(len(bases), len(scalars))
+    stride = bases.strides[0] if (bases.ndim == 2 and len(bases)) else ARK_STRIDE[curve]
+    out = np.zeros(JAC_BYTES[curve], dtype=np.uint8)
+    _check(load().b200_msm(curve, _hptr(bases), stride, _hptr(scalars), n, _hptr(out)))
+    return out.tobytes()
+
+
+def msm_host_ptrs(curve: int, bases_ptr: int, stride: int, scalars_ptr: int, n: int, out: np.ndarray):
+    """b200_msm on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+    _check(load().b200_msm(curve, bases_ptr, stride, scalars_ptr, n, _hptr(out)))
+
+
+def msm_device(curve: int, d_bases: int, d_scalars: int, n: int, d_out: int, stream: int = 0):
+    _check(load().b200_msm_device(curve, d_bases, d_scalars, n, d_out, stream or None))
+
+
+def pack_bases_device(curve: int, src: int, stride: int, n: int, src_on_device: bool, d_dst: int, stream: int = 0):
+    _check(load().b200_pack_bases_device(curve, src, stride, n, int(src_on_device), d_dst, stream or None))
+
+
+def sum_jacobian_device(curve: int, d_points: int, count: int, d_out: int, stream: int = 0):
+    _check(load().b200_sum_jacobian_device(curve, d_points, count, d_out, stream or None))
+
+
+def fixed_base_mul_device(curve: int, d_base: int, d_scalars: int, n: int, d_out: int, stream: int = 0):
+    _check(load().b200_fixed_base_mul_device(curve, d_base, d_scalars, n, d_out, stream or None))
+
+
+def batch_to_affine_device(curve: int, d_jac: int, n: int, d_out: int, stream: int = 0):
+    _check(load().b200_batch_to_affine_device(curve, d_jac, n, d_out, stream or None))
+
+
+FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5, "dbl": 6}
+
+
+def field_op_device(curve: int, op: str, d_a: int, d_b: int, n: int, d_out: int, stream: int = 0):
+    _check(load().b200_field_op_device(curve, FIELD_OPS[op], d_a, d_b, n, d_out, stream or None))
+
+
+def profile_enable(on: bool = True):
+    _check(load().b200_profile_enable(int(on)))
+
+
+def profile_read():
+    """(summed k_bucket_accumulate ms, launches, scalar-point pairs) since the last read."""
+    ms, k, pairs = ctypes.c_double(), ctypes.c_int(), ctypes.c_uint64()
+    _check(load().b200_profile_read(ctypes.byref(ms), ctypes.byref(k), ctypes.byref(pairs)))
+    return ms.value, k.value, pairs.value
+
+
+def sync(stream: int = 0):
+    _check(load().b200_sync(stream or None))

@@ -1,0 +1,119 @@
+/* b200_bls.h -- C-ABI of the B200-native MSM / multi-pairing engine.
+ *
+ * This is the drop-in seam for the arkworks calls celo-bls-snark-rs makes on its
+ * hot path ("B1 engine seam").  Every entry point names the
+ * reference call it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - return value: 0 = ok; non-zero = error (b200_last_error() has the text).
+ *     Never aborts, never falls back to a CPU path: without a usable CUDA device
+ *     every compute call returns B200_ERR_CUDA.
+ *   - field elements are arkworks' in-memory form: Montgomery residues, 64-bit
+ *     little-endian limbs (Fp384 = 6 limbs, Fp768 = 12 limbs; Fq2 = c0 | c1).
+ *   - scalars are canonical (non-Montgomery) integers, little-endian 64-bit limbs,
+ *     i.e. what PrimeField::into_repr() yields (signature.rs:83, public.rs:59):
+ *     4 limbs for BLS12-377 Fr, 6 limbs for BW6-761 Fr.
+ *   - affine bases are `n` records of `stride` bytes: x | y [| u8 infinity | pad].
+ *     Pass stride = sizeof(GroupAffine<P>) from Rust (104 for BLS12-377 G1, 200 for
+ *     the others); stride == 2 * coordinate bytes means "packed, no flag" and then
+ *     (0, 0) denotes the point at infinity.
+ *   - results are arkworks GroupProjective: Jacobian X | Y | Z (x = X/Z^2,
+ *     y = Y/Z^3, infinity <=> Z == 0), 144 bytes (BLS12-377 G1) or 288 bytes.
+ *     Compare results as group elements / canonical compressed bytes, never as raw
+ *     (X, Y, Z): the representative depends on the order of additions.
+ *   - the caller owns all buffers; nothing is retained after a call returns.
+ *   - thread-safety: calls may come from any host thread; calls on one device
+ *     serialise on an internal mutex (cgo callers use arbitrary threads).
+ */
+#ifndef B200_BLS_H
+#define B200_BLS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B200_BLS12_377_G1 = 0, /* G1Affine / G1Projective, Fq 6 limbs, Fr 4 limbs */
+    B200_BLS12_377_G2 = 1, /* G2Affine / G2Projective, Fq2 coordinates       */
+    B200_BW6_761_G1 = 2,   /* Fq 12 limbs, Fr 6 limbs                         */
+    B200_BW6_761_G2 = 3
+} b200_curve;
+
+enum {
+    B200_OK = 0,
+    B200_ERR_ARG = 1,      /* null pointer, bad curve id, n too large, bad stride */
+    B200_ERR_CUDA = 2,     /* no device / CUDA runtime failure                     */
+    B200_ERR_STATE = 3     /* b200_init not called                                 */
+};
+
+/* Selects the CUDA device this thread's process-wide engine uses (-1: current device)
+ * and creates its stream and workspace.  Idempotent per device.
+ * Reference analogue: bls-snark-sys `init()` (crates/bls-snark-sys/src/lib.rs:29-34). */
+int b200_init(int device);
+void b200_shutdown(void);
+const char *b200_last_error(void);
+
+/* ---- MSM: replaces VariableBaseMSM::multi_scalar_mul ------------------------------
+ * Host-pointer form (copies in, computes on the GPU, copies the 144/288-byte result out).
+ *   crates/bls-crypto/src/bls/signature.rs:85   -> b200_msm_bls12_377_g1
+ *   crates/bls-crypto/src/bls/public.rs:61      -> b200_msm_bls12_377_g2
+ *   crates/epoch-snark/src/api/prover.rs:78     -> b200_msm_bw6_761_g1 / _g2 (via ark-groth16)
+ *   crates/epoch-snark/src/api/prover.rs:112    -> b200_msm_bls12_377_g1 / _g2 (inner proof)
+ * Semantics follow arkworks: min(len) is the caller's job (pass one n), zero scalars
+ * and infinite bases contribute nothing, bases may repeat. */
+int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian);
+int b200_msm_bls12_377_g1(const void *bases_104B, const uint64_t *scalars, size_t n, void *out_144B);
+int b200_msm_bls12_377_g2(const void *bases_200B, const uint64_t *scalars, size_t n, void *out_288B);
+int b200_msm_bw6_761_g1(const void *bases_200B, const uint64_t *scalars, size_t n, void *out_288B);
+int b200_msm_bw6_761_g2(const void *bases_200B, const uint64_t *scalars, size_t n, void *out_288B);
+
+/* Device-pointer form: everything already resident in HBM, asynchronous on `stream`
+ * (a cudaStream_t; NULL = the engine's own stream).  d_bases_packed is the packed
+ * layout (x | y, 16-byte aligned, no flag).  d_out_jacobian receives the result. */
+int b200_msm_device(int curve, const void *d_bases_packed, const void *d_scalars, size_t n, void *d_out_jacobian,
+                    void *stream);
+
+/* arkworks-layout records (host or device memory) -> packed device records.
+ * `src_on_device` != 0: d/h pointer is device memory. */
+int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, int src_on_device, void *d_dst_packed,
+                           void *stream);
+
+/* out = sum of `count` Jacobian points (device pointers).  Used to combine per-GPU
+ * partial MSM results after the all-gather. */
+int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void *d_out_jacobian, void *stream);
+
+/* d_out_packed[i] = scalars[i] * base, as packed affine records (device pointers;
+ * base is one packed affine record).  Synthesises benchmark / test bases on the GPU. */
+int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void *d_scalars, size_t n,
+                               void *d_out_packed, void *stream);
+
+/* Jacobian -> affine with Montgomery batch inversion; replaces
+ * ProjectiveCurve::batch_normalization_into_affine (signature.rs:82, public.rs:58).
+ * d_out_packed receives packed affine records, infinity as (0, 0). */
+int b200_batch_to_affine_device(int curve, const void *d_jacobian, size_t n, void *d_out_packed, void *stream);
+
+/* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
+ * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),
+ * 6 double(a).  Exists so the field layer can be checked against the oracle directly. */
+int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream);
+
+/* Blocks until everything queued on the engine's stream (or `stream`) has finished. */
+int b200_sync(void *stream);
+
+/* Introspection for tests and bench: the window plan the engine picks for n. */
+int b200_msm_plan(int curve, size_t n, int *window_bits, int *windows, uint32_t *buckets_per_window);
+/* Timing of the dominant kernel (bucket accumulation) with CUDA events on the launching
+ * stream: enable, run MSMs, then read the summed duration, launch count and pairs covered
+ * (resets the counters; at most 256 launches are recorded between reads). */
+int b200_profile_enable(int on);
+int b200_profile_read(double *accumulate_ms, int *launches, uint64_t *pairs);
+/* Number of kernel launches the engine has issued since b200_init. */
+uint64_t b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_BLS_H */

@@ -1,0 +1,57 @@
+"""CPU-only checks of the drop-in boundary: the library loads and exports every symbol
+include/b200_bls.h declares; without a GPU compute calls fail loudly (no fallback)."""
+import os
+import re
+
+import pytest
+
+from celo_bls_snark_rs_b200 import engine as E
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b200_bls.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = E.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(E.EXPORTS) == syms
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(E.B200Error):
+        E.init(0)
+    lib = E.load()
+    assert lib.b200_msm(0, None, 104, None, 0, None) != 0
+
+
+def test_product_never_imports_the_oracle():
+    """The product path may not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "celo_bls_snark_rs_b200")
+    banned = re.compile(r"(import\s+oracle|from\s+oracle|from\s+\.\.?oracle|oracle/|cpu_ref|libcpu_ref|cref)")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not banned.search(text), f
+    # and the shared library has no dependency on the C oracle
+    import subprocess
+    out = subprocess.run(["ldd", E.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cpu_ref" not in out
+
+
+def test_plan_is_sane():
+    c, w, nb = E.msm_plan(E.BLS12_377_G1, 1 << 20)
+    assert nb == 1 << (c - 1) and w * c >= 254
+    c, w, nb = E.msm_plan(E.BW6_761_G1, 1 << 22)
+    assert w * c >= 378
