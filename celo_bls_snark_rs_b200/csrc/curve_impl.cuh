@@ -36,13 +36,28 @@ static MsmPlan make_plan(size_t n) {
     return best;
 }
 
+// arkworks records (device memory) -> native packed images
 template <class C>
-int msm_device(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
+int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStream_t st) {
+    using F = typename C::F;
+    if (n == 0) return B200_OK;
+    constexpr size_t XY = sizeof(AffineMem<F>);
+    if (stride % 4 || stride < XY) return fail(B200_ERR_ARG, "bad base stride %zu", stride);
+    constexpr int TH = 128;
+    k_pack_bases<F, TH><<<ceil_div(n, TH), TH, 0, st>>>(reinterpret_cast<const uint32_t *>(src_dev), (uint32_t)n,
+                                                        (uint32_t)(stride / 4), stride > XY ? 1 : 0,
+                                                        reinterpret_cast<AffineMem<F> *>(dst));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// d_bases: native packed images (pack_bases output); d_out: arkworks GroupProjective image
+template <class C>
+int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
     using F = typename C::F;
     using T = CurveTraits<C>;
     if (n == 0) {
-        Jacobian<F> *o = reinterpret_cast<Jacobian<F> *>(d_out);
-        k_sum_jacobian<F><<<1, 1, 0, st>>>(nullptr, 0, o);
+        k_sum_jacobian<F><<<1, 1, 0, st>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(d_out));
         LAUNCH_CHECK();
         return B200_OK;
     }
@@ -54,9 +69,9 @@ int msm_device(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     if ((rc = E.counts.reserve(total * 4)) || (rc = E.offsets.reserve((total + 1) * 4)) ||
         (rc = E.cursor.reserve(total * 4)) || (rc = E.tile_sums.reserve((size_t)tiles * 4)) ||
         (rc = E.bins.reserve(2 * SIZE_BINS * 4)) || (rc = E.order.reserve(total * 4)) ||
-        (rc = E.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = E.buckets.reserve(total * sizeof(XYZZ<F>))) ||
-        (rc = E.partials.reserve((size_t)p.windows * p.segs * sizeof(XYZZ<F>))) ||
-        (rc = E.window_sums.reserve((size_t)p.windows * sizeof(XYZZ<F>))))
+        (rc = E.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = E.buckets.reserve(total * sizeof(XYZZMem<F>))) ||
+        (rc = E.partials.reserve((size_t)p.windows * p.segs * sizeof(XYZZMem<F>))) ||
+        (rc = E.window_sums.reserve((size_t)p.windows * sizeof(XYZZMem<F>))))
         return rc;
 
     if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
@@ -90,8 +105,8 @@ int msm_device(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     if (prof) CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used], st));
     k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
         <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
-            reinterpret_cast<const Affine<F> *>(d_bases), E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(),
-            (uint32_t)total, E.buckets.as<XYZZ<F>>());
+            reinterpret_cast<const AffineMem<F> *>(d_bases), E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(),
+            (uint32_t)total, E.buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     if (prof) {
         CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));
@@ -101,25 +116,40 @@ int msm_device(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
 
     uint32_t red_threads = (uint32_t)p.windows * p.segs;
     k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
-        E.buckets.as<XYZZ<F>>(), p, E.partials.as<XYZZ<F>>());
+        E.buckets.as<XYZZMem<F>>(), p, E.partials.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     constexpr int WS_THREADS = 64;
-    size_t ws_smem = WS_THREADS * sizeof(XYZZ<F>);
-    k_window_sum<F, WS_THREADS><<<p.windows, WS_THREADS, ws_smem, st>>>(E.partials.as<XYZZ<F>>(), p,
-                                                                        E.window_sums.as<XYZZ<F>>());
+    size_t ws_smem = WS_THREADS * sizeof(XYZZMem<F>);
+    k_window_sum<F, WS_THREADS><<<p.windows, WS_THREADS, ws_smem, st>>>(E.partials.as<XYZZMem<F>>(), p,
+                                                                        E.window_sums.as<XYZZMem<F>>());
     LAUNCH_CHECK();
-    k_window_combine<F><<<1, 32, 0, st>>>(E.window_sums.as<XYZZ<F>>(), p, reinterpret_cast<Jacobian<F> *>(d_out));
+    k_window_combine<F><<<1, 32, 0, st>>>(E.window_sums.as<XYZZMem<F>>(), p,
+                                          reinterpret_cast<JacobianMem<F> *>(d_out));
     LAUNCH_CHECK();
     CUDA_TRY(cudaEventRecord(E.done, st));
     E.has_pending = true;
     return B200_OK;
 }
 
+// d_bases: arkworks-radix records in device memory at `stride` bytes
+template <class C>
+int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scalars, size_t n, void *d_out,
+               cudaStream_t st) {
+    using F = typename C::F;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    // packed records are already the engine's layout (same Montgomery radix as arkworks)
+    if (stride == sizeof(AffineMem<F>)) return msm_native<C>(E, d_bases, d_scalars, n, d_out, st);
+    int rc = E.native_bases.reserve(n * sizeof(AffineMem<F>));
+    if (rc) return rc;
+    if ((rc = pack_bases<C>(d_bases, stride, n, E.native_bases.p, st))) return rc;
+    return msm_native<C>(E, E.native_bases.p, d_scalars, n, d_out, st);
+}
+
 template <class C>
 int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st) {
     using F = typename C::F;
-    k_sum_jacobian<F><<<1, 1, 0, st>>>(reinterpret_cast<const Jacobian<F> *>(pts), (uint32_t)count,
-                                       reinterpret_cast<Jacobian<F> *>(out));
+    k_sum_jacobian<F><<<1, 1, 0, st>>>(reinterpret_cast<const JacobianMem<F> *>(pts), (uint32_t)count,
+                                       reinterpret_cast<JacobianMem<F> *>(out));
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -128,15 +158,15 @@ template <class C>
 int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st) {
     using F = typename C::F;
     if (n == 0) return B200_OK;
-    int rc = E.buckets.reserve(n * sizeof(XYZZ<F>));
+    int rc = E.buckets.reserve(n * sizeof(XYZZMem<F>));
     if (rc) return rc;
     constexpr int TH = 64;
     k_fixed_base_mul<F, C::SCALAR_WORDS, TH><<<ceil_div(n, TH), TH, 0, st>>>(
-        reinterpret_cast<const Affine<F> *>(base), reinterpret_cast<const uint32_t *>(scalars), (uint32_t)n,
-        E.buckets.as<XYZZ<F>>());
+        reinterpret_cast<const AffineMem<F> *>(base), reinterpret_cast<const uint32_t *>(scalars), (uint32_t)n,
+        E.buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
-    k_xyzz_to_affine<F, TH><<<ceil_div(n, TH), TH, 0, st>>>(E.buckets.as<XYZZ<F>>(), (uint32_t)n,
-                                                            reinterpret_cast<Affine<F> *>(out));
+    k_xyzz_to_affine<F, TH><<<ceil_div(n, TH), TH, 0, st>>>(E.buckets.as<XYZZMem<F>>(), (uint32_t)n,
+                                                            reinterpret_cast<AffineMem<F> *>(out));
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -147,7 +177,7 @@ int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st) {
     if (n == 0) return B200_OK;
     constexpr int TH = 64, BATCH = 8;
     k_jacobian_to_affine<F, TH, BATCH><<<ceil_div(ceil_div(n, BATCH), TH), TH, 0, st>>>(
-        reinterpret_cast<const Jacobian<F> *>(jac), (uint32_t)n, reinterpret_cast<Affine<F> *>(out));
+        reinterpret_cast<const JacobianMem<F> *>(jac), (uint32_t)n, reinterpret_cast<AffineMem<F> *>(out));
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -166,14 +196,17 @@ template <class C>
 int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStream_t st) {
     using F = typename C::F;
     if (n == 0) return B200_OK;
-    k_field_op<F><<<ceil_div(n, 64), 64, 0, st>>>(op, reinterpret_cast<const F *>(a), reinterpret_cast<const F *>(b),
-                                                  (uint32_t)n, reinterpret_cast<F *>(out));
+    using M = typename F::Mem;
+    k_field_op<F><<<ceil_div(n, 64), 64, 0, st>>>(op, reinterpret_cast<const M *>(a), reinterpret_cast<const M *>(b),
+                                                  (uint32_t)n, reinterpret_cast<M *>(out));
     LAUNCH_CHECK();
     return B200_OK;
 }
 
 #define B200_INSTANTIATE(C)                                                                                       \
-    template int msm_device<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);               \
+    template int msm_device<C>(Engine &, const void *, size_t, const void *, size_t, void *, cudaStream_t);       \
+    template int pack_bases<C>(const void *, size_t, size_t, void *, cudaStream_t);                               \
+    template int msm_native<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);               \
     template int sum_jacobian<C>(const void *, size_t, void *, cudaStream_t);                                     \
     template int fixed_base_mul<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);           \
     template int batch_to_affine<C>(const void *, size_t, void *, cudaStream_t);                                  \

@@ -21,6 +21,13 @@ namespace b200 {
 template <class B>
 struct Fp2 {
     B c0, c1;
+    struct alignas(16) Mem {
+        typename B::Mem c0, c1;
+    };
+    B200_DEV static Fp2 from_ark(const Mem &m) { return {B::from_ark(m.c0), B::from_ark(m.c1)}; }
+    B200_DEV Mem to_ark() const { return {c0.to_ark(), c1.to_ark()}; }
+    B200_DEV static Fp2 load(const Mem &m) { return {B::load(m.c0), B::load(m.c1)}; }
+    B200_DEV Mem store() const { return {c0.store(), c1.store()}; }
     B200_DEV static Fp2 zero() { return {B::zero(), B::zero()}; }
     B200_DEV static Fp2 one() { return {B::one(), B::zero()}; }
     B200_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
@@ -55,17 +62,53 @@ struct Fp2 {
 };
 
 // ---------------- points --------------------------------------------------------------
+// *Mem types are the memory images (packed 32-bit words); the plain types live in registers.
+// "ark" conversions change the Montgomery radix at the C-ABI boundary, load/store keep the
+// engine's native radix (buckets, partial sums).
 template <class F>
-struct alignas(16) Affine {                                     // finite point; (0, 0) encodes infinity
+struct alignas(16) AffineMem {
+    typename F::Mem x, y;
+};
+template <class F>
+struct alignas(16) JacobianMem {
+    typename F::Mem x, y, z;
+};
+template <class F>
+struct alignas(16) XYZZMem {
+    typename F::Mem x, y, zz, zzz;
+};
+
+// 128-bit vector copy of a memory image (global -> registers)
+template <class M>
+B200_DEV M ldg_mem(const M *__restrict__ src) {
+    static_assert(sizeof(M) % 16 == 0, "memory images are 16-byte multiples");
+    M r;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(M) / 16); k++) d4[k] = __ldg(s4 + k);
+    return r;
+}
+
+template <class F>
+struct Affine {                                     // finite point; (0, 0) encodes infinity
     F x, y;
     B200_DEV bool is_inf() const { return x.is_zero() && y.is_zero(); }
+    B200_DEV static Affine load(const AffineMem<F> &m) { return {F::load(m.x), F::load(m.y)}; }
+    B200_DEV static Affine from_ark(const AffineMem<F> &m) { return {F::from_ark(m.x), F::from_ark(m.y)}; }
+    B200_DEV AffineMem<F> store() const { return {x.store(), y.store()}; }
+    B200_DEV AffineMem<F> to_ark() const { return {x.to_ark(), y.to_ark()}; }
 };
 
 template <class F>
-struct alignas(16) Jacobian {
+struct Jacobian {
     F x, y, z;
     B200_DEV static Jacobian inf() { return {F::one(), F::one(), F::zero()}; }
     B200_DEV bool is_inf() const { return z.is_zero(); }
+    B200_DEV static Jacobian from_ark(const JacobianMem<F> &m) {
+        return {F::from_ark(m.x), F::from_ark(m.y), F::from_ark(m.z)};
+    }
+    B200_DEV JacobianMem<F> to_ark() const { return {x.to_ark(), y.to_ark(), z.to_ark()}; }
 
     // Out-of-line bodies take and return points BY VALUE (see the note at Fp::mul_outline).
     // dbl-2009-l (2M + 5S)
@@ -113,10 +156,14 @@ struct alignas(16) Jacobian {
 };
 
 template <class F>
-struct alignas(16) XYZZ {
+struct XYZZ {
     F x, y, zz, zzz;
     B200_DEV static XYZZ inf() { return {F::zero(), F::zero(), F::zero(), F::zero()}; }
     B200_DEV bool is_inf() const { return zz.is_zero(); }
+    B200_DEV static XYZZ load(const XYZZMem<F> &m) {
+        return {F::load(m.x), F::load(m.y), F::load(m.zz), F::load(m.zzz)};
+    }
+    B200_DEV XYZZMem<F> store() const { return {x.store(), y.store(), zz.store(), zzz.store()}; }
 
     // mdbl-2008-s-1: 2 * (affine point)
     B200_COLD static XYZZ dbl_affine(F px, F py) {

@@ -42,18 +42,6 @@ static bool curve_info(int curve, CurveInfo &ci) {
      : (curve) == B200_BLS12_377_G2 ? FN<G2_377>(__VA_ARGS__)                              \
                                     : FN<G_761>(__VA_ARGS__))
 
-static int pack_bases(Engine &E, const void *src_dev, size_t stride, size_t n, const CurveInfo &ci, void *dst,
-                      cudaStream_t st) {
-    if (n == 0) return B200_OK;
-    size_t xy = 2 * ci.coord_bytes;
-    if (stride % 8 || stride < xy) return fail(B200_ERR_ARG, "bad base stride %zu", stride);
-    k_pack_bases<<<ceil_div(n, 256), 256, 0, st>>>(reinterpret_cast<const uint64_t *>(src_dev), (uint32_t)n,
-                                                   (uint32_t)(stride / 8), (uint32_t)(xy / 8), stride > xy ? 1 : 0,
-                                                   reinterpret_cast<uint64_t *>(dst));
-    LAUNCH_CHECK();
-    return B200_OK;
-}
-
 }  // namespace b200
 
 using namespace b200;
@@ -96,7 +84,7 @@ void b200_shutdown(void) {
     cudaSetDevice(E->device);
     cudaStreamSynchronize(E->stream);
     for (Buffer *b : {&E->counts, &E->offsets, &E->cursor, &E->tile_sums, &E->bins, &E->order, &E->sorted, &E->buckets,
-                      &E->partials, &E->window_sums, &E->h2d_bases, &E->packed_bases, &E->scalars, &E->result})
+                      &E->partials, &E->window_sums, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result})
         b->release();
     for (auto &ev : E->prof_ev)
         if (ev) cudaEventDestroy(ev);
@@ -120,7 +108,18 @@ int b200_msm_device(int curve, const void *d_bases_packed, const void *d_scalars
     if (!d_out_jacobian || (n && (!d_bases_packed || !d_scalars))) return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    return DISPATCH_CURVE(curve, msm_device, E, d_bases_packed, d_scalars, n, d_out_jacobian, st);
+    return DISPATCH_CURVE(curve, msm_device, E, d_bases_packed, 2 * ci.coord_bytes, d_scalars, n, d_out_jacobian, st);
+}
+
+int b200_msm_prepared_device(int curve, const void *d_bases_prepared, const void *d_scalars, size_t n,
+                             void *d_out_jacobian, void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!d_out_jacobian || (n && (!d_bases_prepared || !d_scalars))) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    return DISPATCH_CURVE(curve, msm_native, E, d_bases_prepared, d_scalars, n, d_out_jacobian, st);
 }
 
 int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, int src_on_device, void *d_dst_packed,
@@ -137,7 +136,7 @@ int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, 
         CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, src, n * stride, cudaMemcpyHostToDevice, st));
         dsrc = E.h2d_bases.p;
     }
-    return pack_bases(E, dsrc, stride, n, ci, d_dst_packed, st);
+    return DISPATCH_CURVE(curve, pack_bases, dsrc, stride, n, d_dst_packed, st);
 }
 
 int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian) {
@@ -148,19 +147,15 @@ int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalar
     cudaStream_t st = E.stream;
     int rc;
     if ((rc = E.result.reserve(ci.jac_bytes))) return rc;
+    const void *d_bases = nullptr;
     if (n) {
-        size_t xy = 2 * ci.coord_bytes;
-        if ((rc = E.scalars.reserve(n * ci.scalar_bytes)) || (rc = E.packed_bases.reserve(n * xy))) return rc;
+        if (stride % 4 || stride < 2 * ci.coord_bytes) return fail(B200_ERR_ARG, "bad base stride %zu", stride);
+        if ((rc = E.scalars.reserve(n * ci.scalar_bytes)) || (rc = E.h2d_bases.reserve(n * stride))) return rc;
         CUDA_TRY(cudaMemcpyAsync(E.scalars.p, scalars, n * ci.scalar_bytes, cudaMemcpyHostToDevice, st));
-        if (stride == xy) {
-            CUDA_TRY(cudaMemcpyAsync(E.packed_bases.p, bases, n * xy, cudaMemcpyHostToDevice, st));
-        } else {
-            if ((rc = E.h2d_bases.reserve(n * stride))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bases, n * stride, cudaMemcpyHostToDevice, st));
-            if ((rc = pack_bases(E, E.h2d_bases.p, stride, n, ci, E.packed_bases.p, st))) return rc;
-        }
+        CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bases, n * stride, cudaMemcpyHostToDevice, st));
+        d_bases = E.h2d_bases.p;
     }
-    rc = DISPATCH_CURVE(curve, msm_device, E, E.packed_bases.p, E.scalars.p, n, E.result.p, st);
+    rc = DISPATCH_CURVE(curve, msm_device, E, d_bases, stride, E.scalars.p, n, E.result.p, st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_jacobian, E.result.p, ci.jac_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -60,7 +60,7 @@ struct Engine {
     // workspace (grow-only)
     Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums;
     // staging for the host-pointer API
-    Buffer h2d_bases, packed_bases, scalars, result;
+    Buffer h2d_bases, native_bases, scalars, result;
     // optional timing of the dominant kernel (b200_profile_*): event pairs around k_bucket_accumulate
     bool profile = false;
     static constexpr int PROF_SLOTS = 256;
@@ -74,7 +74,9 @@ struct Engine {
 inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 // per-curve entry points; each is instantiated in its own translation unit (inst_*.cu)
-template <class C> int msm_device(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
+template <class C> int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
+template <class C> int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
+template <class C> int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStream_t st);
 template <class C> int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st);
 template <class C> int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st);
 template <class C> int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st);

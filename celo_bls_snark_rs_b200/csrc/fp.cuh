@@ -1,18 +1,29 @@
-// Prime-field arithmetic for sm_100a: Montgomery residues on 32-bit limbs held in
-// registers, carry chains written as PTX mad.lo.cc / madc.hi.cc pairs that ptxas
-// fuses into IMAD.WIDE.U32 with predicate carries.
+// Prime-field arithmetic for sm_100a.
 //
-// Replaces (on the device) ark-ff 0.1.0 Fp384 / Fp768 as reached from
-// crates/bls-crypto/src/bls/signature.rs:85 and public.rs:61; the memory format is
-// arkworks' own (Montgomery, R = 2^384 / 2^768, little-endian limbs) so device
-// buffers are bit-compatible with what the Rust side holds.
+// Device replacement for ark-ff 0.1.0 Fp384 / Fp768 as reached from
+// crates/bls-crypto/src/bls/signature.rs:85 and public.rs:61.  Elements are arkworks' own
+// representation both in memory and in registers: Montgomery residues (R = 2^384 / 2^768),
+// canonical in [0, p), 32-bit limbs (12 for BLS12-377 Fq, 24 for BW6-761 Fq), so device
+// buffers are bit-compatible with what the Rust side holds and nothing is converted at the
+// C-ABI boundary.
 //
-// Multiplication is a row-interleaved (CIOS-style) Montgomery product with the
-// partial products split into an "even" and an "odd" accumulator (each N limbs,
-// the odd one offset by one limb).  A wide product a[j]*b lands on limbs (j, j+1),
-// so products of even j chain through one accumulator without overlapping and
-// products of odd j through the other.  Dividing by 2^32 after each row is free:
-// the two accumulators swap roles (see mont_row()).
+// Multiplication is a row-interleaved (CIOS-style) Montgomery product with the partial
+// products split into an "even" and an "odd" accumulator (each N limbs, the odd one offset by
+// one limb).  A wide product a[j]*b lands on limbs (j, j+1), so products of even j chain
+// through one accumulator without overlapping and products of odd j through the other.
+// Dividing by 2^32 after each row is free: the two accumulators swap roles (mont_row()).
+// The chains are PTX mad.lo.cc / madc.hi.cc pairs that ptxas fuses into IMAD.WIDE.U32.X.
+//
+// Measured on B200 (profiles/r1_microbench_*.txt, profiles/r1_field_layer_notes.md):
+//   * a 32x32->64 multiply-add (IMAD.WIDE.U32, with or without carry) occupies the FMA-heavy
+//     pipe for 4 cycles per warp; IMAD.HI also 4, a 32-bit IMAD 2.  2*N*N wide products per
+//     Montgomery product is therefore the floor; an unsaturated 28-bit-limb variant (no carry
+//     chains, 14 limbs) was built and measured: it saturates the pipe (93 %) but needs 36 %
+//     more products and lost.
+//   * -p^-1 mod 2^32 is read from constant memory at run time on purpose: when ptxas can see
+//     that it is 0xffffffff (BLS12-377: p = 1 mod 2^32) it rewrites the reduction products as
+//     IMAD.X + IMAD.HI.U32.X pairs (6 pipe cycles instead of 4); with an opaque value all
+//     2*N*N products stay fused.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -22,6 +33,9 @@
 namespace b200 {
 
 #define B200_DEV __device__ __forceinline__
+
+// -p^-1 mod 2^32 per field (slot 0: BLS12-377 Fq, slot 1: BW6-761 Fq); see the note above.
+static __constant__ uint32_t c_mont_inv[2] = {Fq377Params::INV, Fq761Params::INV};
 
 // ---- carry-chain primitives (all volatile: the CC flag links consecutive asm statements) ----
 B200_DEV void add_cc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
@@ -53,9 +67,16 @@ B200_DEV void madc_wide_top(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) 
     asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 
+template <int NW>
+struct alignas(16) FpMem {                         // memory image: NW little-endian 32-bit words
+    uint32_t w[NW];
+};
+
 template <class P>
 struct Fp {
     static constexpr int N = P::N;
+    static constexpr int NW = P::N;
+    using Mem = FpMem<NW>;
     uint32_t l[N];
 
     B200_DEV static Fp zero() {
@@ -70,18 +91,25 @@ struct Fp {
         for (int i = 0; i < N; i++) r.l[i] = P::one(i);
         return r;
     }
-    __device__ __noinline__ static uint32_t pm2_word(int w) {   // runtime-indexed p - 2
-        uint32_t r = 0;
-#pragma unroll
-        for (int i = 0; i < N; i++) r = (i == w) ? P::pm2(i) : r;
-        return r;
-    }
-    B200_DEV static Fp r2() {
+
+    // ---- memory image <-> registers.  The register form IS the arkworks form, so the "ark"
+    // and the engine-internal ("load/store") flavours coincide; both names are kept so the
+    // kernels say which side of the C-ABI a buffer is on.
+    B200_DEV static Fp load(const Mem &m) {
         Fp r;
 #pragma unroll
-        for (int i = 0; i < N; i++) r.l[i] = P::r2(i);
+        for (int i = 0; i < N; i++) r.l[i] = m.w[i];
         return r;
     }
+    B200_DEV Mem store() const {
+        Mem m;
+#pragma unroll
+        for (int i = 0; i < N; i++) m.w[i] = l[i];
+        return m;
+    }
+    B200_DEV static Fp from_ark(const Mem &m) { return load(m); }
+    B200_DEV Mem to_ark() const { return store(); }
+
     B200_DEV bool is_zero() const {
         uint32_t o = 0;
 #pragma unroll
@@ -135,21 +163,6 @@ struct Fp {
         for (int i = 0; i < N; i++) r.l[i] = flag ? n.l[i] : l[i];
         return r;
     }
-    // a^(p-2) (Fermat); inv(0) = 0.  Cold path: kept out of line and rolled.
-    B200_DEV Fp inv() const { return inv_outline(*this); }
-    __device__ __noinline__ static Fp inv_outline(Fp base) {
-        Fp acc = one();
-#pragma unroll 1
-        for (int w = 0; w < N; w++) {
-            uint32_t e = pm2_word(w);
-#pragma unroll 1
-            for (int b = 0; b < 32; b++) {
-                if ((e >> b) & 1u) acc = acc * base;
-                base = base.sqr();
-            }
-        }
-        return acc;
-    }
     B200_DEV Fp dbl() const { return *this + *this; }
 
     // one row of the interleaved product: (even, odd) += a * bi + m * p, then / 2^32 by role swap.
@@ -157,7 +170,8 @@ struct Fp {
     // previous even one, whose limb 0 is zero: odd >> 64 re-aligns it one limb above `even`,
     // and its limb 1 is folded into even[0] with the carry entering the odd chain.
     template <bool FIRST>
-    B200_DEV static void mont_row(uint32_t (&even)[N], uint32_t (&odd)[N], const uint32_t (&a)[N], uint32_t bi) {
+    B200_DEV static void mont_row(uint32_t (&even)[N], uint32_t (&odd)[N], const uint32_t (&a)[N], uint32_t bi,
+                                  uint32_t inv) {
         if (FIRST) {
 #pragma unroll
             for (int j = 0; j < N; j += 2) {
@@ -174,7 +188,7 @@ struct Fp {
             for (int j = 2; j < N; j += 2) madc_wide_cc(even[j], even[j + 1], a[j], bi);
             addc(odd[N - 1], odd[N - 1], 0);
         }
-        uint32_t m = even[0] * P::INV;
+        uint32_t m = even[0] * inv;
         mad_wide_cc(odd[0], odd[1], P::mod(1), m);
 #pragma unroll
         for (int j = 2; j < N; j += 2) madc_wide_cc(odd[j], odd[j + 1], P::mod(j + 1), m);
@@ -185,13 +199,14 @@ struct Fp {
     }
 
     B200_DEV static Fp mul_inline(const Fp &a, const Fp &b) {
+        const uint32_t inv = c_mont_inv[P::INV_SLOT];
         uint32_t even[N], odd[N];
-        mont_row<true>(even, odd, a.l, b.l[0]);
-        mont_row<false>(odd, even, a.l, b.l[1]);
+        mont_row<true>(even, odd, a.l, b.l[0], inv);
+        mont_row<false>(odd, even, a.l, b.l[1], inv);
 #pragma unroll
         for (int i = 2; i < N; i += 2) {
-            mont_row<false>(even, odd, a.l, b.l[i]);
-            mont_row<false>(odd, even, a.l, b.l[i + 1]);
+            mont_row<false>(even, odd, a.l, b.l[i], inv);
+            mont_row<false>(odd, even, a.l, b.l[i + 1], inv);
         }
         // the last row left odd[0] == 0: value = even + (odd >> 32), i.e. r[k] = even[k] + odd[k + 1]
         Fp r;
@@ -203,11 +218,10 @@ struct Fp {
         return r;
     }
     // by value on purpose: pointer-taking out-of-line helpers were observed to be miscompiled
-    // (caller passed one stack slot for all three pointers); value semantics cannot alias.
+    // (the caller passed one stack slot for all three pointers); value semantics cannot alias.
     __device__ __noinline__ static Fp mul_outline(Fp a, Fp b) { return mul_inline(a, b); }
-    // N = 12 (BLS12-377): fully inlined, ~300 IMAD.WIDE.  N = 24 (BW6-761) is ~1200
-    // instructions per product: one shared out-of-line body keeps code size (and the
-    // instruction cache) sane; the call overhead is ~4% of the body.
+    // N = 12 (BLS12-377): fully inlined, 288 IMAD.WIDE.  N = 24 (BW6-761) is 1152 per product:
+    // one shared out-of-line body keeps code size (and the instruction cache) sane.
     B200_DEV friend Fp operator*(const Fp &a, const Fp &b) {
         if constexpr (N <= 12) {
             return mul_inline(a, b);
@@ -217,11 +231,26 @@ struct Fp {
     }
     B200_DEV Fp sqr() const { return *this * *this; }
 
-    B200_DEV Fp to_mont() const { return *this * r2(); }
-    B200_DEV Fp from_mont() const {
-        Fp o = zero();
-        o.l[0] = 1;
-        return *this * o;
+    // ---- inversion: a^(p-2) (Fermat); inv(0) = 0.  Cold path: out of line and rolled. --------
+    __device__ __noinline__ static uint32_t pm2_word(int w) {        // runtime-indexed word of p - 2
+        uint32_t r = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) r = (i == w) ? P::pm2(i) : r;
+        return r;
+    }
+    B200_DEV Fp inv() const { return inv_outline(*this); }
+    __device__ __noinline__ static Fp inv_outline(Fp base) {
+        Fp acc = one();
+#pragma unroll 1
+        for (int w = 0; w < N; w++) {
+            uint32_t e = pm2_word(w);
+#pragma unroll 1
+            for (int b = 0; b < 32; b++) {
+                if ((e >> b) & 1u) acc = acc * base;
+                base = base.sqr();
+            }
+        }
+        return acc;
     }
 };
 

@@ -210,23 +210,13 @@ static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__r
 }
 
 // ---- bucket accumulation: the dominant kernel ---------------------------------------------
-template <class F>
-B200_DEV Affine<F> load_affine(const Affine<F> *__restrict__ bases, uint32_t idx) {
-    static_assert(sizeof(Affine<F>) % 16 == 0, "packed affine records are 16-byte multiples");
-    constexpr int V = sizeof(Affine<F>) / 16;
-    Affine<F> r;
-    const uint4 *src = reinterpret_cast<const uint4 *>(bases + idx);
-    uint4 *dst = reinterpret_cast<uint4 *>(&r);
-#pragma unroll
-    for (int k = 0; k < V; k++) dst[k] = __ldg(src + k);
-    return r;
-}
-
+// One thread per bucket.  bases are native-radix packed affine images (k_pack_bases output);
+// the next image is prefetched (still packed: 24 / 48 registers) while the current point is added.
 template <class F, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-k_bucket_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
-                    XYZZ<F> *__restrict__ buckets) {
+                    XYZZMem<F> *__restrict__ buckets) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     if (t >= total_buckets) return;
     uint32_t id = order[t];
@@ -234,23 +224,24 @@ k_bucket_accumulate(const Affine<F> *__restrict__ bases, const uint32_t *__restr
     XYZZ<F> acc = XYZZ<F>::inf();
     if (k < end) {
         uint32_t e = __ldg(sorted + k);
-        Affine<F> pt = load_affine(bases, e & 0x7fffffffu);
+        AffineMem<F> img = ldg_mem(bases + (e & 0x7fffffffu));
         for (;;) {
             ++k;
             uint32_t e_next = 0;
-            Affine<F> pt_next;
+            AffineMem<F> img_next;
             bool more = k < end;
-            if (more) {                             // prefetch while the current point is added
+            if (more) {
                 e_next = __ldg(sorted + k);
-                pt_next = load_affine(bases, e_next & 0x7fffffffu);
+                img_next = ldg_mem(bases + (e_next & 0x7fffffffu));
             }
+            Affine<F> pt = Affine<F>::load(img);
             if (!pt.is_inf()) acc.madd(pt.x, pt.y.cneg(e >> 31));
             if (!more) break;
             e = e_next;
-            pt = pt_next;
+            img = img_next;
         }
     }
-    buckets[id] = acc;
+    buckets[id] = acc.store();
 }
 
 // ---- bucket reduction ----------------------------------------------------------------------
@@ -267,86 +258,97 @@ B200_DEV XYZZ<F> small_mul(const XYZZ<F> &p, uint32_t k) {
 
 // thread (w, seg): partial = sum_{j < L} (seg*L + j + 1) * B[w][seg*L + j]
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZ<F> *__restrict__ buckets, MsmPlan p,
-                                                           XYZZ<F> *__restrict__ partials) {
+__global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__restrict__ buckets, MsmPlan p,
+                                                           XYZZMem<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     uint32_t total = (uint32_t)p.windows * p.segs;
     if (t >= total) return;
     uint32_t w = t / p.segs, seg = t % p.segs;
-    const XYZZ<F> *b = buckets + (size_t)w * p.nb + (size_t)seg * p.seg_len;
+    const XYZZMem<F> *b = buckets + (size_t)w * p.nb + (size_t)seg * p.seg_len;
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
     for (int j = p.seg_len - 1; j >= 0; j--) {
-        run.add(b[j]);
+        run.add(XYZZ<F>::load(ldg_mem(b + j)));
         acc.add(run);
     }
     if (seg) acc.add(small_mul(run, seg * (uint32_t)p.seg_len));
-    partials[t] = acc;
+    partials[t] = acc.store();
 }
 
 // block w: window_sums[w] = sum of the window's partials
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZ<F> *__restrict__ partials, MsmPlan p,
-                                                        XYZZ<F> *__restrict__ window_sums) {
+__global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__restrict__ partials, MsmPlan p,
+                                                        XYZZMem<F> *__restrict__ window_sums) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    XYZZ<F> *sm = reinterpret_cast<XYZZ<F> *>(smem_raw);
-    const XYZZ<F> *src = partials + (size_t)blockIdx.x * p.segs;
+    XYZZMem<F> *sm = reinterpret_cast<XYZZMem<F> *>(smem_raw);
+    const XYZZMem<F> *src = partials + (size_t)blockIdx.x * p.segs;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t i = threadIdx.x; i < p.segs; i += THREADS) acc.add(src[i]);
-    sm[threadIdx.x] = acc;
+    for (uint32_t i = threadIdx.x; i < p.segs; i += THREADS) acc.add(XYZZ<F>::load(ldg_mem(src + i)));
+    sm[threadIdx.x] = acc.store();
     __syncthreads();
     for (int s = THREADS / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) {
-            acc.add(sm[threadIdx.x + s]);
-            sm[threadIdx.x] = acc;
+            acc.add(XYZZ<F>::load(sm[threadIdx.x + s]));
+            sm[threadIdx.x] = acc.store();
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) window_sums[blockIdx.x] = acc;
+    if (threadIdx.x == 0) window_sums[blockIdx.x] = acc.store();
 }
 
-// one thread: Horner over the windows, high to low
+// one thread: Horner over the windows, high to low; result leaves in arkworks radix
 template <class F>
-__global__ void k_window_combine(const XYZZ<F> *__restrict__ window_sums, MsmPlan p, Jacobian<F> *__restrict__ out) {
+__global__ void k_window_combine(const XYZZMem<F> *__restrict__ window_sums, MsmPlan p,
+                                 JacobianMem<F> *__restrict__ out) {
     if (threadIdx.x || blockIdx.x) return;
     Jacobian<F> total = Jacobian<F>::inf();
     for (int w = p.windows - 1; w >= 0; w--) {
-        total.add(window_sums[w].to_jacobian());
+        total.add(XYZZ<F>::load(window_sums[w]).to_jacobian());
         if (w)
             for (int k = 0; k < p.c; k++) total.dbl();
     }
-    *out = total;
+    *out = total.to_ark();
 }
 
-// ---- layout conversion: arkworks GroupAffine records -> packed (x | y), infinity -> (0, 0) ----
-// 8-byte granularity (arkworks records are only 8-byte aligned: 104 / 200 byte stride).
-static __global__ void __launch_bounds__(256) k_pack_bases(const uint64_t *__restrict__ src, uint32_t n, uint32_t stride_words,
-                                                    uint32_t coord_words2 /* words of x|y */, int has_flag,
-                                                    uint64_t *__restrict__ dst) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t *s = src + (size_t)i * stride_words;
-    uint64_t *d = dst + (size_t)i * coord_words2;
-    bool inf = has_flag && (s[coord_words2] & 0xffu);
-    for (uint32_t k = 0; k < coord_words2; k++) d[k] = inf ? 0ull : s[k];
-}
-
-// out = sum of `count` Jacobian points (multi-GPU partial combine; tiny)
-template <class F>
-__global__ void k_sum_jacobian(const Jacobian<F> *__restrict__ pts, uint32_t count, Jacobian<F> *__restrict__ out) {
-    if (threadIdx.x || blockIdx.x) return;
-    Jacobian<F> total = Jacobian<F>::inf();
-    for (uint32_t i = 0; i < count; i++) total.add(pts[i]);
-    *out = total;
-}
-
-// out[i] = scalars[i] * base (double-and-add); used to synthesise benchmark / test bases on device
-template <class F, int SW, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_fixed_base_mul(const Affine<F> *__restrict__ base,
-                                                            const uint32_t *__restrict__ scalars, uint32_t n,
-                                                            XYZZ<F> *__restrict__ out) {
+// ---- layout + radix conversion: arkworks GroupAffine records -> native packed images ---------
+// src records: x | y [| u8 infinity | pad] at `stride` bytes (4-byte aligned); infinity -> (0, 0).
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_pack_bases(const uint32_t *__restrict__ src, uint32_t n,
+                                                        uint32_t stride_words, int has_flag,
+                                                        AffineMem<F> *__restrict__ dst) {
     uint32_t i = blockIdx.x * THREADS + threadIdx.x;
     if (i >= n) return;
-    Affine<F> g = load_affine(base, 0);
+    constexpr int WORDS = sizeof(AffineMem<F>) / 4;
+    const uint32_t *s = src + (size_t)i * stride_words;
+    AffineMem<F> img;
+    uint32_t *iw = reinterpret_cast<uint32_t *>(&img);
+    uint32_t any = 0;
+#pragma unroll
+    for (int k = 0; k < WORDS; k++) {
+        iw[k] = __ldg(s + k);
+        any |= iw[k];
+    }
+    bool inf = (has_flag && (__ldg(s + WORDS) & 0xffu)) || any == 0;
+    Affine<F> pt = inf ? Affine<F>{F::zero(), F::zero()} : Affine<F>::from_ark(img);
+    dst[i] = pt.store();
+}
+
+// out = sum of `count` Jacobian points in arkworks radix (multi-GPU partial combine; tiny)
+template <class F>
+__global__ void k_sum_jacobian(const JacobianMem<F> *__restrict__ pts, uint32_t count, JacobianMem<F> *__restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    Jacobian<F> total = Jacobian<F>::inf();
+    for (uint32_t i = 0; i < count; i++) total.add(Jacobian<F>::from_ark(pts[i]));
+    *out = total.to_ark();
+}
+
+// out[i] = scalars[i] * base (double-and-add); synthesises benchmark / test bases on device
+template <class F, int SW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_fixed_base_mul(const AffineMem<F> *__restrict__ base,
+                                                            const uint32_t *__restrict__ scalars, uint32_t n,
+                                                            XYZZMem<F> *__restrict__ out) {
+    uint32_t i = blockIdx.x * THREADS + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> g = Affine<F>::from_ark(ldg_mem(base));
     XYZZ<F> r = XYZZ<F>::inf();
     for (int w = SW - 1; w >= 0; w--) {
         uint32_t word = __ldg(scalars + (size_t)i * SW + w);
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(THREADS) k_fixed_base_mul(const Affine<F> *__r
             if ((word >> b) & 1u) r.madd(g.x, g.y);
         }
     }
-    out[i] = r;
+    out[i] = r.store();
 }
 
 }  // namespace b200
@@ -375,26 +377,28 @@ template <class B> struct FieldInv<Fp2<B>> {
     }
 };
 
+// native XYZZ images -> arkworks-radix packed affine records
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_xyzz_to_affine(const XYZZ<F> *__restrict__ in, uint32_t n,
-                                                            Affine<F> *__restrict__ out) {
+__global__ void __launch_bounds__(THREADS) k_xyzz_to_affine(const XYZZMem<F> *__restrict__ in, uint32_t n,
+                                                            AffineMem<F> *__restrict__ out) {
     uint32_t i = blockIdx.x * THREADS + threadIdx.x;
     if (i >= n) return;
-    XYZZ<F> p = in[i];
+    XYZZ<F> p = XYZZ<F>::load(ldg_mem(in + i));
     Affine<F> r = {F::zero(), F::zero()};
     if (!p.is_inf()) {
         F iv = FieldInv<F>::inv(p.zz * p.zzz);      // 1/ZZ = iv * ZZZ, 1/ZZZ = iv * ZZ
         r.x = p.x * (iv * p.zzz);
         r.y = p.y * (iv * p.zz);
     }
-    out[i] = r;
+    out[i] = r.to_ark();
 }
 
 // One inversion per thread, shared by BATCH consecutive points (Montgomery's trick):
 // the device form of batch_normalization_into_affine (signature.rs:82, public.rs:58).
+// Input: arkworks GroupProjective images; output: arkworks-radix packed affine records.
 template <class F, int THREADS, int BATCH>
-__global__ void __launch_bounds__(THREADS) k_jacobian_to_affine(const Jacobian<F> *__restrict__ in, uint32_t n,
-                                                                Affine<F> *__restrict__ out) {
+__global__ void __launch_bounds__(THREADS) k_jacobian_to_affine(const JacobianMem<F> *__restrict__ in, uint32_t n,
+                                                                AffineMem<F> *__restrict__ out) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     uint32_t first = t * BATCH;
     if (first >= n) return;
@@ -402,34 +406,36 @@ __global__ void __launch_bounds__(THREADS) k_jacobian_to_affine(const Jacobian<F
     F prefix[BATCH];                                // prefix[k] = prod of non-zero z[0..k]
     F run = F::one();
     for (uint32_t k = 0; k < cnt; k++) {
-        F z = in[first + k].z;
+        F z = F::from_ark(ldg_mem(&in[first + k].z));
         if (!z.is_zero()) run = run * z;
         prefix[k] = run;
     }
     F iv = FieldInv<F>::inv(run);
     for (int k = (int)cnt - 1; k >= 0; k--) {
-        Jacobian<F> p = in[first + k];
+        Jacobian<F> p = Jacobian<F>::from_ark(ldg_mem(in + first + k));
         Affine<F> r = {F::zero(), F::zero()};
         if (!p.z.is_zero()) {
-            F zi = k ? iv * prefix[k - 1] : iv;      // 1 / z_k
+            F zi = iv;                               // 1 / z_k
+            if (k) zi = zi * prefix[k - 1];
             iv = iv * p.z;
             F zi2 = zi.sqr();
             r.x = p.x * zi2;
             r.y = p.y * (zi2 * zi);
         }
-        out[first + k] = r;
+        out[first + k] = r.to_ark();
     }
 }
 
-// ---- element-wise field ops (parity tests of the field layer against the oracle) -------------
+// ---- element-wise field ops (parity tests of the field layer against the CPU restatement) ----
 enum FieldOp { FOP_ADD = 0, FOP_SUB = 1, FOP_MUL = 2, FOP_SQR = 3, FOP_INV = 4, FOP_NEG = 5, FOP_DBL = 6 };
 
 template <class F>
-__global__ void __launch_bounds__(64) k_field_op(int op, const F *__restrict__ a, const F *__restrict__ b, uint32_t n,
-                                                 F *__restrict__ out) {
+__global__ void __launch_bounds__(64) k_field_op(int op, const typename F::Mem *__restrict__ a,
+                                                 const typename F::Mem *__restrict__ b, uint32_t n,
+                                                 typename F::Mem *__restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    F x = a[i], y = b[i], r;
+    F x = F::from_ark(ldg_mem(a + i)), y = F::from_ark(ldg_mem(b + i)), r;
     switch (op) {
     case FOP_ADD: r = x + y; break;
     case FOP_SUB: r = x - y; break;
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(64) k_field_op(int op, const F *__restrict__ a
     case FOP_NEG: r = x.neg(); break;
     default: r = x.dbl(); break;
     }
-    out[i] = r;
+    out[i] = r.to_ark();
 }
 
 }  // namespace b200

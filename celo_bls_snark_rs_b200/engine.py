@@ -27,7 +27,7 @@ PACKED_STRIDE = {k: 2 * v for k, v in COORD_BYTES.items()}
 
 EXPORTS = [
     "b200_init", "b200_shutdown", "b200_last_error", "b200_msm", "b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2",
-    "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device",
+    "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device", "b200_msm_prepared_device",
     "b200_sum_jacobian_device", "b200_fixed_base_mul_device", "b200_batch_to_affine_device", "b200_sync",
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device",
@@ -57,6 +57,7 @@ def load() -> ctypes.CDLL:
         getattr(lib, name).argtypes = [vp, vp, sz, vp]
     lib.b200_msm_device.argtypes = [i32, vp, vp, sz, vp, vp]
     lib.b200_pack_bases_device.argtypes = [i32, vp, sz, sz, i32, vp, vp]
+    lib.b200_msm_prepared_device.argtypes = [i32, vp, vp, sz, vp, vp]
     lib.b200_sum_jacobian_device.argtypes = [i32, vp, sz, vp, vp]
     lib.b200_fixed_base_mul_device.argtypes = [i32, vp, vp, sz, vp, vp]
     lib.b200_batch_to_affine_device.argtypes = [i32, vp, sz, vp, vp]
@@ -118,6 +119,10 @@ def msm_host_ptrs(curve: int, bases_ptr: int, stride: int, scalars_ptr: int, n: 
 
 def msm_device(curve: int, d_bases: int, d_scalars: int, n: int, d_out: int, stream: int = 0):
     _check(load().b200_msm_device(curve, d_bases, d_scalars, n, d_out, stream or None))
+
+
+def msm_prepared_device(curve: int, d_bases_prepared: int, d_scalars: int, n: int, d_out: int, stream: int = 0):
+    _check(load().b200_msm_prepared_device(curve, d_bases_prepared, d_scalars, n, d_out, stream or None))
 
 
 def pack_bases_device(curve: int, src: int, stride: int, n: int, src_on_device: bool, d_dst: int, stream: int = 0):

@@ -71,15 +71,21 @@ int b200_msm_bw6_761_g1(const void *bases_200B, const uint64_t *scalars, size_t 
 int b200_msm_bw6_761_g2(const void *bases_200B, const uint64_t *scalars, size_t n, void *out_288B);
 
 /* Device-pointer form: everything already resident in HBM, asynchronous on `stream`
- * (a cudaStream_t; NULL = the engine's own stream).  d_bases_packed is the packed
- * layout (x | y, 16-byte aligned, no flag).  d_out_jacobian receives the result. */
+ * (a cudaStream_t; NULL = the engine's own stream).  d_bases_packed holds packed arkworks
+ * residues (x | y, 16-byte aligned records of 2 * coordinate bytes, (0, 0) = infinity).
+ * d_out_jacobian receives the arkworks GroupProjective image. */
 int b200_msm_device(int curve, const void *d_bases_packed, const void *d_scalars, size_t n, void *d_out_jacobian,
                     void *stream);
 
-/* arkworks-layout records (host or device memory) -> packed device records.
- * `src_on_device` != 0: d/h pointer is device memory. */
-int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, int src_on_device, void *d_dst_packed,
-                           void *stream);
+/* Fixed-base use (a Groth16 proving key is multiplied by many witnesses,
+ * crates/epoch-snark/src/api/prover.rs:78): convert the bases once with
+ * b200_pack_bases_device into the engine's prepared form (same size as the packed
+ * records; internal Montgomery radix), then call b200_msm_prepared_device per witness.
+ * src: arkworks records at `stride` bytes in host (src_on_device = 0) or device memory. */
+int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, int src_on_device,
+                           void *d_dst_prepared, void *stream);
+int b200_msm_prepared_device(int curve, const void *d_bases_prepared, const void *d_scalars, size_t n,
+                             void *d_out_jacobian, void *stream);
 
 /* out = sum of `count` Jacobian points (device pointers).  Used to combine per-GPU
  * partial MSM results after the all-gather. */

@@ -10,19 +10,6 @@
 
 using namespace b200;
 
-__constant__ uint32_t c_mod377[12];
-
-struct Fq377ParamsConst {
-    static constexpr int N = 12;
-    static constexpr int BITS = 377;
-    static constexpr uint32_t INV = 0xffffffffu;
-    __device__ static uint32_t mod(int i) { return c_mod377[i]; }
-    __host__ __device__ static constexpr uint32_t one(int i) { return Fq377Params::one(i); }
-    __host__ __device__ static constexpr uint32_t r2(int i) { return Fq377Params::r2(i); }
-    __host__ __device__ static constexpr uint32_t pm2(int i) { return Fq377Params::pm2(i); }
-};
-using Fq377C = Fp<Fq377ParamsConst>;
-
 template <int MODE>
 __global__ void __launch_bounds__(256) k_imad(uint32_t *out, uint32_t seed, int iters) {
     uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
@@ -61,35 +48,35 @@ __global__ void __launch_bounds__(256) k_imad(uint32_t *out, uint32_t seed, int 
 }
 
 template <class F>
-__global__ void __launch_bounds__(256) k_mul(F *io, int iters) {
+__global__ void __launch_bounds__(256) k_mul(typename F::Mem *io, int iters) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    F x = io[t], y = io[t + 1];
+    F x = F::load(io[t]), y = F::load(io[t + 1]);
     for (int i = 0; i < iters; i++) {
         x = x * y;
         y = y * x;
     }
-    io[t] = x + y;
+    io[t] = (x + y).store();
 }
 template <class F>
-__global__ void __launch_bounds__(256) k_addsub(F *io, int iters) {
+__global__ void __launch_bounds__(256) k_addsub(typename F::Mem *io, int iters) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    F x = io[t], y = io[t + 1];
+    F x = F::load(io[t]), y = F::load(io[t + 1]);
     for (int i = 0; i < iters; i++) {
         x = x + y;
         y = y - x;
     }
-    io[t] = x + y;
+    io[t] = (x + y).store();
 }
 template <class F, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_madd(XYZZ<F> *io, const Affine<F> *pts, int iters) {
+__global__ void __launch_bounds__(THREADS, MINB) k_madd(XYZZMem<F> *io, const AffineMem<F> *pts, int iters) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    XYZZ<F> acc = io[t];
-    Affine<F> p = pts[t & 1023];
+    XYZZ<F> acc = XYZZ<F>::load(io[t]);
+    Affine<F> p = Affine<F>::load(pts[t & 1023]);
     for (int i = 0; i < iters; i++) {
         acc.madd(p.x, p.y);
         p.x = p.x + acc.zz;   // keep operands changing
     }
-    io[t] = acc;
+    io[t] = acc.store();
 }
 
 template <class K, class... A>
@@ -115,14 +102,11 @@ int main() {
     cudaGetDeviceProperties(&prop, 0);
     int sms = prop.multiProcessorCount;
     printf("device %s, %d SMs, %d MHz\n", prop.name, sms, prop.clockRate / 1000);
-    uint32_t mod[12];
-    for (int i = 0; i < 12; i++) mod[i] = Fq377Params::mod(i);
-    cudaMemcpyToSymbol(c_mod377, mod, sizeof mod);
 
     void *buf;
     size_t bytes = (size_t)sms * 8 * 256 * 512 + 4096;
     cudaMalloc(&buf, bytes);
-    cudaMemset(buf, 0x5a, bytes);
+    cudaMemset(buf, 0x01, bytes);
     dim3 grid(sms * 8), block(256);
     double threads = (double)sms * 8 * 256;
 
@@ -141,26 +125,27 @@ int main() {
     printf("%-22s %8.3f ms  %7.2f Tinstr/s\n", names[4], ms, threads * iters * 8 / ms / 1e9);
 
     iters = 256;
-    ms = time_kernel(k_mul<Fq377>, grid, block, (Fq377 *)buf, iters);
-    printf("Fq377 mul (immediates) %8.3f ms  %7.2f Gmul/s\n", ms, threads * iters * 2 / ms / 1e6);
-    ms = time_kernel(k_mul<Fq377C>, grid, block, (Fq377C *)buf, iters);
-    printf("Fq377 mul (const bank) %8.3f ms  %7.2f Gmul/s\n", ms, threads * iters * 2 / ms / 1e6);
-    ms = time_kernel(k_addsub<Fq377>, grid, block, (Fq377 *)buf, iters * 4);
-    printf("Fq377 add+sub          %8.3f ms  %7.2f Gop/s\n", ms, threads * iters * 8 / ms / 1e6);
-    ms = time_kernel(k_mul<Fq761>, grid, block, (Fq761 *)buf, iters / 4);
-    printf("Fq761 mul (out-of-line)%8.3f ms  %7.2f Gmul/s\n", ms, threads * (iters / 4) * 2 / ms / 1e6);
+    ms = time_kernel(k_mul<Fq377>, grid, block, (Fq377::Mem *)buf, iters);
+    printf("Fq377 mul (32-bit limbs)  %8.3f ms  %7.2f Gmul/s\n", ms, threads * iters * 2 / ms / 1e6);
+    ms = time_kernel(k_addsub<Fq377>, grid, block, (Fq377::Mem *)buf, iters * 4);
+    printf("Fq377 add+sub             %8.3f ms  %7.2f Gop/s\n", ms, threads * iters * 8 / ms / 1e6);
+    ms = time_kernel(k_mul<Fq761>, grid, block, (Fq761::Mem *)buf, iters / 4);
+    printf("Fq761 mul (out-of-line)   %8.3f ms  %7.2f Gmul/s\n", ms, threads * (iters / 4) * 2 / ms / 1e6);
+    // single-warp latency of a dependent product chain
+    ms = time_kernel(k_mul<Fq377>, dim3(1), dim3(32), (Fq377::Mem *)buf, 4096);
+    printf("Fq377 mul latency (1 warp, dependent chain) %8.1f ns/mul\n", ms * 1e6 / (4096 * 2));
 
     iters = 64;
     {
         dim3 g(sms * 12), b(128);
         double th = (double)sms * 12 * 128;
-        ms = time_kernel(k_madd<Fq377, 128, 3>, g, b, (XYZZ<Fq377> *)buf, (const Affine<Fq377> *)buf, iters);
+        ms = time_kernel(k_madd<Fq377, 128, 2>, g, b, (XYZZMem<Fq377> *)buf, (const AffineMem<Fq377> *)buf, iters);
+        printf("G1-377 madd 128x2      %8.3f ms  %7.2f Gmadd/s\n", ms, th * iters / ms / 1e6);
+        ms = time_kernel(k_madd<Fq377, 128, 3>, g, b, (XYZZMem<Fq377> *)buf, (const AffineMem<Fq377> *)buf, iters);
         printf("G1-377 madd 128x3      %8.3f ms  %7.2f Gmadd/s\n", ms, th * iters / ms / 1e6);
-        ms = time_kernel(k_madd<Fq377C, 128, 3>, g, b, (XYZZ<Fq377C> *)buf, (const Affine<Fq377C> *)buf, iters);
-        printf("G1-377 madd const 128x3%8.3f ms  %7.2f Gmadd/s\n", ms, th * iters / ms / 1e6);
-        ms = time_kernel(k_madd<Fq377, 128, 4>, g, b, (XYZZ<Fq377> *)buf, (const Affine<Fq377> *)buf, iters);
+        ms = time_kernel(k_madd<Fq377, 128, 4>, g, b, (XYZZMem<Fq377> *)buf, (const AffineMem<Fq377> *)buf, iters);
         printf("G1-377 madd 128x4      %8.3f ms  %7.2f Gmadd/s\n", ms, th * iters / ms / 1e6);
-        ms = time_kernel(k_madd<Fq377, 256, 1>, g, b, (XYZZ<Fq377> *)buf, (const Affine<Fq377> *)buf, iters);
+        ms = time_kernel(k_madd<Fq377, 256, 1>, g, b, (XYZZMem<Fq377> *)buf, (const AffineMem<Fq377> *)buf, iters);
         printf("G1-377 madd 256x1      %8.3f ms  %7.2f Gmadd/s\n", ms, th * iters / ms / 1e6);
     }
     cudaFree(buf);
