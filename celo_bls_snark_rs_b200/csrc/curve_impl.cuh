@@ -30,6 +30,14 @@ static MsmPlan make_plan(size_t n) {
             best.nb = 1u << (c - 1);
         }
     }
+    if (const char *env = getenv("B200_MSM_C")) {                  // experiments: force the window width
+        int c = atoi(env);
+        if (c >= 2 && c <= 22) {
+            best.c = c;
+            best.windows = (C::SCALAR_BITS + 1 + c - 1) / c;
+            best.nb = 1u << (c - 1);
+        }
+    }
     best.n = (uint32_t)n;
     best.seg_len = best.nb >= 4096 ? 16 : (best.nb >= 64 ? 8 : (int)std::min<uint32_t>(best.nb, 4u));
     best.segs = best.nb / best.seg_len;
@@ -114,12 +122,12 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
         E.prof_units += n;
     }
 
-    uint32_t red_threads = (uint32_t)p.windows * p.segs;
+    uint32_t red_threads = (uint32_t)p.windows * p.segs * 4;      // one quad per segment
     k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
         E.buckets.as<XYZZMem<F>>(), p, E.partials.as<XYZZMem<F>>());
     LAUNCH_CHECK();
-    constexpr int WS_THREADS = 64;
-    size_t ws_smem = WS_THREADS * sizeof(XYZZMem<F>);
+    constexpr int WS_THREADS = 256;                                // 64 quads per window
+    size_t ws_smem = (WS_THREADS / 4) * sizeof(XYZZMem<F>);
     k_window_sum<F, WS_THREADS><<<p.windows, WS_THREADS, ws_smem, st>>>(E.partials.as<XYZZMem<F>>(), p,
                                                                         E.window_sums.as<XYZZMem<F>>());
     LAUNCH_CHECK();

@@ -37,6 +37,10 @@ struct Fp2 {
     B200_DEV Fp2 dbl() const { return {c0.dbl(), c1.dbl()}; }
     B200_DEV Fp2 neg() const { return {c0.neg(), c1.neg()}; }
     B200_DEV Fp2 cneg(bool f) const { return {c0.cneg(f), c1.cneg(f)}; }
+    B200_DEV Fp2 shfl(unsigned mask, int src_lane) const { return {c0.shfl(mask, src_lane), c1.shfl(mask, src_lane)}; }
+    B200_DEV static Fp2 sel4(int q, const Fp2 &a0, const Fp2 &a1, const Fp2 &a2, const Fp2 &a3) {
+        return {B::sel4(q, a0.c0, a1.c0, a2.c0, a3.c0), B::sel4(q, a0.c1, a1.c1, a2.c1, a3.c1)};
+    }
     B200_DEV static B mul5(const B &a) {
         B t = a.dbl().dbl();
         return t + a;
@@ -254,5 +258,83 @@ struct XYZZ {
     }
     B200_DEV Jacobian<F> to_jacobian() const { return to_jacobian_outline(*this); }
 };
+
+// ---------------- quad-cooperative point operations ------------------------------------------
+// The tail of the MSM (bucket reduction, window sums, Horner combine) is a few thousand
+// point operations deep but only a few thousand threads wide: it is bound by the LATENCY of
+// dependent field products (about 0.94 us each in one warp, profiles/r1_field_layer_notes.md),
+// and most of the GPU idles.  Four consecutive lanes (a "quad") therefore share one point
+// operation: all four hold identical copies of the operands, each computes ONE of the up to
+// four independent products of a round, and the products are exchanged with shuffles.  An
+// XYZZ addition drops from 14 sequential products to 4 rounds, a doubling from 9 to 3.
+struct Quad {
+    int q, base;
+    unsigned mask;
+    B200_DEV Quad() {
+        int lane = threadIdx.x & 31;
+        q = lane & 3;
+        base = lane & ~3;
+        mask = 0xFu << base;
+    }
+    // p_k = a_k * b_k for k = 0..3, every lane receives all four
+    template <class F>
+    B200_DEV void mul4(const F &a0, const F &b0, const F &a1, const F &b1, const F &a2, const F &b2, const F &a3,
+                       const F &b3, F &p0, F &p1, F &p2, F &p3) const {
+        F p = F::sel4(q, a0, a1, a2, a3) * F::sel4(q, b0, b1, b2, b3);
+        p0 = p.shfl(mask, base);
+        p1 = p.shfl(mask, base + 1);
+        p2 = p.shfl(mask, base + 2);
+        p3 = p.shfl(mask, base + 3);
+    }
+};
+
+// dbl-2008-s-1 in 3 rounds.  All lanes of the quad must call with identical arguments.
+template <class F>
+B200_DEV void quad_dbl(const Quad &Q, XYZZ<F> &a) {
+    if (a.is_inf()) return;
+    F u = a.y.dbl();
+    F v, xx, d0, d1;
+    Q.mul4(u, u, a.x, a.x, u, u, a.x, a.x, v, xx, d0, d1);
+    F m = xx.dbl() + xx;
+    F w, s, mm, zz3;
+    Q.mul4(u, v, a.x, v, m, m, v, a.zz, w, s, mm, zz3);
+    F x3 = mm - s.dbl();
+    F t1, t2, zzz3;
+    Q.mul4(m, s - x3, w, a.y, w, a.zzz, w, a.zzz, t1, t2, zzz3, d0);
+    a.x = x3;
+    a.y = t1 - t2;
+    a.zz = zz3;
+    a.zzz = zzz3;
+}
+
+// add-2008-s in 4 rounds (exceptional cases exact, as in XYZZ::add_outline).
+template <class F>
+B200_DEV void quad_add(const Quad &Q, XYZZ<F> &a, const XYZZ<F> &o) {
+    if (o.is_inf()) return;
+    if (a.is_inf()) {
+        a = o;
+        return;
+    }
+    F u1, u2, s1, s2;
+    Q.mul4(a.x, o.zz, o.x, a.zz, a.y, o.zzz, o.y, a.zzz, u1, u2, s1, s2);
+    F p = u2 - u1;
+    F r = s2 - s1;
+    if (p.is_zero()) {
+        if (r.is_zero()) quad_dbl(Q, a);
+        else a = XYZZ<F>::inf();
+        return;
+    }
+    F pp, rr, zza, zzza;
+    Q.mul4(p, p, r, r, a.zz, o.zz, a.zzz, o.zzz, pp, rr, zza, zzza);
+    F ppp, qq, zz3, d0;
+    Q.mul4(p, pp, u1, pp, zza, pp, zza, pp, ppp, qq, zz3, d0);
+    F x3 = rr - ppp - qq.dbl();
+    F t1, t2, zzz3;
+    Q.mul4(r, qq - x3, s1, ppp, zzza, ppp, zzza, ppp, t1, t2, zzz3, d0);
+    a.x = x3;
+    a.y = t1 - t2;
+    a.zz = zz3;
+    a.zzz = zzz3;
+}
 
 }  // namespace b200

@@ -110,6 +110,24 @@ struct Fp {
     B200_DEV static Fp from_ark(const Mem &m) { return load(m); }
     B200_DEV Mem to_ark() const { return store(); }
 
+    // lane exchange / selection helpers for the quad-cooperative point operations (ec.cuh)
+    B200_DEV Fp shfl(unsigned mask, int src_lane) const {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = __shfl_sync(mask, l[i], src_lane);
+        return r;
+    }
+    B200_DEV static Fp sel4(int q, const Fp &a0, const Fp &a1, const Fp &a2, const Fp &a3) {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t lo = (q & 1) ? a1.l[i] : a0.l[i];
+            uint32_t hi = (q & 1) ? a3.l[i] : a2.l[i];
+            r.l[i] = (q & 2) ? hi : lo;
+        }
+        return r;
+    }
+
     B200_DEV bool is_zero() const {
         uint32_t o = 0;
 #pragma unroll

@@ -244,69 +244,74 @@ k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__re
     buckets[id] = acc.store();
 }
 
-// ---- bucket reduction ----------------------------------------------------------------------
+// ---- bucket reduction (quad-cooperative: 4 lanes per point operation, see ec.cuh) -----------
 // k * p for small k (double-and-add, MSB first)
 template <class F>
-B200_DEV XYZZ<F> small_mul(const XYZZ<F> &p, uint32_t k) {
+B200_DEV XYZZ<F> quad_small_mul(const Quad &Q, const XYZZ<F> &p, uint32_t k) {
     XYZZ<F> r = XYZZ<F>::inf();
     for (int b = 31 - __clz(k | 1u); b >= 0; b--) {
-        r.dbl();
-        if ((k >> b) & 1u) r.add(p);
+        quad_dbl(Q, r);
+        if ((k >> b) & 1u) quad_add(Q, r, p);
     }
     return r;
 }
 
-// thread (w, seg): partial = sum_{j < L} (seg*L + j + 1) * B[w][seg*L + j]
+// quad (w, seg): partial = sum_{j < L} (seg*L + j + 1) * B[w][seg*L + j]
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__restrict__ buckets, MsmPlan p,
                                                            XYZZMem<F> *__restrict__ partials) {
-    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    const Quad Q;
+    uint32_t t = (blockIdx.x * THREADS + threadIdx.x) >> 2;
     uint32_t total = (uint32_t)p.windows * p.segs;
-    if (t >= total) return;
+    if (t >= total) return;                          // whole quads leave together (THREADS % 4 == 0)
     uint32_t w = t / p.segs, seg = t % p.segs;
     const XYZZMem<F> *b = buckets + (size_t)w * p.nb + (size_t)seg * p.seg_len;
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
     for (int j = p.seg_len - 1; j >= 0; j--) {
-        run.add(XYZZ<F>::load(ldg_mem(b + j)));
-        acc.add(run);
+        quad_add(Q, run, XYZZ<F>::load(ldg_mem(b + j)));
+        quad_add(Q, acc, run);
     }
-    if (seg) acc.add(small_mul(run, seg * (uint32_t)p.seg_len));
-    partials[t] = acc.store();
+    if (seg) quad_add(Q, acc, quad_small_mul(Q, run, seg * (uint32_t)p.seg_len));
+    if (Q.q == 0) partials[t] = acc.store();
 }
 
-// block w: window_sums[w] = sum of the window's partials
+// block w: window_sums[w] = sum of the window's partials (THREADS / 4 quads, tree in smem)
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__restrict__ partials, MsmPlan p,
                                                         XYZZMem<F> *__restrict__ window_sums) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XYZZMem<F> *sm = reinterpret_cast<XYZZMem<F> *>(smem_raw);
+    constexpr int QUADS = THREADS / 4;
+    const Quad Q;
+    const int quad = threadIdx.x >> 2;
     const XYZZMem<F> *src = partials + (size_t)blockIdx.x * p.segs;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t i = threadIdx.x; i < p.segs; i += THREADS) acc.add(XYZZ<F>::load(ldg_mem(src + i)));
-    sm[threadIdx.x] = acc.store();
+    for (uint32_t i = quad; i < p.segs; i += QUADS) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(src + i)));
+    if (Q.q == 0) sm[quad] = acc.store();
     __syncthreads();
-    for (int s = THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            acc.add(XYZZ<F>::load(sm[threadIdx.x + s]));
-            sm[threadIdx.x] = acc.store();
+    for (int s = QUADS / 2; s > 0; s >>= 1) {
+        if (quad < s) {
+            quad_add(Q, acc, XYZZ<F>::load(sm[quad + s]));
+            if (Q.q == 0) sm[quad] = acc.store();
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) window_sums[blockIdx.x] = acc.store();
 }
 
-// one thread: Horner over the windows, high to low; result leaves in arkworks radix
+// one quad: Horner over the windows, high to low; result leaves as an arkworks GroupProjective
 template <class F>
-__global__ void k_window_combine(const XYZZMem<F> *__restrict__ window_sums, MsmPlan p,
-                                 JacobianMem<F> *__restrict__ out) {
-    if (threadIdx.x || blockIdx.x) return;
-    Jacobian<F> total = Jacobian<F>::inf();
+__global__ void __launch_bounds__(32) k_window_combine(const XYZZMem<F> *__restrict__ window_sums, MsmPlan p,
+                                                       JacobianMem<F> *__restrict__ out) {
+    if (blockIdx.x || threadIdx.x >= 4) return;
+    const Quad Q;
+    XYZZ<F> total = XYZZ<F>::inf();
     for (int w = p.windows - 1; w >= 0; w--) {
-        total.add(XYZZ<F>::load(window_sums[w]).to_jacobian());
+        quad_add(Q, total, XYZZ<F>::load(ldg_mem(window_sums + w)));
         if (w)
-            for (int k = 0; k < p.c; k++) total.dbl();
+            for (int k = 0; k < p.c; k++) quad_dbl(Q, total);
     }
-    *out = total.to_ark();
+    if (Q.q == 0) *out = total.to_jacobian().to_ark();
 }
 
 // ---- layout + radix conversion: arkworks GroupAffine records -> native packed images ---------
