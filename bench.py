@@ -206,16 +206,13 @@ def run_b200(args):
         sets.append((d_bases, d_sc, sc))
     torch.cuda.synchronize()
 
-    d_part = torch.zeros(144, dtype=torch.uint8, device=dev)
-    d_all = torch.zeros(world * 144, dtype=torch.uint8, device=dev)
-    d_res = torch.zeros(144, dtype=torch.uint8, device=dev)
+    from celo_bls_snark_rs_b200.sharded import ShardedMsm
+    job = ShardedMsm(cid, dev)
+    d_part, d_all, d_res = job.partial, job.gathered, job.result
 
     def step(i):
         d_bases, d_sc, _ = sets[i & 1]
-        E.msm_device(cid, d_bases.data_ptr(), d_sc.data_ptr(), n, d_part.data_ptr(), sp)
-        if world > 1:
-            dist.all_gather_into_tensor(d_all, d_part)
-            E.sum_jacobian_device(cid, d_all.data_ptr(), world, d_res.data_ptr(), sp)
+        job.run(d_bases, d_sc, n, sp)          # local MSM [-> all-gather of partials -> local sum]
 
     def barrier():
         if world > 1:

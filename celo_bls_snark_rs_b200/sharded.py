@@ -1,0 +1,57 @@
+"""Chunk-sharded MSM across the GPUs of one box.
+
+An MSM is a sum, so the (base, scalar) arrays are split into `world` contiguous chunks, every
+rank reduces its chunk to one partial Jacobian point with the local bucket MSM, and the single
+exchange step is an all-gather of those partials (144 or 288 bytes each) followed by a local
+sum on every rank.  NCCL cannot reduce elliptic-curve points, hence all-gather + add rather
+than all-reduce.  torch.distributed provides the plumbing; the arithmetic stays in the CUDA
+library (engine.sum_jacobian_device).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import engine as E
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous chunk [lo, hi) of rank `rank`; the first n % world ranks get one extra pair."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_partials(partial: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather of one partial result per rank: uint8 [jac_bytes] -> uint8 [world * jac_bytes],
+    rank-major.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    world = dist.get_world_size(group)
+    out = torch.empty(world * partial.numel(), dtype=partial.dtype, device=partial.device)
+    dist.all_gather_into_tensor(out, partial.contiguous(), group=group)
+    return out
+
+
+class ShardedMsm:
+    """Per-rank state of a sharded MSM: the local chunk stays resident in HBM."""
+
+    def __init__(self, curve: int, device: torch.device, group=None):
+        self.curve, self.device, self.group = curve, device, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        jb = E.JAC_BYTES[curve]
+        self.partial = torch.zeros(jb, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(self.world * jb, dtype=torch.uint8, device=device)
+        self.result = torch.zeros(jb, dtype=torch.uint8, device=device)
+
+    def run(self, d_bases: torch.Tensor, d_scalars: torch.Tensor, n_local: int, stream: int = 0) -> torch.Tensor:
+        """Local MSM over this rank's chunk, exchange, combine.  Asynchronous on `stream`
+        (which must be torch's current stream so NCCL orders after the MSM)."""
+        E.msm_device(self.curve, d_bases.data_ptr(), d_scalars.data_ptr(), n_local, self.partial.data_ptr(), stream)
+        if self.world == 1:
+            return self.partial
+        dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
+        E.sum_jacobian_device(self.curve, self.gathered.data_ptr(), self.world, self.result.data_ptr(), stream)
+        return self.result

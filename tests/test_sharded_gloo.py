@@ -1,0 +1,78 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the chunk partition + all-gather of partial
+results.  The per-rank MSM and the final point sum are done by the CPU oracle here (there is no
+GPU); what is under test is the partitioning and the exchange layout used by ShardedMsm."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from celo_bls_snark_rs_b200 import sharded
+from oracle import cref as C
+from oracle import inputs as H
+from oracle import oracle as O
+
+
+def test_shard_bounds_cover_everything_once():
+    for n in (0, 1, 7, 8, 1000, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            spans = [sharded.shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharded.shard_bounds(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        name = "bls12_377_g1"
+        L = C.LAYOUTS[name]
+        pts, scalars = H.edge_case_inputs(name, n, 5150)          # same seeded inputs on every rank
+        lo, hi = sharded.shard_bounds(n, world, rank)
+        part = C.msm(L, L.affine_records(pts[lo:hi]), L.scalars_array(scalars[lo:hi]), threads=1)
+        t = torch.from_numpy(np.frombuffer(part, dtype=np.uint8).copy())
+        gathered = sharded.gather_partials(t)
+        assert gathered.numel() == world * L.jac_bytes
+        raw = gathered.numpy().tobytes()
+        assert raw[rank * L.jac_bytes:(rank + 1) * L.jac_bytes] == part    # rank-major layout
+        total = None
+        for r in range(world):
+            total = L.curve.padd(total, L.jacobian_to_affine(raw[r * L.jac_bytes:(r + 1) * L.jac_bytes]))
+        q.put((rank, O.serialize_compressed(L.curve, total)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_msm_matches_single_msm():
+    n, world = 101, 2
+    name = "bls12_377_g1"
+    L = C.LAYOUTS[name]
+    pts, scalars = H.edge_case_inputs(name, n, 5150)
+    want = O.serialize_compressed(L.curve, L.curve.msm_naive(pts, scalars))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == want and got[1] == want
