@@ -84,7 +84,8 @@ void b200_shutdown(void) {
     cudaSetDevice(E->device);
     cudaStreamSynchronize(E->stream);
     for (Buffer *b : {&E->counts, &E->offsets, &E->cursor, &E->tile_sums, &E->bins, &E->order, &E->sorted, &E->buckets,
-                      &E->partials, &E->window_sums, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result})
+                      &E->partials, &E->window_sums, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
+                      &E->miller, &E->g2_packed, &E->h2d_g2})
         b->release();
     for (auto &ev : E->prof_ev)
         if (ev) cudaEventDestroy(ev);
@@ -198,6 +199,61 @@ int b200_batch_to_affine_device(int curve, const void *d_jacobian, size_t n, voi
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
     return DISPATCH_CURVE(curve, batch_to_affine, d_jacobian, n, d_out_packed, st);
+}
+
+int b200_miller_product_bls12_377_device(const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out_fq12,
+                                         void *stream) {
+    if (!d_out_fq12 || (n && (!d_g1_packed || !d_g2_packed))) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    int rc = miller_product(E, d_g1_packed, d_g2_packed, n, d_out_fq12, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(E.done, st));
+    E.has_pending = true;
+    return B200_OK;
+}
+
+int b200_final_exp_bls12_377_device(const void *d_fq12_vals, size_t count, void *d_out_fq12, int *d_is_one,
+                                    void *stream) {
+    if (!d_fq12_vals || count == 0) return fail(B200_ERR_ARG, "null pointer / empty input");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    int rc = final_exp(E, d_fq12_vals, count, d_out_fq12, d_is_one, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(E.done, st));
+    E.has_pending = true;
+    return B200_OK;
+}
+
+int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
+                                 void *out_fq12, int *out_is_one) {
+    if (n && (!g1 || !g2)) return fail(B200_ERR_ARG, "null pointer");
+    if (!out_fq12 && !out_is_one) return fail(B200_ERR_ARG, "no output requested");
+    REQUIRE_ENGINE();
+    cudaStream_t st = E.stream;
+    int rc;
+    if ((rc = E.result.reserve(576 + 16))) return rc;
+    if (n) {
+        if (stride1 % 4 || stride1 < 96 || stride2 % 4 || stride2 < 192) return fail(B200_ERR_ARG, "bad stride");
+        if ((rc = E.h2d_bases.reserve(n * stride1)) || (rc = E.h2d_g2.reserve(n * stride2)) ||
+            (rc = E.native_bases.reserve(n * 96)) || (rc = E.g2_packed.reserve(n * 192)))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, g1, n * stride1, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(E.h2d_g2.p, g2, n * stride2, cudaMemcpyHostToDevice, st));
+        if ((rc = pack_bases<G1_377>(E.h2d_bases.p, stride1, n, E.native_bases.p, st))) return rc;
+        if ((rc = pack_bases<G2_377>(E.h2d_g2.p, stride2, n, E.g2_packed.p, st))) return rc;
+    }
+    char *res = E.result.as<char>();
+    if ((rc = miller_product(E, E.native_bases.p, E.g2_packed.p, n, res, st))) return rc;
+    if ((rc = final_exp(E, res, 1, res, reinterpret_cast<int *>(res + 576), st))) return rc;
+    if (out_fq12) CUDA_TRY(cudaMemcpyAsync(out_fq12, res, 576, cudaMemcpyDeviceToHost, st));
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, res + 576, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (out_is_one) *out_is_one = flag;
+    return B200_OK;
 }
 
 int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream) {

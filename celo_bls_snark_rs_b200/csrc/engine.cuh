@@ -62,6 +62,8 @@ struct Engine {
     Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums;
     // staging for the host-pointer API
     Buffer h2d_bases, native_bases, scalars, result;
+    // multi-pairing: Miller values, packed G2 staging
+    Buffer miller, g2_packed, h2d_g2;
     // optional timing of the dominant kernel (b200_profile_*): event pairs around k_bucket_accumulate
     bool profile = false;
     static constexpr int PROF_SLOTS = 256;
@@ -83,5 +85,9 @@ template <class C> int fixed_base_mul(Engine &E, const void *base, const void *s
 template <class C> int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st);
 template <class C> int plan_query(size_t n, int *c, int *w, uint32_t *nb);
 template <class C> int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStream_t st);
+
+// BLS12-377 multi-pairing (inst_pairing.cu)
+int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out, cudaStream_t st);
+int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_is_one, cudaStream_t st);
 
 }  // namespace b200

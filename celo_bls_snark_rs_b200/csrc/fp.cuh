@@ -67,6 +67,16 @@ B200_DEV void madc_wide_top(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) 
     asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 
+// Compiler fence for large aggregates.  cicc (CUDA 12.9) was caught forwarding a stale source
+// into a by-value argument: after `Fq12 r = f;` every `r = f12_sqr(r)` of a loop squared f, not
+// r (the PTX re-stored f's registers into the argument slot at the loop head).  Escaping the
+// object's address into an asm with a memory clobber makes the copy opaque and stops the
+// forwarding.  Used after every copy-initialisation / loop-carried assignment of a large aggregate (Fq12, and the cold MSM helper kernels).
+template <class T>
+B200_DEV void launder(T &x) {
+    asm volatile("" : : "l"(&x) : "memory");
+}
+
 template <int NW>
 struct alignas(16) FpMem {                         // memory image: NW little-endian 32-bit words
     uint32_t w[NW];

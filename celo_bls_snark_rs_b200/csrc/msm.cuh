@@ -342,7 +342,11 @@ template <class F>
 __global__ void k_sum_jacobian(const JacobianMem<F> *__restrict__ pts, uint32_t count, JacobianMem<F> *__restrict__ out) {
     if (threadIdx.x || blockIdx.x) return;
     Jacobian<F> total = Jacobian<F>::inf();
-    for (uint32_t i = 0; i < count; i++) total.add(Jacobian<F>::from_ark(pts[i]));
+    launder(total);
+    for (uint32_t i = 0; i < count; i++) {
+        total.add(Jacobian<F>::from_ark(pts[i]));
+        launder(total);
+    }
     *out = total.to_ark();
 }
 
@@ -359,7 +363,11 @@ __global__ void __launch_bounds__(THREADS) k_fixed_base_mul(const AffineMem<F> *
         uint32_t word = __ldg(scalars + (size_t)i * SW + w);
         for (int b = 31; b >= 0; b--) {
             r.dbl();
-            if ((word >> b) & 1u) r.madd(g.x, g.y);
+            launder(r);
+            if ((word >> b) & 1u) {
+                r.madd(g.x, g.y);
+                launder(r);
+            }
         }
     }
     out[i] = r.store();
@@ -413,6 +421,7 @@ __global__ void __launch_bounds__(THREADS) k_jacobian_to_affine(const JacobianMe
     for (uint32_t k = 0; k < cnt; k++) {
         F z = F::from_ark(ldg_mem(&in[first + k].z));
         if (!z.is_zero()) run = run * z;
+        launder(run);
         prefix[k] = run;
     }
     F iv = FieldInv<F>::inv(run);
@@ -423,6 +432,7 @@ __global__ void __launch_bounds__(THREADS) k_jacobian_to_affine(const JacobianMe
             F zi = iv;                               // 1 / z_k
             if (k) zi = zi * prefix[k - 1];
             iv = iv * p.z;
+            launder(iv);
             F zi2 = zi.sqr();
             r.x = p.x * zi2;
             r.y = p.y * (zi2 * zi);

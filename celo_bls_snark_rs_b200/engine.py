@@ -30,7 +30,8 @@ EXPORTS = [
     "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device", "b200_msm_prepared_device",
     "b200_sum_jacobian_device", "b200_fixed_base_mul_device", "b200_batch_to_affine_device", "b200_sync",
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
-    "b200_field_op_device",
+    "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
+    "b200_final_exp_bls12_377_device",
 ]
 
 
@@ -62,6 +63,9 @@ def load() -> ctypes.CDLL:
     lib.b200_fixed_base_mul_device.argtypes = [i32, vp, vp, sz, vp, vp]
     lib.b200_batch_to_affine_device.argtypes = [i32, vp, sz, vp, vp]
     lib.b200_field_op_device.argtypes = [i32, i32, vp, vp, sz, vp, vp]
+    lib.b200_multi_pairing_bls12_377.argtypes = [vp, sz, vp, sz, sz, vp, ctypes.POINTER(i32)]
+    lib.b200_miller_product_bls12_377_device.argtypes = [vp, vp, sz, vp, vp]
+    lib.b200_final_exp_bls12_377_device.argtypes = [vp, sz, vp, vp, vp]
     lib.b200_sync.argtypes = [vp]
     lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
     lib.b200_launch_count.restype = ctypes.c_uint64
@@ -146,6 +150,33 @@ FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5, "dbl": 
 
 def field_op_device(curve: int, op: str, d_a: int, d_b: int, n: int, d_out: int, stream: int = 0):
     _check(load().b200_field_op_device(curve, FIELD_OPS[op], d_a, d_b, n, d_out, stream or None))
+
+
+FQ12_BYTES = 576
+
+
+def multi_pairing(g1: np.ndarray, g2: np.ndarray, n: Optional[int] = None, want_gt: bool = True):
+    """Host-pointer product of pairings over BLS12-377 (b200_multi_pairing_bls12_377).
+    g1: uint8 [n, 104 | 96], g2: uint8 [n, 200 | 192].  Returns (is_one, gt_bytes | None)."""
+    g1 = np.ascontiguousarray(g1)
+    g2 = np.ascontiguousarray(g2)
+    if n is None:
+        n = min(len(g1), len(g2))
+    s1 = g1.strides[0] if n else 104
+    s2 = g2.strides[0] if n else 200
+    out = np.zeros(FQ12_BYTES, dtype=np.uint8)
+    flag = ctypes.c_int(0)
+    _check(load().b200_multi_pairing_bls12_377(_hptr(g1), s1, _hptr(g2), s2, n, _hptr(out) if want_gt else None,
+                                               ctypes.byref(flag)))
+    return bool(flag.value), (out.tobytes() if want_gt else None)
+
+
+def miller_product_device(d_g1: int, d_g2: int, n: int, d_out: int, stream: int = 0):
+    _check(load().b200_miller_product_bls12_377_device(d_g1, d_g2, n, d_out, stream or None))
+
+
+def final_exp_device(d_vals: int, count: int, d_out: int, d_is_one: int = 0, stream: int = 0):
+    _check(load().b200_final_exp_bls12_377_device(d_vals, count, d_out or None, d_is_one or None, stream or None))
 
 
 def profile_enable(on: bool = True):

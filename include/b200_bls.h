@@ -101,6 +101,26 @@ int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void 
  * d_out_packed receives packed affine records, infinity as (0, 0). */
 int b200_batch_to_affine_device(int curve, const void *d_jacobian, size_t n, void *d_out_packed, void *stream);
 
+/* ---- multi-pairing: replaces Bls12_377::product_of_pairings ---------------------------------
+ *   crates/bls-crypto/src/bls/signature.rs:149  (batch_verify_hashes: (sigma, -g2), (H_i, pk_i) ...)
+ *   crates/bls-crypto/src/bls/public.rs:102     (verify_sig: 2 pairs)
+ * g1: n G1Affine records at stride1 bytes (104 arkworks / 96 packed), g2: n G2Affine records at
+ * stride2 (200 / 192).  Pairs with an infinite member are skipped, as arkworks does.
+ * out_fq12 (may be NULL) receives the GT element as arkworks' Fq12 image: 12 Fq Montgomery
+ * residues in the order c0.c0.c0, c0.c0.c1, c0.c1.c0, ... c1.c2.c1 (576 bytes).
+ * out_is_one (may be NULL) receives 1 iff the product of pairings equals Fq12::one() -- the
+ * comparison the reference makes at signature.rs:150 / public.rs:115. */
+int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
+                                 void *out_fq12, int *out_is_one);
+/* Device-pointer halves, for pipelines and for sharding the pairs across GPUs:
+ * product of the Miller values of n pairs (packed records) -> one Fq12 image; then the product
+ * of `count` such images (e.g. one per GPU after an all-gather) -> final exponentiation.
+ * d_is_one is a device int (may be NULL). */
+int b200_miller_product_bls12_377_device(const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out_fq12,
+                                         void *stream);
+int b200_final_exp_bls12_377_device(const void *d_fq12_vals, size_t count, void *d_out_fq12, int *d_is_one,
+                                    void *stream);
+
 /* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
  * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),
  * 6 double(a).  Exists so the field layer can be checked against the oracle directly. */

@@ -176,3 +176,21 @@ def with_flags(layout: CurveLayout, packed: np.ndarray) -> np.ndarray:
     out = np.zeros((len(packed), layout.ark_stride), dtype=np.uint8)
     out[:, :layout.packed_stride] = packed
     return out
+
+
+# ---- BLS12-377 GT codec (arkworks Fq12 image: 12 Montgomery Fq residues, tower order) ----------
+def fq12_to_ark_bytes(f) -> bytes:
+    L = LAYOUTS["bls12_377_g1"]
+    out = b""
+    for c6 in f:                 # c0, c1 (Fq6)
+        for c2 in c6:            # c0, c1, c2 (Fq2)
+            for c in c2:         # c0, c1 (Fq)
+                out += L.fe_to_mont_bytes(c)
+    return out
+
+
+def fq12_from_ark_bytes(raw: bytes):
+    L = LAYOUTS["bls12_377_g1"]
+    vals = [L.fe_from_mont_bytes(raw[48 * i:48 * (i + 1)]) for i in range(12)]
+    f2 = [(vals[2 * i], vals[2 * i + 1]) for i in range(6)]
+    return ((f2[0], f2[1], f2[2]), (f2[3], f2[4], f2[5]))

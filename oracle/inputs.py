@@ -54,3 +54,26 @@ def edge_case_inputs(name, n, seed):
         pts[6], scalars[6] = L.curve.pneg(pts[5]), scalars[5]    # P + (-P)
         pts[7] = None                                            # infinity base
     return pts, scalars
+
+
+def signature_batch(n, seed, corrupt=None):
+    """n (pk_i, H_i) pairs plus the aggregate signature, as in Signature::batch_verify_hashes
+    (crates/bls-crypto/src/bls/signature.rs:125-155): pk_i = sk_i * g2, H_i = h_i * g1,
+    sigma = sum sk_i * H_i.  Returns the (G1 list, G2 list) of the N + 1 pairs, first pair
+    (sigma, -g2).  corrupt = index of a message hash to replace (verification must then fail)."""
+    L1, L2 = C.LAYOUTS["bls12_377_g1"], C.LAYOUTS["bls12_377_g2"]
+    rng = O.SplitMix64(seed)
+    sks = [rng.below(O.R - 1) + 1 for _ in range(n)]
+    hs = [rng.below(O.R - 1) + 1 for _ in range(n)]
+    pks = L2.affine_from_records(C.fixed_base_batch(L2, O.G2_GEN, sks))
+    if corrupt is not None:
+        hs_used = list(hs)
+        hs_used[corrupt] = (hs[corrupt] + 1) % O.R or 1
+    else:
+        hs_used = hs
+    hashes = L1.affine_from_records(C.fixed_base_batch(L1, O.G1_GEN, hs_used))
+    sig_scalar = sum(s * h for s, h in zip(sks, hs)) % O.R
+    sigma = L1.jacobian_to_affine(C.scalar_mul(L1, O.G1_GEN, sig_scalar))
+    g1s = [sigma] + hashes
+    g2s = [O.G2.pneg(O.G2_GEN)] + pks
+    return g1s, g2s

@@ -1,0 +1,84 @@
+"""BLS12-377 multi-pairing on the GPU (through the C-ABI) vs the Python oracle's restatement of
+Bls12::product_of_pairings, and the behavioural suite of signature.rs:329-426 restated."""
+import numpy as np
+import pytest
+
+from oracle import cref as C
+from oracle import inputs as H
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+L1, L2 = C.LAYOUTS["bls12_377_g1"], C.LAYOUTS["bls12_377_g2"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from celo_bls_snark_rs_b200 import engine as E
+    E.init(0)
+    return E
+
+
+def _random_pairs(n, seed):
+    rng = O.SplitMix64(seed)
+    g1 = L1.affine_from_records(C.fixed_base_batch(L1, O.G1_GEN, [rng.below(O.R) for _ in range(n)]))
+    g2 = L2.affine_from_records(C.fixed_base_batch(L2, O.G2_GEN, [rng.below(O.R) for _ in range(n)]))
+    return g1, g2
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 6])
+def test_gt_bytes_match_oracle(eng, n):
+    g1, g2 = _random_pairs(n, 900 + n)
+    if n >= 3:
+        g1[1] = None                                   # a pair with an infinite member is skipped
+    if n >= 6:
+        g2[4] = None
+    want = O.product_of_pairings(list(zip(g1, g2)))
+    is_one, gt = eng.multi_pairing(L1.affine_records(g1), L2.affine_records(g2), n)
+    assert gt == C.fq12_to_ark_bytes(want)
+    assert is_one == (want == O.FQ12_ONE)
+    # packed records (no flag byte) give the same element
+    is_one2, gt2 = eng.multi_pairing(L1.affine_records(g1, L1.packed_stride), L2.affine_records(g2, L2.packed_stride), n)
+    assert gt2 == gt and is_one2 == is_one
+
+
+def test_bilinearity_on_device(eng):
+    a, b = 0x1234567, 0x7654321
+    e_ab = eng.multi_pairing(L1.affine_records([O.G1.pmul(O.G1_GEN, a)]), L2.affine_records([O.G2.pmul(O.G2_GEN, b)]))[1]
+    e_1 = eng.multi_pairing(L1.affine_records([O.G1.pmul(O.G1_GEN, a * b % O.R)]), L2.affine_records([O.G2_GEN]))[1]
+    assert e_ab == e_1
+
+
+@pytest.mark.parametrize("n", [1, 7, 300])
+def test_batch_verify_hashes_semantics(eng, n):
+    """Signature::batch_verify_hashes: (sigma, -g2), (H_i, pk_i) -> product == 1; any single
+    corrupted message hash -> verification fails (signature.rs:329-361, :390-426)."""
+    g1, g2 = H.signature_batch(n, 77 + n)
+    ok, _ = eng.multi_pairing(L1.affine_records(g1), L2.affine_records(g2), want_gt=False)
+    assert ok is True
+    g1b, g2b = H.signature_batch(n, 77 + n, corrupt=n // 2)
+    bad, _ = eng.multi_pairing(L1.affine_records(g1b), L2.affine_records(g2b), want_gt=False)
+    assert bad is False
+    if n <= 7:
+        assert O.batch_verify_hashes(g1[0], g2[1:], g1[1:]) is True
+
+
+def test_sharded_miller_products_equal_single_shot(eng):
+    """Pairs split in two chunks (as across two GPUs): Miller products, then one final
+    exponentiation over both -> identical GT bytes."""
+    import torch
+    dev = torch.device("cuda:0")
+    n = 10
+    g1, g2 = H.signature_batch(n - 1, 5)
+    r1 = torch.from_numpy(L1.affine_records(g1, L1.packed_stride).copy()).to(dev)
+    r2 = torch.from_numpy(L2.affine_records(g2, L2.packed_stride).copy()).to(dev)
+    parts = torch.zeros((2, 576), dtype=torch.uint8, device=dev)
+    out = torch.zeros(576, dtype=torch.uint8, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    k = 4
+    eng.miller_product_device(r1.data_ptr(), r2.data_ptr(), k, parts[0].data_ptr())
+    eng.miller_product_device(r1[k:].data_ptr(), r2[k:].data_ptr(), n - k, parts[1].data_ptr())
+    eng.final_exp_device(parts.data_ptr(), 2, out.data_ptr(), flag.data_ptr())
+    eng.sync()
+    single_ok, single_gt = eng.multi_pairing(L1.affine_records(g1), L2.affine_records(g2))
+    assert out.cpu().numpy().tobytes() == single_gt
+    assert bool(flag.item()) == single_ok == True  # noqa: E712
