@@ -85,7 +85,7 @@ void b200_shutdown(void) {
     cudaStreamSynchronize(E->stream);
     for (Buffer *b : {&E->counts, &E->offsets, &E->cursor, &E->tile_sums, &E->bins, &E->order, &E->sorted, &E->buckets,
                       &E->partials, &E->window_sums, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff})
         b->release();
     for (auto &ev : E->prof_ev)
         if (ev) cudaEventDestroy(ev);
@@ -254,6 +254,21 @@ int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2,
     CUDA_TRY(cudaStreamSynchronize(st));
     if (out_is_one) *out_is_one = flag;
     return B200_OK;
+}
+
+int b200_batch_verify_hashes(const void *signature, const void *pubkeys, const void *message_hashes, size_t n,
+                             int *out_verified) {
+    if (!signature || !out_verified || (n && (!pubkeys || !message_hashes))) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    return batch_verify_hashes(E, signature, pubkeys, message_hashes, n, out_verified);
+}
+
+int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,
+                                  const void *message_hash, int *out_verified) {
+    if (!message_hash || !out_verified || (n && (!pubkeys || !signatures || !exponents)))
+        return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    return batch_verify_strict_hash(E, pubkeys, signatures, exponents, n, message_hash, out_verified);
 }
 
 int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream) {

@@ -47,7 +47,7 @@ int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_i
         k_fq12_product<128><<<1, 128, 0, st>>>(vals, (uint32_t)count);
         LAUNCH_CHECK();
     }
-    k_final_exp<<<1, 32, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one);
+    k_final_exp<<<1, 32, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one);   // d_out may be NULL
     LAUNCH_CHECK();
     return B200_OK;
 }

@@ -31,7 +31,7 @@ EXPORTS = [
     "b200_sum_jacobian_device", "b200_fixed_base_mul_device", "b200_batch_to_affine_device", "b200_sync",
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
-    "b200_final_exp_bls12_377_device",
+    "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
 ]
 
 
@@ -66,6 +66,8 @@ def load() -> ctypes.CDLL:
     lib.b200_multi_pairing_bls12_377.argtypes = [vp, sz, vp, sz, sz, vp, ctypes.POINTER(i32)]
     lib.b200_miller_product_bls12_377_device.argtypes = [vp, vp, sz, vp, vp]
     lib.b200_final_exp_bls12_377_device.argtypes = [vp, sz, vp, vp, vp]
+    lib.b200_batch_verify_hashes.argtypes = [vp, vp, vp, sz, ctypes.POINTER(i32)]
+    lib.b200_batch_verify_strict_hash.argtypes = [vp, vp, vp, sz, vp, ctypes.POINTER(i32)]
     lib.b200_sync.argtypes = [vp]
     lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
     lib.b200_launch_count.restype = ctypes.c_uint64

@@ -121,6 +121,24 @@ int b200_miller_product_bls12_377_device(const void *d_g1_packed, const void *d_
 int b200_final_exp_bls12_377_device(const void *d_fq12_vals, size_t count, void *d_out_fq12, int *d_is_one,
                                     void *stream);
 
+/* ---- the two batch-verification flows of bls-crypto, after message hashing -------------------
+ * Inputs are the Rust types' memory images: Signature = G1Projective (144 B), PublicKey =
+ * G2Projective (288 B), message hashes = G1Projective (what HashToCurve::hash returns).
+ * *out_verified = 1 iff the reference would return Ok(()).
+ *
+ * b200_batch_verify_hashes: Signature::batch_verify_hashes (signature.rs:125-155) --
+ *   into_affine() of all points, pairs (sigma, -g2), (H_i, pk_i), product == Fq12::one().
+ *   (Length mismatch is the caller's UnevenNumKeysMessages check, signature.rs:130-132.)
+ * b200_batch_verify_strict_hash: Batch::verify (batch.rs:44-84) with the exponents supplied by
+ *   the caller (the reference draws exp_size random bytes per entry, batch.rs:51-65, and calls
+ *   into_repr(): pass those canonical 4 x u64 values): batch_normalization_into_affine of the
+ *   keys and signatures, G2 MSM (public.rs:61), G1 MSM (signature.rs:85), then verify_sig
+ *   (public.rs:94-120) on the message hash. */
+int b200_batch_verify_hashes(const void *signature, const void *pubkeys, const void *message_hashes, size_t n,
+                             int *out_verified);
+int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,
+                                  const void *message_hash, int *out_verified);
+
 /* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
  * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),
  * 6 double(a).  Exists so the field layer can be checked against the oracle directly. */
