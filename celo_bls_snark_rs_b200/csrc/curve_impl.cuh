@@ -78,8 +78,9 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
         (rc = E.cursor.reserve(total * 4)) || (rc = E.tile_sums.reserve((size_t)tiles * 4)) ||
         (rc = E.bins.reserve(2 * SIZE_BINS * 4)) || (rc = E.order.reserve(total * 4)) ||
         (rc = E.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = E.buckets.reserve(total * sizeof(XYZZMem<F>))) ||
-        (rc = E.partials.reserve((size_t)p.windows * p.segs * sizeof(XYZZMem<F>))) ||
-        (rc = E.window_sums.reserve((size_t)p.windows * sizeof(XYZZMem<F>))))
+        (rc = E.partials.reserve(((size_t)p.windows * p.segs + ONES_PARTS) * sizeof(XYZZMem<F>))) ||
+        (rc = E.window_sums.reserve((size_t)(p.windows + 1) * sizeof(XYZZMem<F>))) ||
+        (rc = E.ones.reserve((n + 1) * 4)))
         return rc;
 
     if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
@@ -89,6 +90,7 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     uint32_t *bins = E.bins.as<uint32_t>();
     CUDA_TRY(cudaMemsetAsync(counts, 0, total * 4, st));
     CUDA_TRY(cudaMemsetAsync(bins, 0, 2 * SIZE_BINS * 4, st));
+    CUDA_TRY(cudaMemsetAsync(E.ones.p, 0, 4, st));
 
     int nblk = ceil_div(n, 256);
     k_digit_hist<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, counts);
@@ -99,7 +101,7 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     LAUNCH_CHECK();
     k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)total, E.tile_sums.as<uint32_t>(), offsets, cursor);
     LAUNCH_CHECK();
-    k_digit_scatter<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, cursor, E.sorted.as<uint32_t>());
+    k_digit_scatter<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, cursor, E.sorted.as<uint32_t>(), E.ones.as<uint32_t>());
     LAUNCH_CHECK();
     k_size_hist<<<std::min(ceil_div(total, 256), E.sm_count * 4), 256, 0, st>>>(counts, (uint32_t)total, bins);
     LAUNCH_CHECK();
@@ -122,13 +124,25 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
         E.prof_units += n;
     }
 
+    {   // over-populated buckets (skewed scalars) and unit scalars: bounded extra launches
+        constexpr int BT = T::RED_THREADS;                         // smem: BT XYZZ images (<= 24.5 KB)
+        uint32_t max_big = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / BIG_BUCKET + 1);
+        k_big_buckets<F, BT><<<max_big, BT, BT * sizeof(XYZZMem<F>), st>>>(
+            reinterpret_cast<const AffineMem<F> *>(d_bases), E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(),
+            bins, E.buckets.as<XYZZMem<F>>());
+        LAUNCH_CHECK();
+        k_ones_accumulate<F, BT><<<ONES_PARTS / BT, BT, 0, st>>>(
+            reinterpret_cast<const AffineMem<F> *>(d_bases), E.ones.as<uint32_t>(),
+            E.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs);
+        LAUNCH_CHECK();
+    }
     uint32_t red_threads = (uint32_t)p.windows * p.segs * 4;      // one quad per segment
     k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
         E.buckets.as<XYZZMem<F>>(), p, E.partials.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     constexpr int WS_THREADS = 256;                                // 64 quads per window
     size_t ws_smem = (WS_THREADS / 4) * sizeof(XYZZMem<F>);
-    k_window_sum<F, WS_THREADS><<<p.windows, WS_THREADS, ws_smem, st>>>(E.partials.as<XYZZMem<F>>(), p,
+    k_window_sum<F, WS_THREADS><<<p.windows + 1, WS_THREADS, ws_smem, st>>>(E.partials.as<XYZZMem<F>>(), p,
                                                                         E.window_sums.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     k_window_combine<F><<<1, 32, 0, st>>>(E.window_sums.as<XYZZMem<F>>(), p,

@@ -59,12 +59,24 @@ B200_DEV int signed_digit(const uint32_t *__restrict__ s, int w, int c, int &car
     return carry ? d - (1 << c) : d;
 }
 
+// scalar == 1: arkworks adds such bases once, outside the buckets; here
+// they go to a separate list summed by k_ones_accumulate -- Groth16 witnesses are mostly 0/1
+// (crates/epoch-snark/src/api/prover.rs:78), which would otherwise pile half the input into one bucket.
+template <int SW>
+B200_DEV bool scalar_is_one(const uint32_t *__restrict__ s) {
+    uint32_t o = __ldg(s) ^ 1u;
+#pragma unroll
+    for (int k = 1; k < SW; k++) o |= __ldg(s + k);
+    return o == 0;
+}
+
 template <int SW>
 __global__ void __launch_bounds__(256) k_digit_hist(const uint32_t *__restrict__ scalars, MsmPlan p,
                                                     uint32_t *__restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     const uint32_t *s = scalars + (size_t)i * SW;
+    if (scalar_is_one<SW>(s)) return;
     int carry = 0;
     for (int w = 0; w < p.windows; w++) {
         int d = signed_digit<SW>(s, w, p.c, carry);
@@ -74,10 +86,15 @@ __global__ void __launch_bounds__(256) k_digit_hist(const uint32_t *__restrict__
 
 template <int SW>
 __global__ void __launch_bounds__(256) k_digit_scatter(const uint32_t *__restrict__ scalars, MsmPlan p,
-                                                       uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+                                                       uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted,
+                                                       uint32_t *__restrict__ ones /*[0] = count, [1..] = indices*/) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n) return;
     const uint32_t *s = scalars + (size_t)i * SW;
+    if (scalar_is_one<SW>(s)) {
+        ones[1 + atomicAdd(ones, 1u)] = i;
+        return;
+    }
     int carry = 0;
     for (int w = 0; w < p.windows; w++) {
         int d = signed_digit<SW>(s, w, p.c, carry);
@@ -209,6 +226,10 @@ static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__r
     order[base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
+// buckets holding at least this many points (the top population bin of k_size_*) are summed by a
+// whole block instead of one thread: skewed scalar sets (many equal small scalars) stay bounded
+constexpr uint32_t BIG_BUCKET = SIZE_BINS - 1;
+
 // ---- bucket accumulation: the dominant kernel ---------------------------------------------
 // One thread per bucket.  bases are native-radix packed affine images (k_pack_bases output);
 // the next image is prefetched (still packed: 24 / 48 registers) while the current point is added.
@@ -221,6 +242,7 @@ k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__re
     if (t >= total_buckets) return;
     uint32_t id = order[t];
     uint32_t k = offsets[id], end = offsets[id + 1];
+    if (end - k >= BIG_BUCKET) return;               // left to k_big_buckets (one block per bucket)
     XYZZ<F> acc = XYZZ<F>::inf();
     if (k < end) {
         uint32_t e = __ldg(sorted + k);
@@ -242,6 +264,61 @@ k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__re
         }
     }
     buckets[id] = acc.store();
+}
+
+// block-wide sum of XYZZ values held one per thread (smem tree); result valid in thread 0
+template <class F, int THREADS>
+B200_DEV XYZZ<F> block_sum(XYZZ<F> acc, XYZZMem<F> *sm) {
+    sm[threadIdx.x] = acc.store();
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            acc.add(XYZZ<F>::load(sm[threadIdx.x + s]));
+            sm[threadIdx.x] = acc.store();
+        }
+        __syncthreads();
+    }
+    return acc;
+}
+
+// one block per over-populated bucket: order[] is sorted by population, so the first
+// bin_counts[top] entries are exactly the buckets k_bucket_accumulate skipped
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_big_buckets(const AffineMem<F> *__restrict__ bases,
+                                                         const uint32_t *__restrict__ sorted,
+                                                         const uint32_t *__restrict__ offsets,
+                                                         const uint32_t *__restrict__ order,
+                                                         const uint32_t *__restrict__ bin_counts,
+                                                         XYZZMem<F> *__restrict__ buckets) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (blockIdx.x >= bin_counts[SIZE_BINS - 1]) return;
+    uint32_t id = order[blockIdx.x];
+    uint32_t lo = offsets[id], hi = offsets[id + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = lo + threadIdx.x; k < hi; k += THREADS) {
+        uint32_t e = __ldg(sorted + k);
+        Affine<F> pt = Affine<F>::load(ldg_mem(bases + (e & 0x7fffffffu)));
+        if (!pt.is_inf()) acc.madd(pt.x, pt.y.cneg(e >> 31));
+    }
+    acc = block_sum<F, THREADS>(acc, reinterpret_cast<XYZZMem<F> *>(smem_raw));
+    if (threadIdx.x == 0) buckets[id] = acc.store();
+}
+
+// unit scalars: ONES_PARTS strided partial sums of the listed bases (weight 1, added after Horner)
+constexpr uint32_t ONES_PARTS = 8192;
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_ones_accumulate(const AffineMem<F> *__restrict__ bases,
+                                                             const uint32_t *__restrict__ ones,
+                                                             XYZZMem<F> *__restrict__ parts) {
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    if (t >= ONES_PARTS) return;
+    uint32_t count = ones[0];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = t; k < count; k += ONES_PARTS) {
+        Affine<F> pt = Affine<F>::load(ldg_mem(bases + __ldg(ones + 1 + k)));
+        if (!pt.is_inf()) acc.madd(pt.x, pt.y);
+    }
+    parts[t] = acc.store();
 }
 
 // ---- bucket reduction (quad-cooperative: 4 lanes per point operation, see ec.cuh) -----------
@@ -284,9 +361,12 @@ __global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__rest
     constexpr int QUADS = THREADS / 4;
     const Quad Q;
     const int quad = threadIdx.x >> 2;
-    const XYZZMem<F> *src = partials + (size_t)blockIdx.x * p.segs;
+    // blocks 0 .. windows-1: the window's segment partials; block `windows`: the unit-scalar partials
+    const bool ones_block = blockIdx.x == (uint32_t)p.windows;
+    const XYZZMem<F> *src = partials + (size_t)(ones_block ? p.windows : blockIdx.x) * p.segs;
+    const uint32_t count = ones_block ? ONES_PARTS : p.segs;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t i = quad; i < p.segs; i += QUADS) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(src + i)));
+    for (uint32_t i = quad; i < count; i += QUADS) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(src + i)));
     if (Q.q == 0) sm[quad] = acc.store();
     __syncthreads();
     for (int s = QUADS / 2; s > 0; s >>= 1) {
@@ -311,6 +391,7 @@ __global__ void __launch_bounds__(32) k_window_combine(const XYZZMem<F> *__restr
         if (w)
             for (int k = 0; k < p.c; k++) quad_dbl(Q, total);
     }
+    quad_add(Q, total, XYZZ<F>::load(ldg_mem(window_sums + p.windows)));      // bases with scalar == 1
     if (Q.q == 0) *out = total.to_jacobian().to_ark();
 }
 

@@ -154,3 +154,32 @@ def test_fixed_base_mul_matches_oracle(eng, name):
     got = L.affine_from_records(d_o.cpu().numpy())
     want = [L.jacobian_to_affine(C.scalar_mul(L, g, k)) for k in ks]
     assert got == want
+
+
+@pytest.mark.parametrize("name,n", [("bls12_377_g1", 1 << 15), ("bw6_761_g1", 1 << 13), ("bls12_377_g2", 1 << 12)])
+def test_msm_groth16_like_density(eng, name, n):
+    """Witness-shaped scalars (crates/epoch-snark/src/api/prover.rs:78): ~49 % zeros, ~47 % ones,
+    a run of one repeated small scalar (an over-populated bucket) and a few dense ones."""
+    L = C.LAYOUTS[name]
+    bases = L.affine_records(H.random_points(name, n, 909, distinct=128))
+    rng = np.random.default_rng(17)
+    sc = np.zeros((n, L.scalar_limbs), dtype=np.uint64)
+    kind = rng.integers(0, 100, size=n)
+    sc[(kind >= 49) & (kind < 96), 0] = 1                     # unit scalars
+    sc[kind >= 96] = H.random_scalars_array(L, int((kind >= 96).sum()), 3)
+    rep = slice(n // 4, n // 4 + min(3000, n // 3))           # > BIG_BUCKET entries in one bucket per window
+    sc[rep] = 0
+    sc[rep, 0] = 0x2B
+    want = L.jacobian_compressed(C.msm(L, bases, sc))
+    assert L.jacobian_compressed(eng.msm(L.id, bases, sc)) == want
+
+
+def test_msm_all_unit_scalars(eng):
+    L = C.LAYOUTS["bls12_377_g1"]
+    n = 5000
+    pts = H.random_points("bls12_377_g1", n, 4, distinct=50)
+    acc = None
+    for p in pts:
+        acc = L.curve.padd(acc, p)
+    got = eng.msm(L.id, L.affine_records(pts), L.scalars_array([1] * n))
+    assert L.jacobian_to_affine(got) == acc
