@@ -1,0 +1,368 @@
+// BLS12-377 multi-pairing, warp-cooperative: ONE PAIRING PER WARP.
+//
+// Same function as pairing.cuh (Bls12::product_of_pairings, crates/bls-crypto/src/bls/
+// signature.rs:149, public.rs:102; algorithm per SURVEY.md appendix A.3) -- pairing.cuh's
+// one-thread-per-pair tower is kept as the cross-check and for the single Fq12 inversion.
+// A pairing is ~12 k dependent-looking field products; done by one thread it is bound by product
+// latency (0.94 us each).  Here the 32 lanes of a warp share the work of one pairing:
+//
+//   * Fq12 is held in the POWER BASIS Fq[w]/(w^12 + 5) (w^2 = v, v^3 = u, u^2 = -5, so w^12 = -5;
+//     the tower coefficient c[I][J][K] of u^K v^J w^I sits at exponent e = 6K + 2J + I).  A product
+//     is a length-12 negacyclic-style convolution: 144 independent Fq products.  24 lanes take
+//     6 products each (lane = (output exponent e, half h)), halves are combined by one shuffle.
+//     Frobenius is a coefficient-wise product with constants gamma_j^e, conjugation negates the
+//     odd exponents.
+//   * G2 line steps are lists of independent Fq2 products: 4 lanes per product (schoolbook),
+//     up to 8 products per round, operands and results in per-warp shared-memory slots;
+//     the linear glue (add / sub / small multiples) runs 2 lanes per statement.
+//
+// Values (Miller value and GT element) are identical to pairing.cuh's and to arkworks': same
+// formulas, same line scaling, same final-exponentiation chain.
+#pragma once
+#include "pairing.cuh"
+
+namespace b200 {
+
+using FqImg = PFq::Mem;                              // 48-byte memory image of one Fq
+
+struct alignas(16) Fq2Slot {
+    FqImg c0, c1;
+};
+
+constexpr int W_SLOTS = 24;
+struct alignas(16) WarpScratch {                     // per-warp shared memory (4032 bytes)
+    FqImg f[3][12];                                  // three Fq12 values in the power basis (rotating roles)
+    Fq2Slot s[W_SLOTS];                              // Fq2 registers of the line computation
+};
+
+// slot numbers
+enum : int { S_RX = 0, S_RY, S_RZ, S_QX, S_QY, S_PX, S_PY, S_TWOINV, S_TWISTB, S_L0, S_L1, S_L2, S_T0 /* = 12 .. 23 temps */ };
+
+B200_DEV PFq w_ld(const FqImg &m) { return PFq::load(m); }
+B200_DEV void w_st(FqImg &m, const PFq &v) { m = v.store(); }
+
+// tower image index m = 6I + 2J + K  <->  power-basis exponent e = 6K + 2J + I
+B200_DEV int tower_to_power(int m) { return 6 * (m & 1) + 2 * ((m % 6) >> 1) + (m / 6); }
+
+// ---- Fq12 product in the power basis -----------------------------------------------------------
+// O = A * B.  NJ = number of non-zero exponents of B handled per half (6 dense, 3 for a line);
+// jpack holds the exponent list: nibble 2k + h is the k-th exponent of half h.
+template <int NJ>
+__device__ __noinline__ void w_f12_mul(const FqImg *A, const FqImg *B, FqImg *O, uint64_t jpack, int lane) {
+    PFq part = PFq::zero();
+    const int e = lane % 12, h = lane / 12;
+    if (lane < 24) {
+        PFq accP = PFq::zero(), accN = PFq::zero();
+#pragma unroll 1
+        for (int k = 0; k < NJ; k++) {
+            int j = (int)((jpack >> (4 * (2 * k + h))) & 0xFull);
+            int i = e - j;
+            bool wrap = i < 0;
+            i += wrap ? 12 : 0;
+            PFq prod = w_ld(A[i]) * w_ld(B[j]);
+            if (wrap) accN = accN + prod;
+            else accP = accP + prod;
+        }
+        part = accP - (accN.dbl().dbl() + accN);     // w^12 = -5
+    }
+    PFq other = part.shfl(0xffffffffu, (lane + 12) & 31);
+    __syncwarp();                                    // all reads of A / B done before O is written (O may be A's buffer of a later call)
+    if (lane < 12) w_st(O[e], part + other);
+    __syncwarp();
+}
+constexpr uint64_t JPACK_DENSE = 0xBA9876543210ull;  // half 0: 0,2,4,6,8,10   half 1: 1,3,5,7,9,11
+constexpr uint64_t JPACK_LINE = 0x976310ull;         // exponents {0,1,3,6,7,9}: half 0: 0,3,7  half 1: 1,6,9
+
+// coefficient-wise: O[e] = A[e] * gamma_j^e (Frobenius), or negate odd e (conjugation)
+B200_DEV void w_f12_frob(const FqImg *A, FqImg *O, int j, int lane) {
+    if (lane < 12) w_st(O[lane], w_ld(A[lane]) * pfq_const(PAIRING_GAMMA[j - 1][lane]));
+    __syncwarp();
+}
+B200_DEV void w_f12_conj(const FqImg *A, FqImg *O, int lane) {
+    if (lane < 12) {
+        PFq v = w_ld(A[lane]);
+        w_st(O[lane], (lane & 1) ? v.neg() : v);
+    }
+    __syncwarp();
+}
+B200_DEV void w_f12_copy(const FqImg *A, FqImg *O, int lane) {
+    if (lane < 12) O[lane] = A[lane];
+    __syncwarp();
+}
+B200_DEV void w_f12_set_one(FqImg *O, int lane) {
+    if (lane < 12) w_st(O[lane], lane == 0 ? PFq::one() : PFq::zero());
+    __syncwarp();
+}
+// global tower image <-> shared power basis
+B200_DEV void w_f12_load_global(const Fq12::Mem *g, FqImg *O, int lane) {
+    if (lane < 12) O[tower_to_power(lane)] = reinterpret_cast<const FqImg *>(g)[lane];
+    __syncwarp();
+}
+B200_DEV void w_f12_store_global(const FqImg *A, Fq12::Mem *g, int lane) {
+    if (lane < 12) reinterpret_cast<FqImg *>(g)[lane] = A[tower_to_power(lane)];
+    __syncwarp();
+}
+
+// ---- batches of Fq2 products / linear statements on the slots ----------------------------------
+// product k (lanes 4k .. 4k+3): slot[dst_k] = slot[x_k] * slot[y_k]; packs hold one byte per product
+static __device__ __noinline__ void w_f2_mul(Fq2Slot *s, int nprod, uint64_t xpack, uint64_t ypack, uint64_t dpack, int lane) {
+    const int k = lane >> 2, t = lane & 3;
+    const bool live = k < nprod;
+    PFq prod = PFq::zero();
+    if (live) {
+        const Fq2Slot &X = s[(xpack >> (8 * k)) & 0xff], &Y = s[(ypack >> (8 * k)) & 0xff];
+        PFq a = w_ld((t & 1) ? X.c1 : X.c0);                       // t: 0 (c0,c0) 1 (c1,c1) 2 (c0,c1) 3 (c1,c0)
+        PFq b = w_ld((t == 1 || t == 2) ? Y.c1 : Y.c0);
+        prod = a * b;
+    }
+    PFq other = prod.shfl(0xffffffffu, lane ^ 1);
+    __syncwarp();                                                  // operands read before any slot is overwritten
+    if (live) {
+        Fq2Slot &D = s[(dpack >> (8 * k)) & 0xff];
+        if (t == 0) w_st(D.c0, prod - (other.dbl().dbl() + other));   // a0 b0 - 5 a1 b1
+        if (t == 2) w_st(D.c1, prod + other);                         // a0 b1 + a1 b0
+    }
+    __syncwarp();
+}
+// statement q (lanes 2q, 2q+1; one Fq component each): 32-bit descriptor op | dst<<8 | a<<16 | b<<24
+enum : uint32_t { L_ADD = 0, L_SUB = 1, L_DBL = 2, L_TRI = 3, L_NEG = 4, L_CPY = 5 };
+__host__ __device__ constexpr uint32_t LST(uint32_t op, uint32_t dst, uint32_t a, uint32_t b = 0) { return op | (dst << 8) | (a << 16) | (b << 24); }
+static __device__ __noinline__ void w_f2_lin(Fq2Slot *s, int nstmt, const uint32_t *desc, int lane) {
+    const int q = lane >> 1, comp = lane & 1;
+    const bool live = q < nstmt;
+    PFq r = PFq::zero();
+    uint32_t d = live ? desc[q] : 0u;
+    if (live) {
+        const Fq2Slot &A = s[(d >> 16) & 0xff], &B = s[(d >> 24) & 0xff];
+        PFq a = w_ld(comp ? A.c1 : A.c0), b = w_ld(comp ? B.c1 : B.c0);
+        switch (d & 0xff) {
+        case L_ADD: r = a + b; break;
+        case L_SUB: r = a - b; break;
+        case L_DBL: r = a.dbl(); break;
+        case L_TRI: r = a.dbl() + a; break;
+        case L_NEG: r = a.neg(); break;
+        default: r = a; break;
+        }
+    }
+    __syncwarp();
+    if (live) {
+        Fq2Slot &D = s[(d >> 8) & 0xff];
+        w_st(comp ? D.c1 : D.c0, r);
+    }
+    __syncwarp();
+}
+__host__ __device__ constexpr uint64_t PK(int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0, int a4 = 0, int a5 = 0, int a6 = 0, int a7 = 0) {
+    return (uint64_t)a0 | ((uint64_t)a1 << 8) | ((uint64_t)a2 << 16) | ((uint64_t)a3 << 24) | ((uint64_t)a4 << 32) |
+           ((uint64_t)a5 << 40) | ((uint64_t)a6 << 48) | ((uint64_t)a7 << 56);
+}
+
+// temps
+enum : int { T12 = 12, T13, T14, T15, T16, T17, T18, T19, T20, T21, T22, T23 };
+
+// statement tables (device constant memory)
+__device__ const uint32_t DBL_A[] = {LST(L_ADD, T12, S_RY, S_RZ)};
+__device__ const uint32_t DBL_B[] = {LST(L_TRI, T18, T15)};
+__device__ const uint32_t DBL_C1[] = {LST(L_TRI, T20, T19), LST(L_ADD, T21, T14, T15), LST(L_SUB, T22, T19, T14), LST(L_TRI, T23, T17)};
+__device__ const uint32_t DBL_C2[] = {LST(L_ADD, T12, T14, T20), LST(L_SUB, T18, T14, T20), LST(L_SUB, T16, T16, T21)};
+__device__ const uint32_t DBL_C3[] = {LST(L_NEG, T21, T16)};
+__device__ const uint32_t DBL_D1[] = {LST(L_TRI, T20, T20), LST(L_CPY, S_L2, T22)};
+__device__ const uint32_t DBL_D2[] = {LST(L_SUB, S_RY, T12, T20)};
+
+// doubling_step + line scaling by P (arkworks: coeffs (-h, 3j, i); c0 *= P.y, c1 *= P.x)
+B200_DEV void w_doubling_step(Fq2Slot *s, int lane) {
+    w_f2_lin(s, 1, DBL_A, lane);                                                    // T12 = ry + rz
+    w_f2_mul(s, 5, PK(S_RX, S_RY, S_RZ, T12, S_RX), PK(S_RY, S_RY, S_RZ, T12, S_RX),
+             PK(T13, T14, T15, T16, T17), lane);                                    // rx ry | b | c | (ry+rz)^2 | j
+    w_f2_lin(s, 1, DBL_B, lane);                                                    // T18 = 3c
+    w_f2_mul(s, 2, PK(S_TWISTB, T13), PK(T18, S_TWOINV), PK(T19, T13), lane);       // e = b' 3c | a = rx ry / 2
+    w_f2_lin(s, 4, DBL_C1, lane);                                                   // f | b + c | i | 3j
+    w_f2_lin(s, 3, DBL_C2, lane);                                                   // b + f | b - f | h
+    w_f2_lin(s, 1, DBL_C3, lane);                                                   // -h
+    w_f2_mul(s, 6, PK(T12, T19, T13, T14, T21, T23), PK(S_TWOINV, T19, T18, T16, S_PY, S_PX),
+             PK(T12, T20, S_RX, S_RZ, S_L0, S_L1), lane);                           // g | e^2 | rx' | rz' | l0 | l1
+    w_f2_mul(s, 1, PK(T12), PK(T12), PK(T12), lane);                                // g^2
+    w_f2_lin(s, 2, DBL_D1, lane);                                                   // 3 e^2 | l2 = i
+    w_f2_lin(s, 1, DBL_D2, lane);                                                   // ry' = g^2 - 3 e^2
+}
+
+__device__ const uint32_t ADD_A[] = {LST(L_SUB, T14, S_RY, T12), LST(L_SUB, T15, S_RX, T13)};
+__device__ const uint32_t ADD_B[] = {LST(L_ADD, T21, T18, T19), LST(L_DBL, T22, T20)};
+__device__ const uint32_t ADD_C[] = {LST(L_SUB, T23, T21, T22)};
+__device__ const uint32_t ADD_D[] = {LST(L_SUB, T12, T20, T23)};
+__device__ const uint32_t ADD_E[] = {LST(L_SUB, S_RY, T13, T16), LST(L_SUB, S_L2, T17, T19), LST(L_NEG, T21, T14)};
+
+// addition_step + line scaling (coeffs (lambda, -theta, j))
+B200_DEV void w_addition_step(Fq2Slot *s, int lane) {
+    w_f2_mul(s, 2, PK(S_QY, S_QX), PK(S_RZ, S_RZ), PK(T12, T13), lane);             // qy rz | qx rz
+    w_f2_lin(s, 2, ADD_A, lane);                                                    // theta = T14 | lambda = T15
+    w_f2_mul(s, 2, PK(T14, T15), PK(T14, T15), PK(T16, T17), lane);                 // c = theta^2 | d = lambda^2
+    w_f2_mul(s, 3, PK(T15, S_RZ, S_RX), PK(T17, T16, T17), PK(T18, T19, T20), lane);  // e | f | g
+    w_f2_lin(s, 2, ADD_B, lane);                                                    // e + f | 2g
+    w_f2_lin(s, 1, ADD_C, lane);                                                    // h = T23
+    w_f2_lin(s, 1, ADD_D, lane);                                                    // g - h = T12
+    w_f2_mul(s, 6, PK(T15, T14, T18, S_RZ, T14, T15), PK(T23, T12, S_RY, T18, S_QX, S_QY),
+             PK(S_RX, T13, T16, S_RZ, T17, T19), lane);   // rx' | theta (g-h) | e ry | rz' | theta qx | lambda qy
+    w_f2_lin(s, 3, ADD_E, lane);                                                    // ry' | l2 = j | -theta
+    w_f2_mul(s, 2, PK(T15, T21), PK(S_PY, S_PX), PK(S_L0, S_L1), lane);             // l0 = lambda py | l1 = -theta px
+}
+
+// line (l0, l1, l2) -> sparse power-basis element: exponents 0,6 <- l0 ; 1,7 <- l1 ; 3,9 <- l2
+B200_DEV void w_line_to_power(const Fq2Slot *s, FqImg *B, int lane) {
+    if (lane < 6) {
+        const int which = lane >> 1, comp = lane & 1;
+        const int e = (which == 0 ? 0 : which == 1 ? 1 : 3) + 6 * comp;
+        const Fq2Slot &L = s[S_L0 + which];
+        B[e] = comp ? L.c1 : L.c0;
+    }
+    __syncwarp();
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------
+constexpr int W_WARPS = 4;                           // warps (pairings) per block
+
+// warp w: Miller value of pair w -> out[w] (tower image); infinite members give one
+__global__ void __launch_bounds__(32 * W_WARPS) k_w_miller_loop(const AffineMem<PFq> *__restrict__ g1,
+                                                                const AffineMem<PFq2> *__restrict__ g2, uint32_t n,
+                                                                Fq12::Mem *__restrict__ out) {
+    __shared__ WarpScratch scratch[W_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t pair = blockIdx.x * W_WARPS + wib;
+    if (pair >= n) return;                           // whole warps leave together
+    WarpScratch &S = scratch[wib];
+    Affine<PFq> p = Affine<PFq>::from_ark(ldg_mem(g1 + pair));
+    Affine<PFq2> q = Affine<PFq2>::from_ark(ldg_mem(g2 + pair));
+    int fa = 0;                                      // S.f[fa] holds f
+    w_f12_set_one(S.f[0], lane);
+    if (!p.is_inf() && !q.is_inf()) {                // warp-uniform (every lane loaded the same pair)
+        if (lane == 0) {
+            S.s[S_RX] = {q.x.c0.store(), q.x.c1.store()};
+            S.s[S_RY] = {q.y.c0.store(), q.y.c1.store()};
+            S.s[S_RZ] = {PFq::one().store(), PFq::zero().store()};
+            S.s[S_QX] = S.s[S_RX];
+            S.s[S_QY] = S.s[S_RY];
+            S.s[S_PX] = {p.x.store(), PFq::zero().store()};
+            S.s[S_PY] = {p.y.store(), PFq::zero().store()};
+            S.s[S_TWOINV] = {pfq_const(PAIRING_TWO_INV).store(), PFq::zero().store()};
+            S.s[S_TWISTB] = {PFq::zero().store(), pfq_const(PAIRING_TWIST_B_C1).store()};
+        }
+        if (lane < 12) w_st(S.f[2][lane], PFq::zero());      // line element: untouched exponents stay zero
+        __syncwarp();
+#pragma unroll 1
+        for (int b = 62; b >= 0; b--) {
+            w_f12_mul<6>(S.f[fa], S.f[fa], S.f[fa ^ 1], JPACK_DENSE, lane);          // f^2
+            fa ^= 1;
+            w_doubling_step(S.s, lane);
+            w_line_to_power(S.s, S.f[2], lane);
+            w_f12_mul<3>(S.f[fa], S.f[2], S.f[fa ^ 1], JPACK_LINE, lane);            // f * line
+            fa ^= 1;
+            if ((PAIRING_X >> b) & 1ull) {
+                w_addition_step(S.s, lane);
+                w_line_to_power(S.s, S.f[2], lane);
+                w_f12_mul<3>(S.f[fa], S.f[2], S.f[fa ^ 1], JPACK_LINE, lane);
+                fa ^= 1;
+            }
+        }
+    }
+    w_f12_store_global(S.f[fa], out + pair, lane);
+}
+
+// warp w of the grid: vals[w] = prod_{i = w (mod stride)} vals[i]   (strided in-place partial products)
+__global__ void __launch_bounds__(32 * W_WARPS) k_w_fq12_strided_product(Fq12::Mem *__restrict__ vals, uint32_t n,
+                                                                         uint32_t stride) {
+    __shared__ WarpScratch scratch[W_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * W_WARPS + wib;
+    if (w >= stride || w >= n) return;
+    WarpScratch &S = scratch[wib];
+    int fa = 0;
+    w_f12_load_global(vals + w, S.f[0], lane);
+    for (uint32_t i = w + stride; i < n; i += stride) {
+        w_f12_load_global(vals + i, S.f[2], lane);
+        w_f12_mul<6>(S.f[fa], S.f[2], S.f[fa ^ 1], JPACK_DENSE, lane);
+        fa ^= 1;
+    }
+    w_f12_store_global(S.f[fa], vals + w, lane);
+}
+
+// one warp: r = f^x (x = PAIRING_X), power basis; uses S.f[0..2] as rotating buffers, result index returned
+B200_DEV int w_exp_by_x(WarpScratch &S, FqImg *base /* separate 12-entry buffer holding f */, int lane) {
+    int cur = 0;
+    w_f12_copy(base, S.f[0], lane);
+#pragma unroll 1
+    for (int b = 62; b >= 0; b--) {
+        w_f12_mul<6>(S.f[cur], S.f[cur], S.f[cur ^ 1], JPACK_DENSE, lane);
+        cur ^= 1;
+        if ((PAIRING_X >> b) & 1ull) {
+            w_f12_mul<6>(S.f[cur], base, S.f[cur ^ 1], JPACK_DENSE, lane);
+            cur ^= 1;
+        }
+    }
+    return cur;
+}
+
+// one warp: Bls12::final_exponentiation (2016/130 table 1 chain) of vals[0]
+__global__ void __launch_bounds__(32) k_w_final_exp(const Fq12::Mem *__restrict__ in, Fq12::Mem *__restrict__ out,
+                                                    int *__restrict__ is_one, Fq12::Mem *__restrict__ tmp /* 1 image */) {
+    __shared__ WarpScratch S;
+    __shared__ FqImg V[8][12];                       // named values of the chain, power basis
+    const int lane = threadIdx.x & 31;
+    enum { R = 0, Y0, Y1, Y2, Y3, Y4, Y5, X = 7 };
+    // f^(p^6 - 1) = conj(f) * f^-1 : the one inversion, on lane 0 with the per-thread tower
+    if (lane == 0) {
+        Fq12 f = f12_load(in[0]);
+        launder(f);
+        Fq12 fi = f12_inv(f);
+        launder(fi);
+        tmp[0] = f12_store(fi);
+    }
+    __syncwarp();
+    __threadfence_block();
+    w_f12_load_global(in, V[X], lane);               // f
+    w_f12_conj(V[X], V[Y0], lane);                   // conj(f)
+    w_f12_load_global(tmp, V[Y1], lane);             // f^-1
+    w_f12_mul<6>(V[Y0], V[Y1], V[R], JPACK_DENSE, lane);          // r = conj(f) / f
+    w_f12_frob(V[R], V[Y0], 2, lane);
+    w_f12_mul<6>(V[Y0], V[R], V[Y1], JPACK_DENSE, lane);
+    w_f12_copy(V[Y1], V[R], lane);                   // r = frob^2(r) * r          (easy part)
+    // hard part
+    w_f12_mul<6>(V[R], V[R], V[X], JPACK_DENSE, lane);
+    w_f12_conj(V[X], V[Y0], lane);                   // y0 = conj(r^2)
+    int c = w_exp_by_x(S, V[R], lane);
+    w_f12_copy(S.f[c], V[Y5], lane);                 // y5 = r^x
+    w_f12_mul<6>(V[Y5], V[Y5], V[Y1], JPACK_DENSE, lane);         // y1 = y5^2
+    w_f12_mul<6>(V[Y0], V[Y5], V[Y3], JPACK_DENSE, lane);         // y3 = y0 y5
+    c = w_exp_by_x(S, V[Y3], lane);
+    w_f12_copy(S.f[c], V[Y0], lane);                 // y0 = y3^x
+    c = w_exp_by_x(S, V[Y0], lane);
+    w_f12_copy(S.f[c], V[Y2], lane);                 // y2 = y0^x
+    c = w_exp_by_x(S, V[Y2], lane);
+    w_f12_mul<6>(S.f[c], V[Y1], V[Y4], JPACK_DENSE, lane);        // y4 = y2^x y1
+    c = w_exp_by_x(S, V[Y4], lane);
+    w_f12_copy(S.f[c], V[Y1], lane);                 // y1 = y4^x
+    w_f12_conj(V[Y3], V[X], lane);
+    w_f12_copy(V[X], V[Y3], lane);                   // y3 = conj(y3)
+    w_f12_mul<6>(V[Y1], V[Y3], V[X], JPACK_DENSE, lane);
+    w_f12_mul<6>(V[X], V[R], V[Y1], JPACK_DENSE, lane);           // y1 = y1 y3 r
+    w_f12_conj(V[R], V[Y3], lane);                   // y3 = conj(r)
+    w_f12_mul<6>(V[Y0], V[R], V[X], JPACK_DENSE, lane);
+    w_f12_frob(V[X], V[Y0], 3, lane);                // y0 = frob^3(y0 r)
+    w_f12_mul<6>(V[Y4], V[Y3], V[X], JPACK_DENSE, lane);
+    w_f12_frob(V[X], V[Y4], 1, lane);                // y4 = frob(y4 y3)
+    w_f12_mul<6>(V[Y5], V[Y2], V[X], JPACK_DENSE, lane);
+    w_f12_frob(V[X], V[Y5], 2, lane);                // y5 = frob^2(y5 y2)
+    w_f12_mul<6>(V[Y5], V[Y0], V[X], JPACK_DENSE, lane);
+    w_f12_mul<6>(V[X], V[Y4], V[Y2], JPACK_DENSE, lane);
+    w_f12_mul<6>(V[Y2], V[Y1], V[X], JPACK_DENSE, lane);          // result
+    if (out) w_f12_store_global(V[X], out, lane);
+    if (is_one) {
+        bool ok = true;
+        if (lane < 12) {
+            PFq v = w_ld(V[X][lane]);
+            ok = lane == 0 ? (v == PFq::one()) : v.is_zero();
+        }
+        unsigned all = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) *is_one = all == 0xffffffffu ? 1 : 0;
+    }
+}
+
+}  // namespace b200
