@@ -39,8 +39,14 @@ static MsmPlan make_plan(size_t n) {
         }
     }
     best.n = (uint32_t)n;
-    best.seg_len = best.nb >= 4096 ? 16 : (best.nb >= 64 ? 8 : (int)std::min<uint32_t>(best.nb, 4u));
+    best.seg_len = best.nb >= 8192 ? 32 : best.nb >= 4096 ? 16 : (best.nb >= 64 ? 8 : (int)std::min<uint32_t>(best.nb, 4u));
+    if (const char *env = getenv("B200_MSM_SEG")) {                // experiments: force the reduce segment length
+        int v = atoi(env);
+        if (v >= 1 && (uint32_t)v <= best.nb && (best.nb % v) == 0) best.seg_len = v;
+    }
     best.segs = best.nb / best.seg_len;
+    // block-summed buckets: a few times the mean population of a bucket (uniform digits)
+    best.big = (uint32_t)std::min<size_t>(SIZE_BINS - 1, std::max<size_t>(64, 4 * (n / best.nb) + 32));
     return best;
 }
 
@@ -103,11 +109,11 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     LAUNCH_CHECK();
     k_digit_scatter<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, cursor, E.sorted.as<uint32_t>(), E.ones.as<uint32_t>());
     LAUNCH_CHECK();
-    k_size_hist<<<std::min(ceil_div(total, 256), E.sm_count * 4), 256, 0, st>>>(counts, (uint32_t)total, bins);
+    k_size_hist<<<std::min(ceil_div(total, 256), E.sm_count * 4), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins);
     LAUNCH_CHECK();
     k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins, bins + SIZE_BINS);
     LAUNCH_CHECK();
-    k_size_scatter<<<ceil_div(total, 256), 256, 0, st>>>(counts, (uint32_t)total, bins + SIZE_BINS,
+    k_size_scatter<<<ceil_div(total, 256), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins + SIZE_BINS,
                                                          E.order.as<uint32_t>());
     LAUNCH_CHECK();
 
@@ -116,7 +122,7 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
         <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
             reinterpret_cast<const AffineMem<F> *>(d_bases), E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(),
-            (uint32_t)total, E.buckets.as<XYZZMem<F>>());
+            (uint32_t)total, p.big, E.buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     if (prof) {
         CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));
@@ -126,14 +132,21 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
 
     {   // over-populated buckets (skewed scalars) and unit scalars: bounded extra launches
         constexpr int BT = T::RED_THREADS;                         // smem: BT XYZZ images (<= 24.5 KB)
-        uint32_t max_big = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / BIG_BUCKET + 1);
-        k_big_buckets<F, BT><<<max_big, BT, BT * sizeof(XYZZMem<F>), st>>>(
-            reinterpret_cast<const AffineMem<F> *>(d_bases), E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(),
-            bins, E.buckets.as<XYZZMem<F>>());
+        const AffineMem<F> *bases = reinterpret_cast<const AffineMem<F> *>(d_bases);
+        uint32_t max_big = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / p.big + 1);
+        uint32_t max_huge = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / HUGE_BUCKET + 1);
+        if ((rc = E.huge_slices.reserve((size_t)max_huge * HUGE_SLICES * sizeof(XYZZMem<F>)))) return rc;
+        k_big_buckets<F, BT><<<std::min<uint32_t>(max_big, (uint32_t)E.sm_count * 16), BT, BT * sizeof(XYZZMem<F>), st>>>(
+            bases, E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(), bins, p.big, E.buckets.as<XYZZMem<F>>());
+        LAUNCH_CHECK();
+        k_huge_buckets<F, BT><<<dim3(max_huge, HUGE_SLICES), BT, BT * sizeof(XYZZMem<F>), st>>>(
+            bases, E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(), bins, p.big, E.huge_slices.as<XYZZMem<F>>());
+        LAUNCH_CHECK();
+        k_huge_finish<F, BT><<<ceil_div((size_t)max_huge * 4, BT), BT, 0, st>>>(
+            E.huge_slices.as<XYZZMem<F>>(), offsets, E.order.as<uint32_t>(), bins, p.big, max_huge, E.buckets.as<XYZZMem<F>>());
         LAUNCH_CHECK();
         k_ones_accumulate<F, BT><<<ONES_PARTS / BT, BT, 0, st>>>(
-            reinterpret_cast<const AffineMem<F> *>(d_bases), E.ones.as<uint32_t>(),
-            E.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs);
+            bases, E.ones.as<uint32_t>(), E.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs);
         LAUNCH_CHECK();
     }
     uint32_t red_threads = (uint32_t)p.windows * p.segs * 4;      // one quad per segment

@@ -84,7 +84,7 @@ void b200_shutdown(void) {
     cudaSetDevice(E->device);
     cudaStreamSynchronize(E->stream);
     for (Buffer *b : {&E->counts, &E->offsets, &E->cursor, &E->tile_sums, &E->bins, &E->order, &E->sorted, &E->buckets,
-                      &E->partials, &E->window_sums, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
+                      &E->partials, &E->window_sums, &E->huge_slices, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
                       &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->ones})
         b->release();
     for (auto &ev : E->prof_ev)

@@ -59,7 +59,7 @@ struct Engine {
     bool has_pending = false;
     std::mutex mu;
     // workspace (grow-only)
-    Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums, ones;
+    Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums, ones, huge_slices;
     // staging for the host-pointer API
     Buffer h2d_bases, native_bases, scalars, result;
     // multi-pairing: Miller values, packed G2 staging

@@ -46,6 +46,7 @@ struct MsmPlan {
     uint32_t nb;           // buckets per window = 2^(c-1)
     int seg_len;           // buckets per reduce segment
     uint32_t segs;         // segments per window = nb / seg_len
+    uint32_t big;          // buckets holding >= big points are summed by a whole block (<= SIZE_BINS - 1)
 };
 
 // signed window digit of the scalar at s (global memory, canonical little-endian words)
@@ -190,13 +191,13 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32
 // ---- order buckets by population (descending) so warps are uniformly loaded ---------------
 constexpr int SIZE_BINS = 1024;
 
-static __global__ void __launch_bounds__(256) k_size_hist(const uint32_t *__restrict__ counts, uint32_t total,
+static __global__ void __launch_bounds__(256) k_size_hist(const uint32_t *__restrict__ counts, uint32_t total, uint32_t big,
                                                    uint32_t *__restrict__ bin_counts) {
     __shared__ uint32_t h[SIZE_BINS];
     for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) h[i] = 0;
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-        atomicAdd(&h[min(counts[i], (uint32_t)SIZE_BINS - 1)], 1u);
+        atomicAdd(&h[min(counts[i], big)], 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
         if (h[i]) atomicAdd(&bin_counts[i], h[i]);
@@ -212,11 +213,11 @@ static __global__ void __launch_bounds__(SIZE_BINS) k_size_scan(const uint32_t *
     bin_cursor[rev] = e;
 }
 
-static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__restrict__ counts, uint32_t total,
+static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__restrict__ counts, uint32_t total, uint32_t big,
                                                       uint32_t *__restrict__ bin_cursor, uint32_t *__restrict__ order) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    uint32_t bin = min(counts[i], (uint32_t)SIZE_BINS - 1);
+    uint32_t bin = min(counts[i], big);
     // warp-aggregated cursor bump: one atomic per distinct bin per warp
     uint32_t peers = __match_any_sync(__activemask(), bin);
     int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
@@ -226,9 +227,12 @@ static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__r
     order[base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
-// buckets holding at least this many points (the top population bin of k_size_*) are summed by a
-// whole block instead of one thread: skewed scalar sets (many equal small scalars) stay bounded
-constexpr uint32_t BIG_BUCKET = SIZE_BINS - 1;
+// Buckets holding at least MsmPlan::big points (the top population bin of k_size_*; a few times the
+// mean population) are summed by a whole block instead of one thread, and those holding at least
+// HUGE_BUCKET points by HUGE_SLICES blocks: skewed scalar sets (many equal small scalars in Groth16
+// witnesses, the short top window of any scalar size) stay bounded.
+constexpr uint32_t HUGE_BUCKET = 8192;
+constexpr uint32_t HUGE_SLICES = 32;
 
 // ---- bucket accumulation: the dominant kernel ---------------------------------------------
 // One thread per bucket.  bases are native-radix packed affine images (k_pack_bases output);
@@ -237,12 +241,12 @@ template <class F, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
-                    XYZZMem<F> *__restrict__ buckets) {
+                    uint32_t big, XYZZMem<F> *__restrict__ buckets) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     if (t >= total_buckets) return;
     uint32_t id = order[t];
     uint32_t k = offsets[id], end = offsets[id + 1];
-    if (end - k >= BIG_BUCKET) return;               // left to k_big_buckets (one block per bucket)
+    if (end - k >= big) return;                      // left to k_big_buckets (one block per bucket)
     XYZZ<F> acc = XYZZ<F>::inf();
     if (k < end) {
         uint32_t e = __ldg(sorted + k);
@@ -282,26 +286,57 @@ B200_DEV XYZZ<F> block_sum(XYZZ<F> acc, XYZZMem<F> *sm) {
 }
 
 // one block per over-populated bucket: order[] is sorted by population, so the first
-// bin_counts[top] entries are exactly the buckets k_bucket_accumulate skipped
+// bin_counts[big] entries are exactly the buckets k_bucket_accumulate skipped.  Blocks stride over
+// them; buckets of HUGE_BUCKET points or more are left to k_huge_buckets.
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_big_buckets(const AffineMem<F> *__restrict__ bases,
                                                          const uint32_t *__restrict__ sorted,
                                                          const uint32_t *__restrict__ offsets,
                                                          const uint32_t *__restrict__ order,
-                                                         const uint32_t *__restrict__ bin_counts,
+                                                         const uint32_t *__restrict__ bin_counts, uint32_t big,
                                                          XYZZMem<F> *__restrict__ buckets) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (blockIdx.x >= bin_counts[SIZE_BINS - 1]) return;
-    uint32_t id = order[blockIdx.x];
+    const uint32_t nbig = bin_counts[big];
+    for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
+        uint32_t id = order[b];
+        uint32_t lo = offsets[id], hi = offsets[id + 1];
+        if (hi - lo >= HUGE_BUCKET) continue;
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = lo + threadIdx.x; k < hi; k += THREADS) {
+            uint32_t e = __ldg(sorted + k);
+            Affine<F> pt = Affine<F>::load(ldg_mem(bases + (e & 0x7fffffffu)));
+            if (!pt.is_inf()) acc.madd(pt.x, pt.y.cneg(e >> 31));
+        }
+        acc = block_sum<F, THREADS>(acc, reinterpret_cast<XYZZMem<F> *>(smem_raw));
+        if (threadIdx.x == 0) buckets[id] = acc.store();
+        __syncthreads();
+    }
+}
+
+// block (b, y): slice y of huge bucket order[b] -> slices[b * HUGE_SLICES + y]   (b < max_huge)
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_huge_buckets(const AffineMem<F> *__restrict__ bases,
+                                                          const uint32_t *__restrict__ sorted,
+                                                          const uint32_t *__restrict__ offsets,
+                                                          const uint32_t *__restrict__ order,
+                                                          const uint32_t *__restrict__ bin_counts, uint32_t big,
+                                                          XYZZMem<F> *__restrict__ slices) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t b = blockIdx.x;
+    if (b >= bin_counts[big]) return;
+    uint32_t id = order[b];
     uint32_t lo = offsets[id], hi = offsets[id + 1];
+    if (hi - lo < HUGE_BUCKET) return;
+    uint32_t per = (hi - lo + HUGE_SLICES - 1) / HUGE_SLICES;
+    uint32_t s_lo = lo + blockIdx.y * per, s_hi = min(hi, s_lo + per);
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = lo + threadIdx.x; k < hi; k += THREADS) {
+    for (uint32_t k = s_lo + threadIdx.x; k < s_hi; k += THREADS) {
         uint32_t e = __ldg(sorted + k);
         Affine<F> pt = Affine<F>::load(ldg_mem(bases + (e & 0x7fffffffu)));
         if (!pt.is_inf()) acc.madd(pt.x, pt.y.cneg(e >> 31));
     }
     acc = block_sum<F, THREADS>(acc, reinterpret_cast<XYZZMem<F> *>(smem_raw));
-    if (threadIdx.x == 0) buckets[id] = acc.store();
+    if (threadIdx.x == 0) slices[(size_t)b * HUGE_SLICES + blockIdx.y] = acc.store();
 }
 
 // unit scalars: ONES_PARTS strided partial sums of the listed bases (weight 1, added after Horner)
@@ -331,6 +366,23 @@ B200_DEV XYZZ<F> quad_small_mul(const Quad &Q, const XYZZ<F> &p, uint32_t k) {
         if ((k >> b) & 1u) quad_add(Q, r, p);
     }
     return r;
+}
+
+// quad b: bucket order[b] = sum of its HUGE_SLICES slice sums (huge buckets only)
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_huge_finish(const XYZZMem<F> *__restrict__ slices,
+                                                         const uint32_t *__restrict__ offsets,
+                                                         const uint32_t *__restrict__ order,
+                                                         const uint32_t *__restrict__ bin_counts, uint32_t big, uint32_t max_huge,
+                                                         XYZZMem<F> *__restrict__ buckets) {
+    const Quad Q;
+    uint32_t b = (blockIdx.x * THREADS + threadIdx.x) >> 2;
+    if (b >= max_huge || b >= bin_counts[big]) return;
+    uint32_t id = order[b];
+    if (offsets[id + 1] - offsets[id] < HUGE_BUCKET) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t y = 0; y < HUGE_SLICES; y++) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(slices + (size_t)b * HUGE_SLICES + y)));
+    if (Q.q == 0) buckets[id] = acc.store();
 }
 
 // quad (w, seg): partial = sum_{j < L} (seg*L + j + 1) * B[w][seg*L + j]

@@ -183,3 +183,16 @@ def test_msm_all_unit_scalars(eng):
         acc = L.curve.padd(acc, p)
     got = eng.msm(L.id, L.affine_records(pts), L.scalars_array([1] * n))
     assert L.jacobian_to_affine(got) == acc
+
+
+@pytest.mark.parametrize("name,n,run", [("bls12_377_g1", 1 << 15, 12000), ("bw6_761_g1", 1 << 14, 9000)])
+def test_msm_huge_bucket_is_sliced(eng, name, n, run):
+    """More than HUGE_BUCKET (8192) points with one and the same scalar: the bucket is summed by
+    HUGE_SLICES blocks (k_huge_buckets / k_huge_finish) and must still equal the oracle."""
+    L = C.LAYOUTS[name]
+    bases = L.affine_records(H.random_points(name, n, 31337, distinct=64))
+    sc = H.random_scalars_array(L, n, 8)
+    sc[100:100 + run] = 0
+    sc[100:100 + run, 0] = 0x1D3
+    want = L.jacobian_compressed(C.msm(L, bases, sc))
+    assert L.jacobian_compressed(eng.msm(L.id, bases, sc)) == want

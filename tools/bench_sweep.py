@@ -1,6 +1,6 @@
 """Device-resident MSM timing sweep over curves and sizes (not the headline bench: bench.py).
 Bases are k_i * G generated on the device; BW6-761 uses a seeded curve point as G.
-    PYTHONPATH=. python tools/bench_sweep.py [--quick]
+    PYTHONPATH=. python tools/bench_sweep.py [--quick] [--curve=bw6_761_g1] [--logs=12,20]
 Prints one JSON line per (curve, n): ms per MSM (CUDA events, 3 warm-ups, 5 timed), Mpairs/s."""
 import json
 import sys
@@ -48,6 +48,8 @@ def scalars(n, limbs, top_bits, seed):
 
 def main():
     quick = "--quick" in sys.argv
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--curve=")]
+    logs_override = [[int(v) for v in a.split("=", 1)[1].split(",")] for a in sys.argv if a.startswith("--logs=")]
     E.init(0)
     dev = torch.device("cuda:0")
     stream = torch.cuda.Stream(device=dev)
@@ -57,6 +59,10 @@ def main():
             (E.BLS12_377_G2, "bls12_377_g2", [12, 16, 20] if quick else [10, 12, 14, 16, 18, 20, 22]),
             (E.BW6_761_G1, "bw6_761_g1", [12, 16, 20] if quick else [12, 14, 16, 18, 20, 22])]
     for cid, name, logs in plan:
+        if only and name not in only:
+            continue
+        if logs_override:
+            logs = logs_override[0]
         limbs = E.SCALAR_BYTES[cid] // 8
         top = 60 if limbs == 4 else 56
         gen = torch.from_numpy(np.frombuffer(generator_bytes(cid), dtype=np.uint8).copy()).to(dev)
