@@ -10,6 +10,18 @@ static bool thread_path() {
     return v;
 }
 
+// B200_FINAL_EXP_WARP=1 selects the one-warp final exponentiation (cross-check of the block-cooperative one)
+static bool warp_final_exp() {
+    static const bool v = getenv("B200_FINAL_EXP_WARP") && atoi(getenv("B200_FINAL_EXP_WARP"));
+    return v;
+}
+
+// B200_PAIRING_SINGLE=1: one pair per warp (k_w_miller_loop), the cross-check of the two-pair kernel
+static bool single_pair_warps() {
+    static const bool v = getenv("B200_PAIRING_SINGLE") && atoi(getenv("B200_PAIRING_SINGLE"));
+    return v;
+}
+
 // Miller values of n pairs multiplied together -> d_out (one Fq12 image, before the final exponentiation)
 int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out, cudaStream_t st) {
     static_assert(sizeof(Fq12::Mem) == 576, "arkworks Fq12 image is 576 bytes");
@@ -32,9 +44,15 @@ int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, 
         k_fq12_product<128><<<1, 128, 0, st>>>(vals, (uint32_t)n);
         LAUNCH_CHECK();
     } else {
-        k_w_miller_loop<<<ceil_div(n, W_WARPS), 32 * W_WARPS, 0, st>>>(g1, g2, (uint32_t)n, vals);
+        uint32_t live = (uint32_t)n;                 // Miller values to fold
+        if (single_pair_warps()) {
+            k_w_miller_loop<<<ceil_div(n, W_WARPS), 32 * W_WARPS, 0, st>>>(g1, g2, (uint32_t)n, vals);
+        } else {                                     // two pairs per warp share one Miller variable
+            live = (uint32_t)((n + 1) / 2);
+            k_w2_miller_loop<<<ceil_div(live, W_WARPS), 32 * W_WARPS, 0, st>>>(g1, g2, (uint32_t)n, vals);
+        }
         LAUNCH_CHECK();
-        uint32_t live = (uint32_t)n;                 // fold: n -> <= 4 * SMs -> <= 32 -> 1 partial products
+        // fold: live -> <= 4 * SMs -> <= 32 -> 1 partial products
         const uint32_t steps[3] = {(uint32_t)E.sm_count * W_WARPS, 32u, 1u};
         for (uint32_t stride : steps) {
             if (live <= stride) continue;
@@ -60,8 +78,10 @@ int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_i
     }
     if (thread_path()) {
         k_final_exp<<<1, 32, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one);   // d_out may be NULL
-    } else {
+    } else if (warp_final_exp()) {
         k_w_final_exp<<<1, 32, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one, vals + count);
+    } else {
+        k_b_final_exp<<<1, B_THREADS, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one);
     }
     LAUNCH_CHECK();
     return B200_OK;

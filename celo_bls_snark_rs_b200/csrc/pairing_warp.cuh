@@ -266,6 +266,144 @@ __global__ void __launch_bounds__(32 * W_WARPS) k_w_miller_loop(const AffineMem<
     w_f12_store_global(S.f[fa], out + pair, lane);
 }
 
+// ---- two pairs per warp, one shared f ----------------------------------------------------------------
+// prod_i f_i can be accumulated in ONE Miller variable: f <- f^2 * line_0 * line_1 per bit, so the
+// dense squaring (the largest item of an iteration) is paid once per two pairs, and the two G2 line
+// steps run side by side in the same product rounds (<= 4 Fq2 products per pair and round, 4 lanes
+// each).  Slot sets s0 / s1 hold the two pairs' line state; `two` is false when the warp has only
+// one finite pair.
+static __device__ __noinline__ void w_f2_mul2(Fq2Slot *s0, Fq2Slot *s1, bool two, int nprod, uint32_t xpack,
+                                              uint32_t ypack, uint32_t dpack, int lane) {
+    const int k = lane >> 2, t = lane & 3;
+    const int pr = k >= nprod ? 1 : 0, kk = k - pr * nprod;
+    const bool live = kk < nprod && (pr == 0 || two);
+    Fq2Slot *s = pr ? s1 : s0;
+    PFq prod = PFq::zero();
+    if (live) {
+        const Fq2Slot &X = s[(xpack >> (8 * kk)) & 0xff], &Y = s[(ypack >> (8 * kk)) & 0xff];
+        PFq a = w_ld((t & 1) ? X.c1 : X.c0);                       // t: 0 (c0,c0) 1 (c1,c1) 2 (c0,c1) 3 (c1,c0)
+        PFq b = w_ld((t == 1 || t == 2) ? Y.c1 : Y.c0);
+        prod = a * b;
+    }
+    PFq other = prod.shfl(0xffffffffu, lane ^ 1);
+    __syncwarp();
+    if (live) {
+        Fq2Slot &D = s[(dpack >> (8 * kk)) & 0xff];
+        if (t == 0) w_st(D.c0, prod - (other.dbl().dbl() + other));
+        if (t == 2) w_st(D.c1, prod + other);
+    }
+    __syncwarp();
+}
+static __device__ __noinline__ void w_f2_lin2(Fq2Slot *s0, Fq2Slot *s1, bool two, int nstmt, const uint32_t *desc, int lane) {
+    const int q = lane >> 1, comp = lane & 1;
+    const int pr = q >= nstmt ? 1 : 0, qq = q - pr * nstmt;
+    const bool live = qq < nstmt && (pr == 0 || two);
+    Fq2Slot *s = pr ? s1 : s0;
+    PFq r = PFq::zero();
+    uint32_t d = live ? desc[qq] : 0u;
+    if (live) {
+        const Fq2Slot &A = s[(d >> 16) & 0xff], &B = s[(d >> 24) & 0xff];
+        PFq a = w_ld(comp ? A.c1 : A.c0), b = w_ld(comp ? B.c1 : B.c0);
+        switch (d & 0xff) {
+        case L_ADD: r = a + b; break;
+        case L_SUB: r = a - b; break;
+        case L_DBL: r = a.dbl(); break;
+        case L_TRI: r = a.dbl() + a; break;
+        case L_NEG: r = a.neg(); break;
+        default: r = a; break;
+        }
+    }
+    __syncwarp();
+    if (live) {
+        Fq2Slot &D = s[(d >> 8) & 0xff];
+        w_st(comp ? D.c1 : D.c0, r);
+    }
+    __syncwarp();
+}
+__host__ __device__ constexpr uint32_t PK4(int a0 = 0, int a1 = 0, int a2 = 0, int a3 = 0) {
+    return (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16) | ((uint32_t)a3 << 24);
+}
+// w_doubling_step for both slot sets at once (same statements, product rounds regrouped to <= 4)
+B200_DEV void w_doubling_step2(Fq2Slot *s0, Fq2Slot *s1, bool two, int lane) {
+    w_f2_lin2(s0, s1, two, 1, DBL_A, lane);                                                   // T12 = ry + rz
+    w_f2_mul2(s0, s1, two, 4, PK4(S_RX, S_RY, S_RZ, T12), PK4(S_RY, S_RY, S_RZ, T12), PK4(T13, T14, T15, T16), lane);
+    w_f2_lin2(s0, s1, two, 1, DBL_B, lane);                                                   // T18 = 3c
+    w_f2_mul2(s0, s1, two, 3, PK4(S_TWISTB, T13, S_RX), PK4(T18, S_TWOINV, S_RX), PK4(T19, T13, T17), lane);   // e | a | j
+    w_f2_lin2(s0, s1, two, 4, DBL_C1, lane);
+    w_f2_lin2(s0, s1, two, 3, DBL_C2, lane);
+    w_f2_lin2(s0, s1, two, 1, DBL_C3, lane);
+    w_f2_mul2(s0, s1, two, 4, PK4(T12, T19, T13, T14), PK4(S_TWOINV, T19, T18, T16), PK4(T12, T20, S_RX, S_RZ), lane);   // g | e^2 | rx' | rz'
+    w_f2_mul2(s0, s1, two, 3, PK4(T12, T21, T23), PK4(T12, S_PY, S_PX), PK4(T12, S_L0, S_L1), lane);                     // g^2 | l0 | l1
+    w_f2_lin2(s0, s1, two, 2, DBL_D1, lane);
+    w_f2_lin2(s0, s1, two, 1, DBL_D2, lane);
+}
+
+struct alignas(16) WarpScratch2 {                    // per-warp shared memory: shared f, two line states
+    FqImg f[3][12];
+    Fq2Slot s[2][W_SLOTS];
+};
+
+B200_DEV void w_init_line_state(Fq2Slot *s, const Affine<PFq> &p, const Affine<PFq2> &q) {
+    s[S_RX] = {q.x.c0.store(), q.x.c1.store()};
+    s[S_RY] = {q.y.c0.store(), q.y.c1.store()};
+    s[S_RZ] = {PFq::one().store(), PFq::zero().store()};
+    s[S_QX] = s[S_RX];
+    s[S_QY] = s[S_RY];
+    s[S_PX] = {p.x.store(), PFq::zero().store()};
+    s[S_PY] = {p.y.store(), PFq::zero().store()};
+    s[S_TWOINV] = {pfq_const(PAIRING_TWO_INV).store(), PFq::zero().store()};
+    s[S_TWISTB] = {PFq::zero().store(), pfq_const(PAIRING_TWIST_B_C1).store()};
+}
+
+// warp w: out[w] = Miller value of pair 2w  *  Miller value of pair 2w + 1 (tower image);
+// pairs with an infinite member (and the missing partner of an odd n) contribute one
+__global__ void __launch_bounds__(32 * W_WARPS) k_w2_miller_loop(const AffineMem<PFq> *__restrict__ g1,
+                                                                 const AffineMem<PFq2> *__restrict__ g2, uint32_t n,
+                                                                 Fq12::Mem *__restrict__ out) {
+    __shared__ WarpScratch2 scratch[W_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * W_WARPS + wib;
+    if (2 * w >= n) return;                          // whole warps leave together
+    WarpScratch2 &S = scratch[wib];
+    int live = 0;                                    // finite pairs placed in slot sets 0 .. live-1
+    for (uint32_t pair = 2 * w; pair < min(n, 2 * w + 2); pair++) {
+        Affine<PFq> p = Affine<PFq>::from_ark(ldg_mem(g1 + pair));
+        Affine<PFq2> q = Affine<PFq2>::from_ark(ldg_mem(g2 + pair));
+        if (p.is_inf() || q.is_inf()) continue;      // warp-uniform
+        if (lane == 0) w_init_line_state(S.s[live], p, q);
+        live++;
+    }
+    int fa = 0;
+    w_f12_set_one(S.f[0], lane);
+    if (live) {
+        const bool two = live == 2;
+        if (lane < 12) w_st(S.f[2][lane], PFq::zero());      // line element: untouched exponents stay zero
+        __syncwarp();
+#pragma unroll 1
+        for (int b = 62; b >= 0; b--) {
+            if (b != 62) {                                   // f is still one before the first lines
+                w_f12_mul<6>(S.f[fa], S.f[fa], S.f[fa ^ 1], JPACK_DENSE, lane);      // f^2
+                fa ^= 1;
+            }
+            w_doubling_step2(S.s[0], S.s[1], two, lane);
+            for (int k = 0; k < live; k++) {
+                w_line_to_power(S.s[k], S.f[2], lane);
+                w_f12_mul<3>(S.f[fa], S.f[2], S.f[fa ^ 1], JPACK_LINE, lane);        // f * line
+                fa ^= 1;
+            }
+            if ((PAIRING_X >> b) & 1ull) {
+                for (int k = 0; k < live; k++) {
+                    w_addition_step(S.s[k], lane);
+                    w_line_to_power(S.s[k], S.f[2], lane);
+                    w_f12_mul<3>(S.f[fa], S.f[2], S.f[fa ^ 1], JPACK_LINE, lane);
+                    fa ^= 1;
+                }
+            }
+        }
+    }
+    w_f12_store_global(S.f[fa], out + w, lane);
+}
+
 // warp w of the grid: vals[w] = prod_{i = w (mod stride)} vals[i]   (strided in-place partial products)
 __global__ void __launch_bounds__(32 * W_WARPS) k_w_fq12_strided_product(Fq12::Mem *__restrict__ vals, uint32_t n,
                                                                          uint32_t stride) {
@@ -362,6 +500,125 @@ __global__ void __launch_bounds__(32) k_w_final_exp(const Fq12::Mem *__restrict_
         }
         unsigned all = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) *is_one = all == 0xffffffffu ? 1 : 0;
+    }
+}
+
+// ---- block-cooperative final exponentiation ---------------------------------------------------------
+// The final exponentiation is ONE Fq12 chain of ~350 dependent products: with one warp each product
+// is 6 sequential field products per lane.  Here a block of 160 threads gives every one of the 144
+// coefficient products a[i] * b[j] its own thread (one field-product latency per Fq12 product), the
+// 12 output coefficients are then summed from shared memory by 24 threads (positive / wrapped halves).
+constexpr int B_THREADS = 160;
+struct alignas(16) BlockScratch {
+    FqImg V[9][12];                                  // named values of the chain, power basis
+    FqImg P[144];                                    // coefficient products, P[e * 12 + i] = a[i] * b[(e - i) mod 12]
+};
+
+// O = A * B; all B_THREADS threads call; O may alias A and / or B
+B200_DEV void b_f12_mul(const FqImg *A, const FqImg *B, FqImg *O, FqImg *P, int t) {
+    if (t < 144) {
+        const int i = t / 12, j = t % 12;
+        int e = i + j;
+        e -= e >= 12 ? 12 : 0;
+        w_st(P[e * 12 + i], w_ld(A[i]) * w_ld(B[j]));
+    }
+    __syncthreads();
+    if (t < 32) {                                    // warp 0: lanes (e, h); h = 1 sums the wrapped terms (i > e)
+        const int e = t % 12, h = t / 12;
+        PFq part = PFq::zero();
+        if (t < 24) {
+            const int lo = h ? e + 1 : 0, hi = h ? 12 : e + 1;
+#pragma unroll 1
+            for (int i = lo; i < hi; i++) part = part + w_ld(P[e * 12 + i]);
+        }
+        PFq other = part.shfl(0xffffffffu, (t + 12) & 31);
+        if (t < 12) w_st(O[e], part - (other.dbl().dbl() + other));          // w^12 = -5
+    }
+    __syncthreads();
+}
+B200_DEV void b_f12_frob(const FqImg *A, FqImg *O, int j, int t) {
+    if (t < 12) w_st(O[t], w_ld(A[t]) * pfq_const(PAIRING_GAMMA[j - 1][t]));
+    __syncthreads();
+}
+B200_DEV void b_f12_conj(const FqImg *A, FqImg *O, int t) {
+    if (t < 12) {
+        PFq v = w_ld(A[t]);
+        w_st(O[t], (t & 1) ? v.neg() : v);
+    }
+    __syncthreads();
+}
+B200_DEV void b_f12_copy(const FqImg *A, FqImg *O, int t) {
+    if (t < 12) O[t] = A[t];
+    __syncthreads();
+}
+// O = base^x (x = PAIRING_X), O != base
+B200_DEV void b_exp_by_x(const FqImg *base, FqImg *O, FqImg *P, int t) {
+    b_f12_copy(base, O, t);
+#pragma unroll 1
+    for (int b = 62; b >= 0; b--) {
+        b_f12_mul(O, O, O, P, t);
+        if ((PAIRING_X >> b) & 1ull) b_f12_mul(O, base, O, P, t);
+    }
+}
+
+// one block: Bls12::final_exponentiation (2016/130 table 1 chain) of in[0]
+__global__ void __launch_bounds__(B_THREADS) k_b_final_exp(const Fq12::Mem *__restrict__ in, Fq12::Mem *__restrict__ out,
+                                                           int *__restrict__ is_one) {
+    __shared__ BlockScratch S;
+    __shared__ Fq12::Mem inv_img;
+    const int t = threadIdx.x;
+    enum { R = 0, Y0, Y1, Y2, Y3, Y4, Y5, X, T };
+    FqImg(*V)[12] = S.V;
+    FqImg *P = S.P;
+    // f^(p^6 - 1) = conj(f) * f^-1 : the one inversion, on thread 0 with the per-thread tower
+    if (t == 0) {
+        Fq12 f = f12_load(in[0]);
+        launder(f);
+        Fq12 fi = f12_inv(f);
+        launder(fi);
+        inv_img = f12_store(fi);
+    }
+    if (t < 12) V[X][tower_to_power(t)] = reinterpret_cast<const FqImg *>(in)[t];          // f
+    __syncthreads();
+    if (t < 12) V[Y1][tower_to_power(t)] = reinterpret_cast<const FqImg *>(&inv_img)[t];   // f^-1
+    __syncthreads();
+    b_f12_conj(V[X], V[Y0], t);                      // conj(f)
+    b_f12_mul(V[Y0], V[Y1], V[R], P, t);             // r = conj(f) / f
+    b_f12_frob(V[R], V[Y0], 2, t);
+    b_f12_mul(V[Y0], V[R], V[R], P, t);              // r = frob^2(r) * r          (easy part)
+    // hard part
+    b_f12_mul(V[R], V[R], V[X], P, t);
+    b_f12_conj(V[X], V[Y0], t);                      // y0 = conj(r^2)
+    b_exp_by_x(V[R], V[Y5], P, t);                   // y5 = r^x
+    b_f12_mul(V[Y5], V[Y5], V[Y1], P, t);            // y1 = y5^2
+    b_f12_mul(V[Y0], V[Y5], V[Y3], P, t);            // y3 = y0 y5
+    b_exp_by_x(V[Y3], V[Y0], P, t);                  // y0 = y3^x
+    b_exp_by_x(V[Y0], V[Y2], P, t);                  // y2 = y0^x
+    b_exp_by_x(V[Y2], V[Y4], P, t);
+    b_f12_mul(V[Y4], V[Y1], V[Y4], P, t);            // y4 = y2^x y1
+    b_exp_by_x(V[Y4], V[Y1], P, t);                  // y1 = y4^x
+    b_f12_conj(V[Y3], V[Y3], t);                     // y3 = conj(y3)
+    b_f12_mul(V[Y1], V[Y3], V[Y1], P, t);
+    b_f12_mul(V[Y1], V[R], V[Y1], P, t);             // y1 = y1 y3 r
+    b_f12_conj(V[R], V[Y3], t);                      // y3 = conj(r)
+    b_f12_mul(V[Y0], V[R], V[X], P, t);
+    b_f12_frob(V[X], V[Y0], 3, t);                   // y0 = frob^3(y0 r)
+    b_f12_mul(V[Y4], V[Y3], V[X], P, t);
+    b_f12_frob(V[X], V[Y4], 1, t);                   // y4 = frob(y4 y3)
+    b_f12_mul(V[Y5], V[Y2], V[X], P, t);
+    b_f12_frob(V[X], V[Y5], 2, t);                   // y5 = frob^2(y5 y2)
+    b_f12_mul(V[Y5], V[Y0], V[X], P, t);
+    b_f12_mul(V[X], V[Y4], V[X], P, t);
+    b_f12_mul(V[X], V[Y1], V[X], P, t);              // result
+    if (out && t < 12) reinterpret_cast<FqImg *>(out)[t] = V[X][tower_to_power(t)];
+    if (is_one && t < 32) {
+        bool ok = true;
+        if (t < 12) {
+            PFq v = w_ld(V[X][t]);
+            ok = t == 0 ? (v == PFq::one()) : v.is_zero();
+        }
+        unsigned all = __ballot_sync(0xffffffffu, ok);
+        if (t == 0) *is_one = all == 0xffffffffu ? 1 : 0;
     }
 }
 
