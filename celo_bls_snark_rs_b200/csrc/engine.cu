@@ -87,6 +87,8 @@ void b200_shutdown(void) {
                       &E->partials, &E->window_sums, &E->huge_slices, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
                       &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->ones})
         b->release();
+    for (NttDomain &d : E->ntt)
+        for (Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
     for (auto &ev : E->prof_ev)
         if (ev) cudaEventDestroy(ev);
     cudaEventDestroy(E->done);
@@ -269,6 +271,24 @@ int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, c
         return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     return batch_verify_strict_hash(E, pubkeys, signatures, exponents, n, message_hash, out_verified);
+}
+
+int b200_ntt_device(int field, void *d_data, unsigned log_n, int inverse, int coset, void *stream) {
+    if (field != B200_FR_BLS12_377 && field != B200_FR_BW6_761) return fail(B200_ERR_ARG, "unknown scalar field id %d", field);
+    if (!d_data) return fail(B200_ERR_ARG, "null pointer");
+    if (log_n > 26) return fail(B200_ERR_ARG, "log_n = %u exceeds the 2^26 per-call limit", log_n);
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    return ntt_transform(E, field, d_data, (int)log_n, inverse, coset, st);
+}
+
+int b200_witness_map_device(int field, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_h, void *stream) {
+    if (field != B200_FR_BLS12_377 && field != B200_FR_BW6_761) return fail(B200_ERR_ARG, "unknown scalar field id %d", field);
+    if (!d_a || !d_b || !d_c || !d_h) return fail(B200_ERR_ARG, "null pointer");
+    if (log_n > 26) return fail(B200_ERR_ARG, "log_n = %u exceeds the 2^26 per-call limit", log_n);
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    return witness_map(E, field, d_a, d_b, d_c, (int)log_n, d_h, st);
 }
 
 int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream) {

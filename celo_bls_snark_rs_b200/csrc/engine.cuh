@@ -51,6 +51,12 @@ struct Buffer {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// one cached radix-2 domain per scalar field (ntt.cuh): constants, power tables, twiddles omega^i (i < n/2)
+struct NttDomain {
+    int log_n = -1;
+    Buffer consts, pw, tw;
+};
+
 struct Engine {
     int device = -1;
     int sm_count = 148;
@@ -64,6 +70,8 @@ struct Engine {
     Buffer h2d_bases, native_bases, scalars, result;
     // multi-pairing: Miller values, packed G2 staging
     Buffer miller, g2_packed, h2d_g2;
+    // NTT domains: [0] BLS12-377 Fr, [1] BW6-761 Fr (= BLS12-377 Fq)
+    NttDomain ntt[2];
     // batch-verification composites (inst_verify.cu)
     Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff;
     // optional timing of the dominant kernel (b200_profile_*): event pairs around k_bucket_accumulate
@@ -91,6 +99,9 @@ template <class C> int field_op(int op, const void *a, const void *b, size_t n, 
 // BLS12-377 multi-pairing (inst_pairing.cu)
 int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out, cudaStream_t st);
 int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_is_one, cudaStream_t st);
+// radix-2 NTT / Groth16 witness map (inst_ntt.cu)
+int ntt_transform(Engine &E, int field, void *data, int log_n, int inverse, int coset, cudaStream_t st);
+int witness_map(Engine &E, int field, void *a, void *b, void *c, int log_n, void *h, cudaStream_t st);
 // batch-verification flows (inst_verify.cu)
 int batch_verify_hashes(Engine &E, const void *signature, const void *pubkeys, const void *hashes, size_t n, int *out_verified);
 int batch_verify_strict_hash(Engine &E, const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,

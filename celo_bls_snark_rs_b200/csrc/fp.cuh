@@ -34,8 +34,8 @@ namespace b200 {
 
 #define B200_DEV __device__ __forceinline__
 
-// -p^-1 mod 2^32 per field (slot 0: BLS12-377 Fq, slot 1: BW6-761 Fq); see the note above.
-static __constant__ uint32_t c_mont_inv[2] = {Fq377Params::INV, Fq761Params::INV};
+// -p^-1 mod 2^32 per field (slot 0: BLS12-377 Fq, slot 1: BW6-761 Fq, slot 2: BLS12-377 Fr); see the note above.
+static __constant__ uint32_t c_mont_inv[3] = {Fq377Params::INV, Fq761Params::INV, Fr253Params::INV};
 
 // ---- carry-chain primitives (all volatile: the CC flag links consecutive asm statements) ----
 B200_DEV void add_cc(uint32_t &r, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); }
@@ -360,5 +360,6 @@ struct Fp {
 
 using Fq377 = Fp<Fq377Params>;
 using Fq761 = Fp<Fq761Params>;
+using Fr253 = Fp<Fr253Params>;                      // BLS12-377 scalar field (NTT domain of the inner Groth16 proof)
 
 }  // namespace b200

@@ -32,6 +32,7 @@ EXPORTS = [
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
     "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
+    "b200_ntt_device", "b200_witness_map_device",
 ]
 
 
@@ -68,6 +69,8 @@ def load() -> ctypes.CDLL:
     lib.b200_final_exp_bls12_377_device.argtypes = [vp, sz, vp, vp, vp]
     lib.b200_batch_verify_hashes.argtypes = [vp, vp, vp, sz, ctypes.POINTER(i32)]
     lib.b200_batch_verify_strict_hash.argtypes = [vp, vp, vp, sz, vp, ctypes.POINTER(i32)]
+    lib.b200_ntt_device.argtypes = [i32, vp, ctypes.c_uint, i32, i32, vp]
+    lib.b200_witness_map_device.argtypes = [i32, vp, vp, vp, ctypes.c_uint, vp, vp]
     lib.b200_sync.argtypes = [vp]
     lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
     lib.b200_launch_count.restype = ctypes.c_uint64
@@ -179,6 +182,20 @@ def miller_product_device(d_g1: int, d_g2: int, n: int, d_out: int, stream: int 
 
 def final_exp_device(d_vals: int, count: int, d_out: int, d_is_one: int = 0, stream: int = 0):
     _check(load().b200_final_exp_bls12_377_device(d_vals, count, d_out or None, d_is_one or None, stream or None))
+
+
+FR_BLS12_377, FR_BW6_761 = 0, 1
+FR_BYTES = {0: 32, 1: 48}
+
+
+def ntt_device(field: int, d_data: int, log_n: int, inverse: bool = False, coset: bool = False, stream: int = 0):
+    """In-place radix-2 transform of 2^log_n scalar-field elements (arkworks Montgomery images)."""
+    _check(load().b200_ntt_device(field, d_data, log_n, int(inverse), int(coset), stream or None))
+
+
+def witness_map_device(field: int, d_a: int, d_b: int, d_c: int, log_n: int, d_h: int, stream: int = 0):
+    """Groth16 witness-map transform chain: h = (a b - c) / Z as coefficients; a, b, c are clobbered."""
+    _check(load().b200_witness_map_device(field, d_a, d_b, d_c, log_n, d_h, stream or None))
 
 
 def profile_enable(on: bool = True):

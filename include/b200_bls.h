@@ -139,6 +139,23 @@ int b200_batch_verify_hashes(const void *signature, const void *pubkeys, const v
 int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,
                                   const void *message_hash, int *out_verified);
 
+/* ---- radix-2 NTT and the Groth16 witness map ------------------------------------------------------
+ * Replaces ark-poly 0.1.0 Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place and the
+ * transform chain of ark-groth16 0.1.0 R1CStoQAP::witness_map, which create_proof_no_zk runs right
+ * before its MSMs (crates/epoch-snark/src/api/prover.rs:78 outer proof over BW6-761, :112 inner proof
+ * over BLS12-377).  Elements are the scalar fields' arkworks memory images (Montgomery residues):
+ * B200_FR_BLS12_377 = Fp256, 4 x u64 (32 B); B200_FR_BW6_761 = Fp384, 6 x u64 (48 B; this field is
+ * BLS12-377's Fq).  The domain has n = 2^log_n points, group generator
+ * TWO_ADIC_ROOT_OF_UNITY^(2^(s - log_n)) and coset offset GENERATOR (22 / -5), as in arkworks.
+ * b200_ntt_device: in place, natural order in and out; inverse includes the 1/n scaling; coset
+ *   variants multiply by GENERATOR^i before the forward / by GENERATOR^-i after the inverse transform.
+ * b200_witness_map_device: d_a, d_b, d_c hold the n evaluations of the A, B, C combinations (c_i =
+ *   a_i * b_i on constraint rows); they are overwritten.  d_h receives the n coefficients of
+ *   (a b - c) / Z; the prover's h-query MSM consumes the first n - 1. */
+enum { B200_FR_BLS12_377 = 0, B200_FR_BW6_761 = 1 };
+int b200_ntt_device(int field, void *d_data, unsigned log_n, int inverse, int coset, void *stream);
+int b200_witness_map_device(int field, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_h, void *stream);
+
 /* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
  * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),
  * 6 double(a).  Exists so the field layer can be checked against the oracle directly. */
