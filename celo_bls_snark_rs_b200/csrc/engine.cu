@@ -85,7 +85,7 @@ void b200_shutdown(void) {
     cudaStreamSynchronize(E->stream);
     for (Buffer *b : {&E->counts, &E->offsets, &E->cursor, &E->tile_sums, &E->bins, &E->order, &E->sorted, &E->buckets,
                       &E->partials, &E->window_sums, &E->huge_slices, &E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->ones})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->ones, &E->g16_h, &E->g16_tmp})
         b->release();
     for (NttDomain &d : E->ntt)
         for (Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
@@ -289,6 +289,21 @@ int b200_witness_map_device(int field, void *d_a, void *d_b, void *d_c, unsigned
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
     return witness_map(E, field, d_a, d_b, d_c, (int)log_n, d_h, st);
+}
+
+int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
+                              size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_proof,
+                              void *stream) {
+    if (family != B200_GROTH16_BLS12_377 && family != B200_GROTH16_BW6_761) return fail(B200_ERR_ARG, "unknown Groth16 family %d", family);
+    if (!pk || !pk->a_query || !pk->b_g2_query || !pk->h_query || !pk->alpha_g1 || !pk->beta_g2 || !d_a || !d_b || !d_c ||
+        !d_proof || (num_assign && !d_assignment) || (num_aux && !pk->l_query))
+        return fail(B200_ERR_ARG, "null pointer");
+    if (num_aux > num_assign) return fail(B200_ERR_ARG, "num_aux exceeds num_assign");
+    if (log_n == 0 || log_n > 26) return fail(B200_ERR_ARG, "log_n = %u out of range [1, 26]", log_n);
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    return groth16_prove(E, family, pk, d_assignment, num_assign, num_aux, d_a, d_b, d_c, log_n, d_proof, st);
 }
 
 int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream) {

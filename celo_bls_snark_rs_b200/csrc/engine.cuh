@@ -72,6 +72,8 @@ struct Engine {
     Buffer miller, g2_packed, h2d_g2;
     // NTT domains: [0] BLS12-377 Fr, [1] BW6-761 Fr (= BLS12-377 Fq)
     NttDomain ntt[2];
+    // Groth16 prover composite (inst_groth16.cu): quotient coefficients h, partial MSM results
+    Buffer g16_h, g16_tmp;
     // batch-verification composites (inst_verify.cu)
     Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff;
     // optional timing of the dominant kernel (b200_profile_*): event pairs around k_bucket_accumulate
@@ -102,6 +104,9 @@ int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_i
 // radix-2 NTT / Groth16 witness map (inst_ntt.cu)
 int ntt_transform(Engine &E, int field, void *data, int log_n, int inverse, int coset, cudaStream_t st);
 int witness_map(Engine &E, int field, void *a, void *b, void *c, int log_n, void *h, cudaStream_t st);
+// Groth16 prover arithmetic (inst_groth16.cu)
+int groth16_prove(Engine &E, int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
+                  size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_proof, cudaStream_t st);
 // batch-verification flows (inst_verify.cu)
 int batch_verify_hashes(Engine &E, const void *signature, const void *pubkeys, const void *hashes, size_t n, int *out_verified);
 int batch_verify_strict_hash(Engine &E, const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,

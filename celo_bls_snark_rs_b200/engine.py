@@ -32,8 +32,13 @@ EXPORTS = [
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
     "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
-    "b200_ntt_device", "b200_witness_map_device",
+    "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device",
 ]
+
+
+class Groth16Pk(ctypes.Structure):
+    """b200_groth16_pk: device pointers to the packed proving-key queries."""
+    _fields_ = [(k, ctypes.c_void_p) for k in ("a_query", "b_g2_query", "h_query", "l_query", "alpha_g1", "beta_g2")]
 
 
 class B200Error(RuntimeError):
@@ -71,6 +76,7 @@ def load() -> ctypes.CDLL:
     lib.b200_batch_verify_strict_hash.argtypes = [vp, vp, vp, sz, vp, ctypes.POINTER(i32)]
     lib.b200_ntt_device.argtypes = [i32, vp, ctypes.c_uint, i32, i32, vp]
     lib.b200_witness_map_device.argtypes = [i32, vp, vp, vp, ctypes.c_uint, vp, vp]
+    lib.b200_groth16_prove_device.argtypes = [i32, ctypes.POINTER(Groth16Pk), vp, sz, sz, vp, vp, vp, ctypes.c_uint, vp, vp]
     lib.b200_sync.argtypes = [vp]
     lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
     lib.b200_launch_count.restype = ctypes.c_uint64
@@ -196,6 +202,16 @@ def ntt_device(field: int, d_data: int, log_n: int, inverse: bool = False, coset
 def witness_map_device(field: int, d_a: int, d_b: int, d_c: int, log_n: int, d_h: int, stream: int = 0):
     """Groth16 witness-map transform chain: h = (a b - c) / Z as coefficients; a, b, c are clobbered."""
     _check(load().b200_witness_map_device(field, d_a, d_b, d_c, log_n, d_h, stream or None))
+
+
+GROTH16_BLS12_377, GROTH16_BW6_761 = 0, 1
+
+
+def groth16_prove_device(family: int, pk: "Groth16Pk", d_assignment: int, num_assign: int, num_aux: int, d_a: int,
+                         d_b: int, d_c: int, log_n: int, d_proof: int, stream: int = 0):
+    """Groth16 prover arithmetic after synthesis (witness map + 4 MSMs + assembly); d_proof = A | B | C Jacobian."""
+    _check(load().b200_groth16_prove_device(family, ctypes.byref(pk), d_assignment or None, num_assign, num_aux, d_a, d_b, d_c,
+                                            log_n, d_proof, stream or None))
 
 
 def profile_enable(on: bool = True):

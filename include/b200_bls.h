@@ -156,6 +156,31 @@ enum { B200_FR_BLS12_377 = 0, B200_FR_BW6_761 = 1 };
 int b200_ntt_device(int field, void *d_data, unsigned log_n, int inverse, int coset, void *stream);
 int b200_witness_map_device(int field, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_h, void *stream);
 
+/* ---- Groth16 prover arithmetic --------------------------------------------------------------------
+ * Everything ark-groth16 0.1.0 create_proof_no_zk (= create_proof_with_reduction_no_zk, r = s = 0)
+ * computes after constraint synthesis, for crates/epoch-snark/src/api/prover.rs:78 (family
+ * B200_GROTH16_BW6_761: G1/G2 over BW6-761, scalars 6 x u64) and :112 (B200_GROTH16_BLS12_377).
+ * Proving-key queries are device arrays of PACKED affine records (b200_pack_bases_device output),
+ * resident across proofs:  a_query, b_g2_query: num_assign + 1 records (entry 0 is the constant-one
+ * column), l_query: num_aux, h_query: 2^log_n - 1, alpha_g1 / beta_g2: one record each.
+ * d_assignment: num_assign canonical scalars = public inputs (without the leading one) followed by the
+ * num_aux auxiliary values (what arkworks passes to its MSMs after into_repr()).
+ * d_a, d_b, d_c: the 2^log_n evaluation vectors of the witness map (Montgomery images; overwritten).
+ * d_proof receives A | B | C as arkworks GroupProjective images (G1, G2, G1); the caller's
+ * into_affine() of those is the Proof { a, b, c } the reference serialises. */
+enum { B200_GROTH16_BLS12_377 = 0, B200_GROTH16_BW6_761 = 1 };
+typedef struct {
+    const void *a_query;
+    const void *b_g2_query;
+    const void *h_query;
+    const void *l_query;
+    const void *alpha_g1;
+    const void *beta_g2;
+} b200_groth16_pk;
+int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
+                              size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_proof,
+                              void *stream);
+
 /* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
  * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),
  * 6 double(a).  Exists so the field layer can be checked against the oracle directly. */
