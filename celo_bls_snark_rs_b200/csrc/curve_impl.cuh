@@ -65,11 +65,119 @@ int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStre
     return B200_OK;
 }
 
+// ---- one MSM = three stages over a workspace set ----------------------------------------------------
+// sort (digit histogram, scan, scatter, population order) -> accumulate (buckets) -> tail (bucket
+// reduce, window sums, Horner).  msm_native runs them back to back on the caller's stream;
+// msm_batch software-pipelines consecutive MSMs over three internal streams and two workspace sets.
+template <class C>
+static int msm_reserve(MsmWs &W, const MsmPlan &p, size_t n) {
+    using F = typename C::F;
+    size_t total = (size_t)p.windows * p.nb;
+    uint32_t tiles = (uint32_t)ceil_div(total, SCAN_TILE);
+    size_t max_huge = std::min<size_t>(total, n * (size_t)p.windows / HUGE_BUCKET + 1);
+    int rc;
+    if ((rc = W.counts.reserve(total * 4)) || (rc = W.offsets.reserve((total + 1) * 4)) ||
+        (rc = W.cursor.reserve(total * 4)) || (rc = W.tile_sums.reserve((size_t)tiles * 4)) ||
+        (rc = W.bins.reserve(2 * SIZE_BINS * 4)) || (rc = W.order.reserve(total * 4)) ||
+        (rc = W.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = W.buckets.reserve(total * sizeof(XYZZMem<F>))) ||
+        (rc = W.partials.reserve(((size_t)p.windows * p.segs + ONES_PARTS) * sizeof(XYZZMem<F>))) ||
+        (rc = W.window_sums.reserve((size_t)(p.windows + 1) * sizeof(XYZZMem<F>))) ||
+        (rc = W.ones.reserve((n + 1) * 4)) || (rc = W.huge_slices.reserve(max_huge * HUGE_SLICES * sizeof(XYZZMem<F>))))
+        return rc;
+    return B200_OK;
+}
+
+template <class C>
+static int msm_stage_sort(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_scalars, size_t n, cudaStream_t st) {
+    size_t total = (size_t)p.windows * p.nb;
+    uint32_t tiles = (uint32_t)ceil_div(total, SCAN_TILE);
+    const uint32_t *sc = reinterpret_cast<const uint32_t *>(d_scalars);
+    uint32_t *counts = W.counts.as<uint32_t>(), *offsets = W.offsets.as<uint32_t>(), *cursor = W.cursor.as<uint32_t>();
+    uint32_t *bins = W.bins.as<uint32_t>();
+    CUDA_TRY(cudaMemsetAsync(counts, 0, total * 4, st));
+    CUDA_TRY(cudaMemsetAsync(bins, 0, 2 * SIZE_BINS * 4, st));
+    CUDA_TRY(cudaMemsetAsync(W.ones.p, 0, 4, st));
+    int nblk = ceil_div(n, 256);
+    k_digit_hist<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, counts);
+    LAUNCH_CHECK();
+    k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)total, W.tile_sums.as<uint32_t>());
+    LAUNCH_CHECK();
+    k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(W.tile_sums.as<uint32_t>(), tiles);
+    LAUNCH_CHECK();
+    k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)total, W.tile_sums.as<uint32_t>(), offsets, cursor);
+    LAUNCH_CHECK();
+    k_digit_scatter<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, cursor, W.sorted.as<uint32_t>(), W.ones.as<uint32_t>());
+    LAUNCH_CHECK();
+    k_size_hist<<<std::min(ceil_div(total, 256), E.sm_count * 4), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins);
+    LAUNCH_CHECK();
+    k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins, bins + SIZE_BINS);
+    LAUNCH_CHECK();
+    k_size_scatter<<<ceil_div(total, 256), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins + SIZE_BINS,
+                                                         W.order.as<uint32_t>());
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <class C>
+static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_bases, size_t n, cudaStream_t st) {
+    using F = typename C::F;
+    using T = CurveTraits<C>;
+    size_t total = (size_t)p.windows * p.nb;
+    const AffineMem<F> *bases = reinterpret_cast<const AffineMem<F> *>(d_bases);
+    uint32_t *offsets = W.offsets.as<uint32_t>(), *bins = W.bins.as<uint32_t>();
+    bool prof = E.profile && E.prof_used < Engine::PROF_SLOTS;
+    if (prof) CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used], st));
+    k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
+        <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
+            bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), (uint32_t)total, p.big,
+            W.buckets.as<XYZZMem<F>>());
+    LAUNCH_CHECK();
+    if (prof) {
+        CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));
+        E.prof_used++;
+        E.prof_units += n;
+    }
+    // over-populated buckets (skewed scalars) and unit scalars: bounded extra launches
+    constexpr int BT = T::RED_THREADS;                             // smem: BT XYZZ images (<= 24.5 KB)
+    uint32_t max_big = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / p.big + 1);
+    uint32_t max_huge = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / HUGE_BUCKET + 1);
+    k_big_buckets<F, BT><<<std::min<uint32_t>(max_big, (uint32_t)E.sm_count * 16), BT, BT * sizeof(XYZZMem<F>), st>>>(
+        bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), bins, p.big, W.buckets.as<XYZZMem<F>>());
+    LAUNCH_CHECK();
+    k_huge_buckets<F, BT><<<dim3(max_huge, HUGE_SLICES), BT, BT * sizeof(XYZZMem<F>), st>>>(
+        bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), bins, p.big, W.huge_slices.as<XYZZMem<F>>());
+    LAUNCH_CHECK();
+    k_huge_finish<F, BT><<<ceil_div((size_t)max_huge * 4, BT), BT, 0, st>>>(
+        W.huge_slices.as<XYZZMem<F>>(), offsets, W.order.as<uint32_t>(), bins, p.big, max_huge, W.buckets.as<XYZZMem<F>>());
+    LAUNCH_CHECK();
+    k_ones_accumulate<F, BT><<<ONES_PARTS / BT, BT, 0, st>>>(bases, W.ones.as<uint32_t>(),
+                                                             W.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <class C>
+static int msm_stage_tail(MsmWs &W, const MsmPlan &p, void *d_out, cudaStream_t st) {
+    using F = typename C::F;
+    using T = CurveTraits<C>;
+    uint32_t red_threads = (uint32_t)p.windows * p.segs * 4;      // one quad per segment
+    k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
+        W.buckets.as<XYZZMem<F>>(), p, W.partials.as<XYZZMem<F>>());
+    LAUNCH_CHECK();
+    constexpr int WS_THREADS = 256;                                // 64 quads per window
+    size_t ws_smem = (WS_THREADS / 4) * sizeof(XYZZMem<F>);
+    k_window_sum<F, WS_THREADS><<<p.windows + 1, WS_THREADS, ws_smem, st>>>(W.partials.as<XYZZMem<F>>(), p,
+                                                                        W.window_sums.as<XYZZMem<F>>());
+    LAUNCH_CHECK();
+    k_window_combine<F><<<1, 32, 0, st>>>(W.window_sums.as<XYZZMem<F>>(), p, reinterpret_cast<JacobianMem<F> *>(d_out));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
 // d_bases: native packed images (pack_bases output); d_out: arkworks GroupProjective image
 template <class C>
 int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
     using F = typename C::F;
-    using T = CurveTraits<C>;
     if (n == 0) {
         k_sum_jacobian<F><<<1, 1, 0, st>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(d_out));
         LAUNCH_CHECK();
@@ -77,90 +185,63 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     }
     if (n > (size_t)1 << 26) return fail(B200_ERR_ARG, "n = %zu exceeds the 2^26 per-call limit", n);
     MsmPlan p = make_plan<C>(n);
-    size_t total = (size_t)p.windows * p.nb;
-    uint32_t tiles = (uint32_t)ceil_div(total, SCAN_TILE);
+    MsmWs &W = E.ws[0];
     int rc;
-    if ((rc = E.counts.reserve(total * 4)) || (rc = E.offsets.reserve((total + 1) * 4)) ||
-        (rc = E.cursor.reserve(total * 4)) || (rc = E.tile_sums.reserve((size_t)tiles * 4)) ||
-        (rc = E.bins.reserve(2 * SIZE_BINS * 4)) || (rc = E.order.reserve(total * 4)) ||
-        (rc = E.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = E.buckets.reserve(total * sizeof(XYZZMem<F>))) ||
-        (rc = E.partials.reserve(((size_t)p.windows * p.segs + ONES_PARTS) * sizeof(XYZZMem<F>))) ||
-        (rc = E.window_sums.reserve((size_t)(p.windows + 1) * sizeof(XYZZMem<F>))) ||
-        (rc = E.ones.reserve((n + 1) * 4)))
-        return rc;
-
+    if ((rc = msm_reserve<C>(W, p, n))) return rc;
     if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    if ((rc = msm_stage_sort<C>(E, W, p, d_scalars, n, st))) return rc;
+    if ((rc = msm_stage_accumulate<C>(E, W, p, d_bases, n, st))) return rc;
+    if ((rc = msm_stage_tail<C>(W, p, d_out, st))) return rc;
+    CUDA_TRY(cudaEventRecord(E.done, st));
+    E.has_pending = true;
+    return B200_OK;
+}
 
-    const uint32_t *sc = reinterpret_cast<const uint32_t *>(d_scalars);
-    uint32_t *counts = E.counts.as<uint32_t>(), *offsets = E.offsets.as<uint32_t>(), *cursor = E.cursor.as<uint32_t>();
-    uint32_t *bins = E.bins.as<uint32_t>();
-    CUDA_TRY(cudaMemsetAsync(counts, 0, total * 4, st));
-    CUDA_TRY(cudaMemsetAsync(bins, 0, 2 * SIZE_BINS * 4, st));
-    CUDA_TRY(cudaMemsetAsync(E.ones.p, 0, 4, st));
-
-    int nblk = ceil_div(n, 256);
-    k_digit_hist<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, counts);
-    LAUNCH_CHECK();
-    k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)total, E.tile_sums.as<uint32_t>());
-    LAUNCH_CHECK();
-    k_scan_tiles<<<1, SCAN_THREADS, 0, st>>>(E.tile_sums.as<uint32_t>(), tiles);
-    LAUNCH_CHECK();
-    k_scan_apply<<<tiles, SCAN_THREADS, 0, st>>>(counts, (uint32_t)total, E.tile_sums.as<uint32_t>(), offsets, cursor);
-    LAUNCH_CHECK();
-    k_digit_scatter<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, cursor, E.sorted.as<uint32_t>(), E.ones.as<uint32_t>());
-    LAUNCH_CHECK();
-    k_size_hist<<<std::min(ceil_div(total, 256), E.sm_count * 4), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins);
-    LAUNCH_CHECK();
-    k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins, bins + SIZE_BINS);
-    LAUNCH_CHECK();
-    k_size_scatter<<<ceil_div(total, 256), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins + SIZE_BINS,
-                                                         E.order.as<uint32_t>());
-    LAUNCH_CHECK();
-
-    bool prof = E.profile && E.prof_used < Engine::PROF_SLOTS;
-    if (prof) CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used], st));
-    k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
-        <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
-            reinterpret_cast<const AffineMem<F> *>(d_bases), E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(),
-            (uint32_t)total, p.big, E.buckets.as<XYZZMem<F>>());
-    LAUNCH_CHECK();
-    if (prof) {
-        CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));
-        E.prof_used++;
-        E.prof_units += n;
+// `count` independent MSMs (native packed bases), software-pipelined: the sort of job i+1 and the tail
+// of job i-1 run on their own streams beside the accumulation of job i (workspace sets alternate).
+// Everything is ordered after `st`'s prior work and joined back into `st` before returning.
+template <class C>
+int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st) {
+    using F = typename C::F;
+    int rc;
+    std::vector<MsmPlan> plans(count);
+    for (size_t i = 0; i < count; i++) {
+        if (jobs[i].n > (size_t)1 << 26) return fail(B200_ERR_ARG, "n = %zu exceeds the 2^26 per-call limit", jobs[i].n);
+        if (!jobs[i].d_out_jacobian || (jobs[i].n && (!jobs[i].d_bases_packed || !jobs[i].d_scalars)))
+            return fail(B200_ERR_ARG, "null pointer in job %zu", i);
+        if (jobs[i].n == 0) continue;
+        plans[i] = make_plan<C>(jobs[i].n);
     }
-
-    {   // over-populated buckets (skewed scalars) and unit scalars: bounded extra launches
-        constexpr int BT = T::RED_THREADS;                         // smem: BT XYZZ images (<= 24.5 KB)
-        const AffineMem<F> *bases = reinterpret_cast<const AffineMem<F> *>(d_bases);
-        uint32_t max_big = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / p.big + 1);
-        uint32_t max_huge = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / HUGE_BUCKET + 1);
-        if ((rc = E.huge_slices.reserve((size_t)max_huge * HUGE_SLICES * sizeof(XYZZMem<F>)))) return rc;
-        k_big_buckets<F, BT><<<std::min<uint32_t>(max_big, (uint32_t)E.sm_count * 16), BT, BT * sizeof(XYZZMem<F>), st>>>(
-            bases, E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(), bins, p.big, E.buckets.as<XYZZMem<F>>());
-        LAUNCH_CHECK();
-        k_huge_buckets<F, BT><<<dim3(max_huge, HUGE_SLICES), BT, BT * sizeof(XYZZMem<F>), st>>>(
-            bases, E.sorted.as<uint32_t>(), offsets, E.order.as<uint32_t>(), bins, p.big, E.huge_slices.as<XYZZMem<F>>());
-        LAUNCH_CHECK();
-        k_huge_finish<F, BT><<<ceil_div((size_t)max_huge * 4, BT), BT, 0, st>>>(
-            E.huge_slices.as<XYZZMem<F>>(), offsets, E.order.as<uint32_t>(), bins, p.big, max_huge, E.buckets.as<XYZZMem<F>>());
-        LAUNCH_CHECK();
-        k_ones_accumulate<F, BT><<<ONES_PARTS / BT, BT, 0, st>>>(
-            bases, E.ones.as<uint32_t>(), E.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs);
-        LAUNCH_CHECK();
+    size_t live = 0;                                               // workspace sets alternate over the non-empty jobs
+    for (size_t i = 0; i < count; i++)
+        if (jobs[i].n && (rc = msm_reserve<C>(E.ws[live++ & 1], plans[i], jobs[i].n))) return rc;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    cudaStream_t s_sort = E.pipe_stream[0], s_acc = E.pipe_stream[1], s_tail = E.pipe_stream[2];
+    CUDA_TRY(cudaEventRecord(E.ev_fork, st));
+    for (cudaStream_t s : {s_sort, s_acc, s_tail}) CUDA_TRY(cudaStreamWaitEvent(s, E.ev_fork, 0));
+    size_t k = 0;
+    for (size_t i = 0; i < count; i++) {
+        if (jobs[i].n == 0) {
+            k_sum_jacobian<F><<<1, 1, 0, s_tail>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(jobs[i].d_out_jacobian));
+            LAUNCH_CHECK();
+            continue;
+        }
+        const int w = (int)(k & 1);
+        MsmWs &W = E.ws[w];
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(s_sort, E.ev_acc[w], 0));      // sort buffers of job k-2 consumed
+        if ((rc = msm_stage_sort<C>(E, W, plans[i], jobs[i].d_scalars, jobs[i].n, s_sort))) return rc;
+        CUDA_TRY(cudaEventRecord(E.ev_sorted[w], s_sort));
+        CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_sorted[w], 0));
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_tail[w], 0));      // buckets of job k-2 consumed
+        if ((rc = msm_stage_accumulate<C>(E, W, plans[i], jobs[i].d_bases_packed, jobs[i].n, s_acc))) return rc;
+        CUDA_TRY(cudaEventRecord(E.ev_acc[w], s_acc));
+        CUDA_TRY(cudaStreamWaitEvent(s_tail, E.ev_acc[w], 0));
+        if ((rc = msm_stage_tail<C>(W, plans[i], jobs[i].d_out_jacobian, s_tail))) return rc;
+        CUDA_TRY(cudaEventRecord(E.ev_tail[w], s_tail));
+        k++;
     }
-    uint32_t red_threads = (uint32_t)p.windows * p.segs * 4;      // one quad per segment
-    k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
-        E.buckets.as<XYZZMem<F>>(), p, E.partials.as<XYZZMem<F>>());
-    LAUNCH_CHECK();
-    constexpr int WS_THREADS = 256;                                // 64 quads per window
-    size_t ws_smem = (WS_THREADS / 4) * sizeof(XYZZMem<F>);
-    k_window_sum<F, WS_THREADS><<<p.windows + 1, WS_THREADS, ws_smem, st>>>(E.partials.as<XYZZMem<F>>(), p,
-                                                                        E.window_sums.as<XYZZMem<F>>());
-    LAUNCH_CHECK();
-    k_window_combine<F><<<1, 32, 0, st>>>(E.window_sums.as<XYZZMem<F>>(), p,
-                                          reinterpret_cast<JacobianMem<F> *>(d_out));
-    LAUNCH_CHECK();
+    CUDA_TRY(cudaEventRecord(E.ev_join, s_tail));                  // the tail stream is last in every chain
+    CUDA_TRY(cudaStreamWaitEvent(st, E.ev_join, 0));
     CUDA_TRY(cudaEventRecord(E.done, st));
     E.has_pending = true;
     return B200_OK;
@@ -193,14 +274,14 @@ template <class C>
 int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st) {
     using F = typename C::F;
     if (n == 0) return B200_OK;
-    int rc = E.buckets.reserve(n * sizeof(XYZZMem<F>));
+    int rc = E.ws[0].buckets.reserve(n * sizeof(XYZZMem<F>));
     if (rc) return rc;
     constexpr int TH = 64;
     k_fixed_base_mul<F, C::SCALAR_WORDS, TH><<<ceil_div(n, TH), TH, 0, st>>>(
         reinterpret_cast<const AffineMem<F> *>(base), reinterpret_cast<const uint32_t *>(scalars), (uint32_t)n,
-        E.buckets.as<XYZZMem<F>>());
+        E.ws[0].buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
-    k_xyzz_to_affine<F, TH><<<ceil_div(n, TH), TH, 0, st>>>(E.buckets.as<XYZZMem<F>>(), (uint32_t)n,
+    k_xyzz_to_affine<F, TH><<<ceil_div(n, TH), TH, 0, st>>>(E.ws[0].buckets.as<XYZZMem<F>>(), (uint32_t)n,
                                                             reinterpret_cast<AffineMem<F> *>(out));
     LAUNCH_CHECK();
     return B200_OK;
@@ -242,6 +323,7 @@ int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStre
     template int msm_device<C>(Engine &, const void *, size_t, const void *, size_t, void *, cudaStream_t);       \
     template int pack_bases<C>(const void *, size_t, size_t, void *, cudaStream_t);                               \
     template int msm_native<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);               \
+    template int msm_batch<C>(Engine &, const b200_msm_job *, size_t, cudaStream_t);                              \
     template int sum_jacobian<C>(const void *, size_t, void *, cudaStream_t);                                     \
     template int fixed_base_mul<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);           \
     template int batch_to_affine<C>(const void *, size_t, void *, cudaStream_t);                                  \

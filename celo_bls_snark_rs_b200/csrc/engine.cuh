@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/b200_bls.h"
 #include "msm.cuh"
@@ -51,6 +52,11 @@ struct Buffer {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// workspace of one MSM in flight (grow-only); two sets so consecutive MSMs of a batch can overlap
+struct MsmWs {
+    Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums, ones, huge_slices;
+};
+
 // one cached radix-2 domain per scalar field (ntt.cuh): constants, power tables, twiddles omega^i (i < n/2)
 struct NttDomain {
     int log_n = -1;
@@ -64,8 +70,10 @@ struct Engine {
     cudaEvent_t done = nullptr;      // completion of the last MSM (orders workspace reuse across streams)
     bool has_pending = false;
     std::mutex mu;
-    // workspace (grow-only)
-    Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums, ones, huge_slices;
+    MsmWs ws[2];
+    // software pipeline of b200_msm_batch_device: sort / accumulate / tail streams and their hand-over events
+    cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sorted[2] = {}, ev_acc[2] = {}, ev_tail[2] = {};
     // staging for the host-pointer API
     Buffer h2d_bases, native_bases, scalars, result;
     // multi-pairing: Miller values, packed G2 staging
@@ -91,6 +99,7 @@ inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 // per-curve entry points; each is instantiated in its own translation unit (inst_*.cu)
 template <class C> int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
 template <class C> int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
+template <class C> int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st);
 template <class C> int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStream_t st);
 template <class C> int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st);
 template <class C> int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st);

@@ -32,13 +32,19 @@ EXPORTS = [
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
     "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
-    "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device",
+    "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_msm_batch_device",
 ]
 
 
 class Groth16Pk(ctypes.Structure):
     """b200_groth16_pk: device pointers to the packed proving-key queries."""
     _fields_ = [(k, ctypes.c_void_p) for k in ("a_query", "b_g2_query", "h_query", "l_query", "alpha_g1", "beta_g2")]
+
+
+class MsmJob(ctypes.Structure):
+    """b200_msm_job"""
+    _fields_ = [("d_bases_packed", ctypes.c_void_p), ("d_scalars", ctypes.c_void_p), ("n", ctypes.c_size_t),
+                ("d_out_jacobian", ctypes.c_void_p)]
 
 
 class B200Error(RuntimeError):
@@ -77,6 +83,7 @@ def load() -> ctypes.CDLL:
     lib.b200_ntt_device.argtypes = [i32, vp, ctypes.c_uint, i32, i32, vp]
     lib.b200_witness_map_device.argtypes = [i32, vp, vp, vp, ctypes.c_uint, vp, vp]
     lib.b200_groth16_prove_device.argtypes = [i32, ctypes.POINTER(Groth16Pk), vp, sz, sz, vp, vp, vp, ctypes.c_uint, vp, vp]
+    lib.b200_msm_batch_device.argtypes = [i32, ctypes.POINTER(MsmJob), sz, vp]
     lib.b200_sync.argtypes = [vp]
     lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
     lib.b200_launch_count.restype = ctypes.c_uint64
@@ -134,6 +141,12 @@ def msm_host_ptrs(curve: int, bases_ptr: int, stride: int, scalars_ptr: int, n: 
 
 def msm_device(curve: int, d_bases: int, d_scalars: int, n: int, d_out: int, stream: int = 0):
     _check(load().b200_msm_device(curve, d_bases, d_scalars, n, d_out, stream or None))
+
+
+def msm_batch_device(curve: int, jobs, stream: int = 0):
+    """jobs: sequence of (d_bases_packed, d_scalars, n, d_out) -- independent MSMs, pipelined in the engine."""
+    arr = (MsmJob * len(jobs))(*[MsmJob(b or None, s or None, n, o) for b, s, n, o in jobs])
+    _check(load().b200_msm_batch_device(curve, arr, len(jobs), stream or None))
 
 
 def msm_prepared_device(curve: int, d_bases_prepared: int, d_scalars: int, n: int, d_out: int, stream: int = 0):

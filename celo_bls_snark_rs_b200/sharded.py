@@ -55,3 +55,24 @@ class ShardedMsm:
         dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
         E.sum_jacobian_device(self.curve, self.gathered.data_ptr(), self.world, self.result.data_ptr(), stream)
         return self.result
+
+    def run_batch(self, jobs, stream: int = 0) -> torch.Tensor:
+        """`jobs` = [(d_bases, d_scalars, n_local), ...]: independent sharded MSMs.  The local MSMs go
+        through the engine's pipelined batch entry (sort / accumulate / tail of consecutive MSMs
+        overlap), then every MSM gets its own all-gather + sum, as in run().  Returns uint8
+        [len(jobs), jac_bytes] results (the partials themselves when world == 1)."""
+        jb = E.JAC_BYTES[self.curve]
+        k = len(jobs)
+        if getattr(self, "_batch_k", 0) < k:
+            self._partials = torch.zeros((k, jb), dtype=torch.uint8, device=self.device)
+            self._gathered = torch.zeros((k, self.world * jb), dtype=torch.uint8, device=self.device)
+            self._results = torch.zeros((k, jb), dtype=torch.uint8, device=self.device)
+            self._batch_k = k
+        E.msm_batch_device(self.curve, [(b.data_ptr(), s.data_ptr(), n, self._partials[i].data_ptr())
+                                        for i, (b, s, n) in enumerate(jobs)], stream)
+        if self.world == 1:
+            return self._partials[:k]
+        for i in range(k):
+            dist.all_gather_into_tensor(self._gathered[i], self._partials[i], group=self.group)
+            E.sum_jacobian_device(self.curve, self._gathered[i].data_ptr(), self.world, self._results[i].data_ptr(), stream)
+        return self._results[:k]

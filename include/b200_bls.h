@@ -87,6 +87,21 @@ int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, 
 int b200_msm_prepared_device(int curve, const void *d_bases_prepared, const void *d_scalars, size_t n,
                              void *d_out_jacobian, void *stream);
 
+/* `count` independent MSMs over one curve (prepared / packed bases, device pointers), software-pipelined
+ * inside the engine: the digit sort of job i+1 and the latency-bound tail (bucket reduce, window sums,
+ * Horner) of job i-1 run beside the bucket accumulation of job i, on internal streams and two workspace
+ * sets.  The reference issues such runs of MSMs itself: the three G1 MSMs of one Groth16 proof
+ * (crates/epoch-snark/src/api/prover.rs:78), and one G1 + one G2 MSM per batch for every batch handed to
+ * batch_verify_strict (crates/bls-snark-sys/src/signatures.rs:343-404).  All jobs are ordered after the
+ * work already queued on `stream`, and `stream` waits for all of them before anything queued later. */
+typedef struct {
+    const void *d_bases_packed;
+    const void *d_scalars;
+    size_t n;
+    void *d_out_jacobian;
+} b200_msm_job;
+int b200_msm_batch_device(int curve, const b200_msm_job *jobs, size_t count, void *stream);
+
 /* out = sum of `count` Jacobian points (device pointers).  Used to combine per-GPU
  * partial MSM results after the all-gather. */
 int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void *d_out_jacobian, void *stream);
