@@ -8,6 +8,8 @@
 //   B       = b_g2_query[0] + MSM(b_g2_query[1..], assignment) + beta_g2     (s = 0)
 //   C       = l_acc + h_acc                              (s A + r B1 - r s delta vanish for r = s = 0)
 // Constraint synthesis itself (serial symbolic Rust) stays on the host and is out of scope.
+#include <type_traits>
+
 #include "engine.cuh"
 #include "ntt.cuh"
 
@@ -60,10 +62,18 @@ static int groth16_prove_t(Engine &E, int field, const b200_groth16_pk *pk, cons
     const char *assign = reinterpret_cast<const char *>(d_assignment);
     const char *aux = assign + (num_assign - num_aux) * sizeof(M);
     const char *aq = reinterpret_cast<const char *>(pk->a_query), *bq = reinterpret_cast<const char *>(pk->b_g2_query);
-    if ((rc = msm_native<G1>(E, aq + sizeof(AffineMem<F1>), assign, num_assign, tmp, st))) return rc;
-    if ((rc = msm_native<G1>(E, pk->l_query, aux, num_aux, tmp + J1, st))) return rc;
-    if ((rc = msm_native<G1>(E, pk->h_query, E.g16_h.p, n - 1, tmp + 2 * J1, st))) return rc;
-    if ((rc = msm_native<G2>(E, bq + sizeof(AffineMem<F2>), assign, num_assign, tmp + 3 * J1, st))) return rc;
+    // the three G1 MSMs as one pipelined batch (sort / accumulate / tail of consecutive MSMs overlap),
+    // then the G2 MSM (same batch when G1 and G2 share the coordinate field, i.e. BW6-761)
+    const b200_msm_job g1_jobs[4] = {{aq + sizeof(AffineMem<F1>), assign, num_assign, tmp},
+                                     {pk->l_query, aux, num_aux, tmp + J1},
+                                     {pk->h_query, E.g16_h.p, n - 1, tmp + 2 * J1},
+                                     {bq + sizeof(AffineMem<F2>), assign, num_assign, tmp + 3 * J1}};
+    if constexpr (std::is_same<G1, G2>::value) {
+        if ((rc = msm_batch<G1>(E, g1_jobs, 4, st))) return rc;
+    } else {
+        if ((rc = msm_batch<G1>(E, g1_jobs, 3, st))) return rc;
+        if ((rc = msm_native<G2>(E, g1_jobs[3].d_bases_packed, assign, num_assign, tmp + 3 * J1, st))) return rc;
+    }
     k_proof_coeff<F1><<<1, 1, 0, st>>>(reinterpret_cast<const AffineMem<F1> *>(aq), reinterpret_cast<const JacobianMem<F1> *>(tmp),
                                        reinterpret_cast<const AffineMem<F1> *>(pk->alpha_g1),
                                        reinterpret_cast<JacobianMem<F1> *>(proof));
