@@ -5,9 +5,9 @@
 namespace b200 {
 
 template <class C> struct CurveTraits;
-template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; };
-template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; };
+template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128; static constexpr bool AFFINE = true; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false; };
+template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
 // keeping enough buckets in flight to fill 148 SMs.
@@ -69,9 +69,29 @@ int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStre
 // sort (digit histogram, scan, scatter, population order) -> accumulate (buckets) -> tail (bucket
 // reduce, window sums, Horner).  msm_native runs them back to back on the caller's stream;
 // msm_batch software-pipelines consecutive MSMs over three internal streams and two workspace sets.
+// batched-affine accumulation (k_bucket_accumulate_affine): per-curve switch, scratch within a byte budget
+constexpr size_t AFFINE_SCRATCH_BUDGET = (size_t)12 << 30;
+template <class C>
+static bool msm_use_affine(const MsmPlan &p, size_t n, size_t *rec_a, size_t *rec_b) {
+    using F = typename C::F;
+    static const int mode = getenv("B200_MSM_AFFINE") ? atoi(getenv("B200_MSM_AFFINE")) : 0;
+    size_t total = (size_t)p.windows * p.nb, entries = n * (size_t)p.windows;
+    *rec_a = (entries + total) / 2 + 2;
+    *rec_b = (entries + 3 * total) / 4 + 2;
+    if (!CurveTraits<C>::AFFINE || !mode) return false;
+    return (*rec_a + *rec_b) * sizeof(AffineMem<F>) <= AFFINE_SCRATCH_BUDGET && n / p.nb >= 8;
+}
+
 template <class C>
 static int msm_reserve(MsmWs &W, const MsmPlan &p, size_t n) {
     using F = typename C::F;
+    {
+        size_t ra, rb;
+        int rc0;
+        if (msm_use_affine<C>(p, n, &ra, &rb) &&
+            ((rc0 = W.aff_a.reserve(ra * sizeof(AffineMem<F>))) || (rc0 = W.aff_b.reserve(rb * sizeof(AffineMem<F>)))))
+            return rc0;
+    }
     size_t total = (size_t)p.windows * p.nb;
     uint32_t tiles = (uint32_t)ceil_div(total, SCAN_TILE);
     size_t max_huge = std::min<size_t>(total, n * (size_t)p.windows / HUGE_BUCKET + 1);
@@ -127,10 +147,34 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
     uint32_t *offsets = W.offsets.as<uint32_t>(), *bins = W.bins.as<uint32_t>();
     bool prof = E.profile && E.prof_used < Engine::PROF_SLOTS;
     if (prof) CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used], st));
-    k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
-        <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
-            bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), (uint32_t)total, p.big,
-            W.buckets.as<XYZZMem<F>>());
+    size_t ra, rb;
+    bool affine = false;
+    if constexpr (T::AFFINE) affine = msm_use_affine<C>(p, n, &ra, &rb);
+    if constexpr (T::AFFINE) {
+        if (affine) {
+            static const int variant = getenv("B200_AFFINE_VARIANT") ? atoi(getenv("B200_AFFINE_VARIANT")) : 0;
+            AffineMem<F> *sa = W.aff_a.as<AffineMem<F>>(), *sb = W.aff_b.as<AffineMem<F>>();
+            const uint32_t *so = W.sorted.as<uint32_t>(), *ord = W.order.as<uint32_t>();
+            XYZZMem<F> *bk = W.buckets.as<XYZZMem<F>>();
+#define B200_AFF_LAUNCH(TH, MB, BB, CC)                                                                              \
+    k_bucket_accumulate_affine<F, TH, MB, BB, CC><<<ceil_div(total, TH), TH, 0, st>>>(bases, so, offsets, ord,          \
+                                                                                      (uint32_t)total, p.big, sa, sb, bk)
+            switch (variant) {
+            case 1: B200_AFF_LAUNCH(64, 6, 16, 4); break;
+            case 2: B200_AFF_LAUNCH(64, 6, 32, 4); break;
+            case 3: B200_AFF_LAUNCH(128, 3, 32, 4); break;
+            case 4: B200_AFF_LAUNCH(64, 6, 32, 8); break;
+            case 5: B200_AFF_LAUNCH(32, 12, 32, 4); break;
+            default: B200_AFF_LAUNCH(128, 3, 16, 4); break;
+            }
+#undef B200_AFF_LAUNCH
+        }
+    }
+    if (!affine)
+        k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
+            <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
+                bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), (uint32_t)total, p.big,
+                W.buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     if (prof) {
         CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));

@@ -100,7 +100,7 @@ void b200_shutdown(void) {
     cudaStreamSynchronize(E->stream);
     for (MsmWs &w : E->ws)
         for (Buffer *b : {&w.counts, &w.offsets, &w.cursor, &w.tile_sums, &w.bins, &w.order, &w.sorted, &w.buckets, &w.partials,
-                          &w.window_sums, &w.ones, &w.huge_slices})
+                          &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
                       &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp})

@@ -55,6 +55,7 @@ struct Buffer {
 // workspace of one MSM in flight (grow-only); two sets so consecutive MSMs of a batch can overlap
 struct MsmWs {
     Buffer counts, offsets, cursor, tile_sums, bins, order, sorted, buckets, partials, window_sums, ones, huge_slices;
+    Buffer aff_a, aff_b;             // level outputs of the batched-affine accumulation (ping-pong)
 };
 
 // one cached radix-2 domain per scalar field (ntt.cuh): constants, power tables, twiddles omega^i (i < n/2)

@@ -259,80 +259,138 @@ struct Fp {
     }
     B200_DEV Fp sqr() const { return *this * *this; }
 
-    // ---- inversion; inv(0) = 0.  Cold path: out of line and rolled. ---------------------------
-    // Binary extended Euclid on the residue (HAC 14.61 for an odd modulus): invariants
-    // x1 * a = u, x2 * a = v (mod p); halve the even one of (u, v), else subtract the smaller
-    // from the larger.  At most 2 * BITS halvings, each a few dozen 32-bit instructions on one
-    // thread -- about 5x shorter than the Fermat chain a^(p-2) (BITS squarings + BITS/2 products
-    // of 2 N^2 multiply-adds each), which is kept as inv_fermat() for cross-checking.
-    // The input is the Montgomery residue aR, so the loop yields (aR)^-1; one Montgomery product
-    // with R^3 turns that into a^-1 R.
-    B200_DEV static bool limbs_is_one(const uint32_t (&x)[N]) {
-        uint32_t o = x[0] ^ 1u;
-#pragma unroll
-        for (int i = 1; i < N; i++) o |= x[i];
-        return o == 0;
-    }
-    B200_DEV static void limbs_shr1(uint32_t (&x)[N]) {
-#pragma unroll
-        for (int i = 0; i < N - 1; i++) x[i] = __funnelshift_r(x[i], x[i + 1], 1);
-        x[N - 1] >>= 1;
-    }
-    // x -= y, returns true when the subtraction borrowed (x < y)
-    B200_DEV static bool limbs_sub(uint32_t (&x)[N], const uint32_t (&y)[N]) {
-        uint32_t borrow;
-        sub_cc(x[0], x[0], y[0]);
-#pragma unroll
-        for (int i = 1; i < N; i++) subc_cc(x[i], x[i], y[i]);
-        subc(borrow, 0, 0);
-        return borrow != 0;
-    }
-    // x / 2 mod p for x in [0, p): (x + (x odd ? p : 0)) >> 1; x + p < 2^(32 N) for both moduli
-    B200_DEV void halve() {
-        uint32_t m = 0u - (l[0] & 1u);
-        add_cc(l[0], l[0], P::mod(0) & m);
-#pragma unroll
-        for (int i = 1; i < N - 1; i++) addc_cc(l[i], l[i], P::mod(i) & m);
-        addc(l[N - 1], l[N - 1], P::mod(N - 1) & m);
-        limbs_shr1(l);
+    // ---- inversion; inv(0) = 0.  Cold path: out of line. -------------------------------------------
+    // Bernstein-Yang "safegcd" division steps on signed 30-bit limbs (the modinv32 scheme): 30 division
+    // steps at a time are run on the low words of (f, g) only and collected in a 2x2 integer matrix,
+    // which is then applied to the full-width f, g and -- modulo p, with an exact division by 2^30 --
+    // to d, e (invariants d * a = f, e * a = g mod p).  Ends when g = 0 (f = +-1, d = +-a^-1):
+    // <= 26 / 52 outer iterations of ~800 instructions for the 377 / 761-bit moduli, against ~750 / 1500
+    // iterations of the bit-at-a-time binary Euclid it replaced (5x fewer instructions; the batched-affine
+    // bucket accumulation waits on exactly this latency) and a 570-product Fermat chain before that.
+    // The input is the Montgomery residue aR, so the loop yields (aR)^-1; one Montgomery product with
+    // R^3 turns that into a^-1 R.
+    static constexpr int L30 = (32 * N + 29) / 30;
+    static constexpr uint32_t M30 = (1u << 30) - 1u;
+    __host__ __device__ static constexpr uint32_t mod30(int i) {                 // bits [30 i, 30 i + 30) of p
+        const int pos = 30 * i, w = pos >> 5, sh = pos & 31;
+        const uint64_t lo = w < N ? P::mod(w) : 0u, hi = w + 1 < N ? P::mod(w + 1) : 0u;
+        return (uint32_t)(((hi << 32) | lo) >> sh) & M30;
     }
     B200_DEV Fp inv() const { return inv_outline(*this); }
     __device__ __noinline__ static Fp inv_outline(Fp a) {
         if (a.is_zero()) return a;
-        uint32_t u[N], v[N];
-        Fp x1 = zero(), x2 = zero();
-        x1.l[0] = 1u;
+        int32_t f[L30], g[L30], d[L30], e[L30];
 #pragma unroll
-        for (int i = 0; i < N; i++) {
-            u[i] = a.l[i];
-            v[i] = P::mod(i);
+        for (int i = 0; i < L30; i++) {
+            const int pos = 30 * i, w = pos >> 5, sh = pos & 31;
+            const uint64_t lo = a.l[w < N ? w : N - 1] * (uint64_t)(w < N), hi = w + 1 < N ? a.l[w + 1] : 0u;
+            g[i] = (int32_t)((uint32_t)(((hi << 32) | lo) >> sh) & M30);
+            f[i] = (int32_t)mod30(i);
+            d[i] = 0;
+            e[i] = i == 0;
         }
+        const uint32_t inv30 = (0u - c_mont_inv[P::INV_SLOT]) & M30;             // p^-1 mod 2^30
+        int32_t zeta = -1;
 #pragma unroll 1
-        while (!limbs_is_one(u) && !limbs_is_one(v)) {
-            if (!(u[0] & 1u)) {
-                limbs_shr1(u);
-                x1.halve();
-            } else if (!(v[0] & 1u)) {
-                limbs_shr1(v);
-                x2.halve();
-            } else {
-                uint32_t t[N];
-#pragma unroll
-                for (int i = 0; i < N; i++) t[i] = u[i];
-                if (!limbs_sub(t, v)) {             // u >= v: u -= v
-#pragma unroll
-                    for (int i = 0; i < N; i++) u[i] = t[i];
-                    x1 = x1 - x2;
-                } else {                            // v -= u
-                    limbs_sub(v, u);
-                    x2 = x2 - x1;
+        for (int iter = 0; iter < 4 * L30 + 8; iter++) {
+            // 30 division steps on the low words -> transition matrix (u v; q r), scaled by 2^30
+            int32_t u = 1, v = 0, q = 0, r = 1;
+            {
+                uint32_t fl = (uint32_t)f[0] | ((uint32_t)f[1] << 30), gl = (uint32_t)g[0] | ((uint32_t)g[1] << 30);
+#pragma unroll 1
+                for (int k = 0; k < 30; k++) {
+                    int32_t c1 = zeta >> 31, c2 = -(int32_t)(gl & 1u);
+                    uint32_t x = (fl ^ (uint32_t)c1) - (uint32_t)c1;
+                    int32_t y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+                    gl += x & (uint32_t)c2;
+                    q += y & c2;
+                    r += z & c2;
+                    c1 &= c2;
+                    zeta = (zeta ^ c1) - 1;
+                    fl += gl & (uint32_t)c1;
+                    u += q & c1;
+                    v += r & c1;
+                    gl >>= 1;
+                    u <<= 1;
+                    v <<= 1;
                 }
             }
+            {   // (d, e) <- (u d + v e, q d + r e) / 2^30 mod p
+                const int32_t sd = d[L30 - 1] >> 31, se = e[L30 - 1] >> 31;
+                int32_t md = (u & sd) + (v & se), me = (q & sd) + (r & se);
+                long long cd = (long long)u * d[0] + (long long)v * e[0], ce = (long long)q * d[0] + (long long)r * e[0];
+                md -= (int32_t)((inv30 * (uint32_t)cd + (uint32_t)md) & M30);
+                me -= (int32_t)((inv30 * (uint32_t)ce + (uint32_t)me) & M30);
+                cd += (long long)(int32_t)mod30(0) * md;
+                ce += (long long)(int32_t)mod30(0) * me;
+                cd >>= 30;
+                ce >>= 30;
+#pragma unroll
+                for (int i = 1; i < L30; i++) {
+                    cd += (long long)u * d[i] + (long long)v * e[i] + (long long)(int32_t)mod30(i) * md;
+                    ce += (long long)q * d[i] + (long long)r * e[i] + (long long)(int32_t)mod30(i) * me;
+                    d[i - 1] = (int32_t)((uint32_t)cd & M30);
+                    e[i - 1] = (int32_t)((uint32_t)ce & M30);
+                    cd >>= 30;
+                    ce >>= 30;
+                }
+                d[L30 - 1] = (int32_t)cd;
+                e[L30 - 1] = (int32_t)ce;
+            }
+            uint32_t g_any = 0;
+            {   // (f, g) <- (u f + v g, q f + r g) / 2^30 (exact)
+                long long cf = (long long)u * f[0] + (long long)v * g[0], cg = (long long)q * f[0] + (long long)r * g[0];
+                cf >>= 30;
+                cg >>= 30;
+#pragma unroll
+                for (int i = 1; i < L30; i++) {
+                    cf += (long long)u * f[i] + (long long)v * g[i];
+                    cg += (long long)q * f[i] + (long long)r * g[i];
+                    f[i - 1] = (int32_t)((uint32_t)cf & M30);
+                    g[i - 1] = (int32_t)((uint32_t)cg & M30);
+                    g_any |= (uint32_t)g[i - 1];
+                    cf >>= 30;
+                    cg >>= 30;
+                }
+                f[L30 - 1] = (int32_t)cf;
+                g[L30 - 1] = (int32_t)cg;
+                g_any |= (uint32_t)g[L30 - 1];
+            }
+            if (g_any == 0) break;
         }
-        Fp r = limbs_is_one(u) ? x1 : x2, r3;
+        // d * sign(f) in (-2p, 2p) -> [0, 2p): conditional negation, carry normalisation, += p while negative
+        const int32_t fs = f[L30 - 1] >> 31;
+        int32_t carry = 0;
+#pragma unroll
+        for (int i = 0; i < L30; i++) {
+            int32_t t = ((d[i] ^ fs) - fs) + carry;
+            carry = i < L30 - 1 ? t >> 30 : 0;
+            d[i] = i < L30 - 1 ? (int32_t)((uint32_t)t & M30) : t;
+        }
+#pragma unroll 1
+        for (int rep = 0; rep < 2; rep++) {
+            const int32_t neg = d[L30 - 1] >> 31;
+            carry = 0;
+#pragma unroll
+            for (int i = 0; i < L30; i++) {
+                int32_t t = d[i] + (int32_t)(mod30(i) & (uint32_t)neg) + carry;
+                carry = i < L30 - 1 ? t >> 30 : 0;
+                d[i] = i < L30 - 1 ? (int32_t)((uint32_t)t & M30) : t;
+            }
+        }
+        Fp x = zero();
+#pragma unroll
+        for (int i = 0; i < L30; i++) {
+            const int pos = 30 * i, w = pos >> 5, sh = pos & 31;
+            const uint64_t val = (uint64_t)(uint32_t)d[i] << sh;
+            if (w < N) x.l[w] |= (uint32_t)val;
+            if (w + 1 < N) x.l[w + 1] |= (uint32_t)(val >> 32);
+        }
+        x.reduce_once();
+        Fp r3;
 #pragma unroll
         for (int i = 0; i < N; i++) r3.l[i] = P::r3(i);
-        return r * r3;
+        return x * r3;
     }
 
     // a^(p-2) (Fermat) -- the round-1 inversion, kept to cross-check inv() on the device

@@ -270,6 +270,143 @@ k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__re
     buckets[id] = acc.store();
 }
 
+// ---- bucket accumulation with batched affine additions ------------------------------------------
+// Same job as k_bucket_accumulate (one thread per bucket), different arithmetic: the points of a bucket
+// are summed as a pairwise tree of AFFINE additions, lambda = (y2 - y1) / (x2 - x1), whose inversions
+// are shared by the whole block with Montgomery's trick -- 6 field products per addition (1 prefix
+// product, 2 to peel the shared inverse, lambda, lambda^2, y3) against 10 for the XYZZ mixed addition.
+// A level halves the point count; a thread handles its pairs in rounds of up to B, every round ends in
+// ONE field inversion per block (thread 0, binary Euclid) behind a warp-shuffle product scan.  Level
+// outputs ping-pong between two scratch arrays (per-bucket regions, sized from the bucket offsets);
+// once a bucket is down to CUT points the rest is a short XYZZ chain.  Exceptional pairs are exact:
+// P + P takes the tangent (denominator 2y), P + (-P) and infinite operands use denominator 1.
+template <class F>
+B200_DEV F aff_denominator(const Affine<F> &a, const Affine<F> &b) {
+    if (a.is_inf() || b.is_inf()) return F::one();
+    F d = b.x - a.x;
+    if (!d.is_zero()) return d;
+    F s2 = a.y + b.y;                                // equal x: 2y for P + P, 0 for P + (-P)
+    return s2.is_zero() ? F::one() : s2;
+}
+template <class F>
+B200_DEV Affine<F> aff_add_with_inverse(const Affine<F> &a, const Affine<F> &b, const F &inv) {
+    if (a.is_inf()) return b;
+    if (b.is_inf()) return a;
+    F dx = b.x - a.x, num;
+    if (dx.is_zero()) {
+        if ((a.y + b.y).is_zero()) return {F::zero(), F::zero()};
+        F xx = a.x.sqr();
+        num = xx.dbl() + xx;                         // tangent: 3 x^2 / (2 y)
+    } else {
+        num = b.y - a.y;
+    }
+    F lam = num * inv;
+    F x3 = lam.sqr() - a.x - b.x;
+    return {x3, lam * (a.x - x3) - a.y};
+}
+
+// every thread passes the product `run` of its own denominators (non-zero) and gets 1 / run back:
+// inclusive prefix and suffix product scans inside each warp (shuffles), the warp totals through shared
+// memory, one inversion of the block total.  sm: THREADS / 32 + 1 field images.
+template <class F> struct FieldInv;
+template <class F, int THREADS>
+B200_DEV F block_inverse(const F &run, typename F::Mem *sm) {
+    constexpr int NW = THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    F incl = run, sufx = run;
+#pragma unroll 1
+    for (int o = 1; o < 32; o <<= 1) {
+        F up = incl.shfl(0xffffffffu, lane >= o ? lane - o : lane);
+        F dn = sufx.shfl(0xffffffffu, lane + o < 32 ? lane + o : lane);
+        if (lane >= o) incl = incl * up;
+        if (lane + o < 32) sufx = sufx * dn;
+    }
+    if (lane == 31) sm[warp] = incl.store();
+    __syncthreads();
+    F total = F::one(), others = F::one();
+#pragma unroll 1
+    for (int v = 0; v < NW; v++) {
+        F wv = F::load(sm[v]);
+        total = total * wv;
+        if (v != warp) others = others * wv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sm[NW] = FieldInv<F>::inv(total).store();
+    __syncthreads();
+    F r = F::load(sm[NW]) * others;
+    F pe = incl.shfl(0xffffffffu, lane ? lane - 1 : 0), se = sufx.shfl(0xffffffffu, lane < 31 ? lane + 1 : 31);
+    if (lane) r = r * pe;
+    if (lane < 31) r = r * se;
+    __syncthreads();
+    return r;
+}
+
+template <class F, int THREADS, int MIN_BLOCKS, int B, int CUT>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+k_bucket_accumulate_affine(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                           const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
+                           uint32_t big, AffineMem<F> *scratch_a, AffineMem<F> *scratch_b, XYZZMem<F> *__restrict__ buckets) {
+    __shared__ typename F::Mem sm_inv[THREADS / 32 + 1];
+    const uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    bool mine = t < total_buckets;
+    uint32_t id = mine ? order[t] : 0u, lo = 0, cnt = 0;
+    if (mine) {
+        lo = offsets[id];
+        cnt = offsets[id + 1] - lo;
+        if (cnt >= big) {                            // left to k_big_buckets / k_huge_buckets
+            mine = false;
+            cnt = 0;
+        }
+    }
+    // per-bucket regions: ceil(m / 2) records in A, ceil(m / 4) in B (see msm_reserve for the totals)
+    AffineMem<F> *reg_a = scratch_a + (((size_t)lo + id) >> 1), *reg_b = scratch_b + (((size_t)lo + 3 * (size_t)id) >> 2);
+    int level = 0;
+    auto point = [&](int lvl, uint32_t j) -> Affine<F> {
+        if (lvl == 0) {
+            uint32_t e = __ldg(sorted + lo + j);
+            Affine<F> p = Affine<F>::load(ldg_mem(bases + (e & 0x7fffffffu)));
+            p.y = p.y.cneg(e >> 31);                  // -(0) = 0: the infinity encoding (0, 0) survives
+            return p;
+        }
+        const AffineMem<F> *src = (lvl & 1) ? reg_a : reg_b;
+        return Affine<F>::load(src[j]);
+    };
+    typename F::Mem prefix[B];
+    while (__syncthreads_or(cnt > (uint32_t)CUT)) {
+        const uint32_t pairs = cnt > (uint32_t)CUT ? cnt >> 1 : 0u;
+        AffineMem<F> *dst = (level & 1) ? reg_b : reg_a;           // outputs of level L are the inputs of level L + 1
+        for (uint32_t j0 = 0; __syncthreads_or(j0 < pairs); j0 += B) {
+            const int nb = j0 < pairs ? (int)min((uint32_t)B, pairs - j0) : 0;
+            F run = F::one();
+#pragma unroll 1
+            for (int j = 0; j < nb; j++) {
+                run = run * aff_denominator(point(level, 2 * (j0 + j)), point(level, 2 * (j0 + j) + 1));
+                prefix[j] = run.store();
+            }
+            F inv = block_inverse<F, THREADS>(run, sm_inv);
+#pragma unroll 1
+            for (int j = nb - 1; j >= 0; j--) {
+                Affine<F> p1 = point(level, 2 * (j0 + j)), p2 = point(level, 2 * (j0 + j) + 1);
+                F di = j ? inv * F::load(prefix[j - 1]) : inv;
+                inv = inv * aff_denominator(p1, p2);
+                dst[j0 + j] = aff_add_with_inverse(p1, p2, di).store();
+            }
+        }
+        if (pairs) {
+            if (cnt & 1u) dst[pairs] = point(level, cnt - 1).store();
+            cnt = (cnt + 1) >> 1;
+            level++;
+        }
+    }
+    if (!mine) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t j = 0; j < cnt; j++) {
+        Affine<F> p = point(level, j);
+        if (!p.is_inf()) acc.madd(p.x, p.y);
+    }
+    buckets[id] = acc.store();
+}
+
 // block-wide sum of XYZZ values held one per thread (smem tree); result valid in thread 0
 template <class F, int THREADS>
 B200_DEV XYZZ<F> block_sum(XYZZ<F> acc, XYZZMem<F> *sm) {

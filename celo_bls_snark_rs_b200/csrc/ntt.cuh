@@ -134,7 +134,7 @@ B200_DEV M ntt_ldg(const M *__restrict__ src) {
 // one pass: DIT = false: Gentleman-Sande stages from bit s_lo + k - 1 down to s_lo;
 //           DIT = true : Cooley-Tukey stages from bit s_lo up to s_lo + k - 1
 template <class F, bool DIT>
-__global__ void __launch_bounds__(1 << (NTT_TILE_LOG - 1))
+__global__ void __launch_bounds__(1 << (NTT_TILE_LOG - 1), 2)          // 2 tiles (96 KB) per SM: <= 64 registers
 k_ntt_pass(typename F::Mem *__restrict__ data, const typename F::Mem *__restrict__ tw, NttPass p) {
     extern __shared__ __align__(16) unsigned char ntt_smem[];
     using M = typename F::Mem;

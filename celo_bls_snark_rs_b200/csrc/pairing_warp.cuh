@@ -70,6 +70,36 @@ __device__ __noinline__ void w_f12_mul(const FqImg *A, const FqImg *B, FqImg *O,
     if (lane < 12) w_st(O[e], part + other);
     __syncwarp();
 }
+// O = A^2 in the power basis.  c_e = sum over UNORDERED pairs {i, j}, i + j = e (mod 12): 2 a_i a_j (i < j)
+// or a_i^2 (i = j), times -5 when i + j >= 12.  Exponent e has 7 such pairs when even, 6 when odd: the
+// m-th one is (m, e - m) for m <= e / 2 (no wrap) and (e + m - e / 2, 12 + e / 2 - m) beyond (wrap).
+// Lane (e, h) takes m = h, h + 2, ...: at most 4 products against 6 in the general product.
+__device__ __noinline__ void w_f12_sqr(const FqImg *A, FqImg *O, int lane) {
+    PFq part = PFq::zero();
+    const int e = lane % 12, h = lane / 12;
+    if (lane < 24) {
+        PFq accP = PFq::zero(), accN = PFq::zero();
+        const int half = e >> 1, count = 7 - (e & 1);
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            const int m = 2 * k + h;
+            if (m < count) {
+                const bool wrap = m > half;
+                const int i = wrap ? e + m - half : m;
+                const int j = wrap ? 12 + half - m : e - m;
+                PFq prod = w_ld(A[i]) * w_ld(A[j]);
+                if (i != j) prod = prod.dbl();
+                if (wrap) accN = accN + prod;
+                else accP = accP + prod;
+            }
+        }
+        part = accP - (accN.dbl().dbl() + accN);     // w^12 = -5
+    }
+    PFq other = part.shfl(0xffffffffu, (lane + 12) & 31);
+    __syncwarp();
+    if (lane < 12) w_st(O[e], part + other);
+    __syncwarp();
+}
 constexpr uint64_t JPACK_DENSE = 0xBA9876543210ull;  // half 0: 0,2,4,6,8,10   half 1: 1,3,5,7,9,11
 constexpr uint64_t JPACK_LINE = 0x976310ull;         // exponents {0,1,3,6,7,9}: half 0: 0,3,7  half 1: 1,6,9
 
@@ -382,7 +412,7 @@ __global__ void __launch_bounds__(32 * W_WARPS) k_w2_miller_loop(const AffineMem
 #pragma unroll 1
         for (int b = 62; b >= 0; b--) {
             if (b != 62) {                                   // f is still one before the first lines
-                w_f12_mul<6>(S.f[fa], S.f[fa], S.f[fa ^ 1], JPACK_DENSE, lane);      // f^2
+                w_f12_sqr(S.f[fa], S.f[fa ^ 1], lane);                               // f^2
                 fa ^= 1;
             }
             w_doubling_step2(S.s[0], S.s[1], two, lane);

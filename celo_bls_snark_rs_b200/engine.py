@@ -196,7 +196,7 @@ def multi_pairing(g1: np.ndarray, g2: np.ndarray, n: Optional[int] = None, want_
 
 
 def miller_product_device(d_g1: int, d_g2: int, n: int, d_out: int, stream: int = 0):
-    _check(load().b200_miller_product_bls12_377_device(d_g1, d_g2, n, d_out, stream or None))
+    _check(load().b200_miller_product_bls12_377_device(d_g1 or None, d_g2 or None, n, d_out, stream or None))
 
 
 def final_exp_device(d_vals: int, count: int, d_out: int, d_is_one: int = 0, stream: int = 0):

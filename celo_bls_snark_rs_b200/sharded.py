@@ -76,3 +76,31 @@ class ShardedMsm:
             dist.all_gather_into_tensor(self._gathered[i], self._partials[i], group=self.group)
             E.sum_jacobian_device(self.curve, self._gathered[i].data_ptr(), self.world, self._results[i].data_ptr(), stream)
         return self._results[:k]
+
+
+class ShardedPairing:
+    """Chunk-sharded product of pairings: every rank runs the Miller loops of
+    its chunk of pairs and multiplies them into ONE Fq12 Miller value (576 bytes); the single exchange
+    is an all-gather of those values; every rank then multiplies the `world` values and runs the one
+    final exponentiation.  A product of Miller values is exact, so the GT bytes equal the single-GPU
+    result (crates/bls-crypto/src/bls/signature.rs:149 semantics, pairs in any order)."""
+
+    def __init__(self, device: torch.device, group=None):
+        self.device, self.group = device, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.partial = torch.zeros(E.FQ12_BYTES, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(self.world * E.FQ12_BYTES, dtype=torch.uint8, device=device)
+        self.gt = torch.zeros(E.FQ12_BYTES, dtype=torch.uint8, device=device)
+        self.is_one = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def run(self, d_g1: torch.Tensor, d_g2: torch.Tensor, n_local: int, stream: int = 0):
+        """d_g1 / d_g2: this rank's packed affine records (96 / 192 bytes each).  Returns (gt, is_one)
+        device tensors, asynchronous on `stream` (torch's current stream, so NCCL orders after it)."""
+        E.miller_product_device(d_g1.data_ptr() if n_local else 0, d_g2.data_ptr() if n_local else 0, n_local,
+                                self.partial.data_ptr(), stream)
+        vals = self.partial
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
+            vals = self.gathered
+        E.final_exp_device(vals.data_ptr(), self.world, self.gt.data_ptr(), self.is_one.data_ptr(), stream)
+        return self.gt, self.is_one

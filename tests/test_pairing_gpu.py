@@ -82,3 +82,18 @@ def test_sharded_miller_products_equal_single_shot(eng):
     single_ok, single_gt = eng.multi_pairing(L1.affine_records(g1), L2.affine_records(g2))
     assert out.cpu().numpy().tobytes() == single_gt
     assert bool(flag.item()) == single_ok == True  # noqa: E712
+
+
+def test_sharded_pairing_wrapper_single_rank(eng):
+    """ShardedPairing (the torch.distributed wrapper) on one rank == the host-pointer API."""
+    import torch
+    from celo_bls_snark_rs_b200.sharded import ShardedPairing
+    dev = torch.device("cuda:0")
+    g1, g2 = H.signature_batch(8, 12)
+    r1 = torch.from_numpy(L1.affine_records(g1, L1.packed_stride).copy()).to(dev)
+    r2 = torch.from_numpy(L2.affine_records(g2, L2.packed_stride).copy()).to(dev)
+    job = ShardedPairing(dev)
+    gt, flag = job.run(r1, r2, len(g1))
+    eng.sync()
+    ok, want = eng.multi_pairing(L1.affine_records(g1), L2.affine_records(g2))
+    assert gt.cpu().numpy().tobytes() == want and bool(flag.item()) == ok is True

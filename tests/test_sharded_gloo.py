@@ -76,3 +76,40 @@ def test_two_rank_gloo_sharded_msm_matches_single_msm():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got[0] == want and got[1] == want
+
+
+def _pairing_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g1, g2 = H.signature_batch(n - 1, 31)                    # (sigma, -g2), (H_i, pk_i): product == 1
+        lo, hi = sharded.shard_bounds(n, world, rank)
+        part = O.miller_loop(list(zip(g1[lo:hi], g2[lo:hi])))    # this rank's Miller value (oracle stands in for the GPU)
+        t = torch.from_numpy(np.frombuffer(C.fq12_to_ark_bytes(part), dtype=np.uint8).copy())
+        gathered = sharded.gather_partials(t)
+        raw = gathered.numpy().tobytes()
+        assert len(raw) == world * 576 and raw[rank * 576:(rank + 1) * 576] == t.numpy().tobytes()
+        prod = O.FQ12_ONE
+        for r in range(world):
+            prod = O.f12_mul(prod, C.fq12_from_ark_bytes(raw[r * 576:(r + 1) * 576]))
+        q.put((rank, O.final_exponentiation(prod) == O.FQ12_ONE))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_pairing_product_is_exact():
+    """ShardedPairing's exchange on CPU: Miller values of the two chunks, all-gathered and multiplied,
+    give the same verdict as the single product (a valid 5-signature batch -> one)."""
+    n, world = 6, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pairing_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: True, 1: True}
