@@ -69,7 +69,9 @@ int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStre
 // sort (digit histogram, scan, scatter, population order) -> accumulate (buckets) -> tail (bucket
 // reduce, window sums, Horner).  msm_native runs them back to back on the caller's stream;
 // msm_batch software-pipelines consecutive MSMs over three internal streams and two workspace sets.
-// batched-affine accumulation (k_bucket_accumulate_affine): per-curve switch, scratch within a byte budget
+// batched-affine accumulation (k_bucket_accumulate_affine): EXPERIMENTAL, off unless B200_MSM_AFFINE=1 --
+// parity-green but only level with the XYZZ kernel (6.50 against 6.52 ms at n = 2^20); per-curve switch,
+// scratch within a byte budget
 constexpr size_t AFFINE_SCRATCH_BUDGET = (size_t)12 << 30;
 template <class C>
 static bool msm_use_affine(const MsmPlan &p, size_t n, size_t *rec_a, size_t *rec_b) {
@@ -156,16 +158,13 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
             AffineMem<F> *sa = W.aff_a.as<AffineMem<F>>(), *sb = W.aff_b.as<AffineMem<F>>();
             const uint32_t *so = W.sorted.as<uint32_t>(), *ord = W.order.as<uint32_t>();
             XYZZMem<F> *bk = W.buckets.as<XYZZMem<F>>();
-#define B200_AFF_LAUNCH(TH, MB, BB, CC)                                                                              \
-    k_bucket_accumulate_affine<F, TH, MB, BB, CC><<<ceil_div(total, TH), TH, 0, st>>>(bases, so, offsets, ord,          \
-                                                                                      (uint32_t)total, p.big, sa, sb, bk)
-            switch (variant) {
-            case 1: B200_AFF_LAUNCH(64, 6, 16, 4); break;
-            case 2: B200_AFF_LAUNCH(64, 6, 32, 4); break;
-            case 3: B200_AFF_LAUNCH(128, 3, 32, 4); break;
-            case 4: B200_AFF_LAUNCH(64, 6, 32, 8); break;
-            case 5: B200_AFF_LAUNCH(32, 12, 32, 4); break;
-            default: B200_AFF_LAUNCH(128, 3, 16, 4); break;
+#define B200_AFF_LAUNCH(TH, MB, BB, CC, BI)                                                                          \
+    k_bucket_accumulate_affine<F, TH, MB, BB, CC, BI><<<ceil_div(total, TH), TH, 0, st>>>(bases, so, offsets, ord,      \
+                                                                                          (uint32_t)total, p.big, sa, sb, bk)
+            switch (variant) {                                     // profiles/r1_experiments.md has the measurements
+            case 1: B200_AFF_LAUNCH(128, 3, 32, 4, true); break;   // one inversion per block and round (scans + barriers)
+            case 2: B200_AFF_LAUNCH(128, 3, 32, 4, false); break;  // per-thread inversion, tree down to 4 points
+            default: B200_AFF_LAUNCH(128, 3, 32, 8, false); break; // per-thread inversion, tree down to 8 points
             }
 #undef B200_AFF_LAUNCH
         }

@@ -390,7 +390,7 @@ struct Fp {
         Fp r3;
 #pragma unroll
         for (int i = 0; i < N; i++) r3.l[i] = P::r3(i);
-        return x * r3;
+        return mul_outline(x, r3);                    // shared body: keeps this cold function small
     }
 
     // a^(p-2) (Fermat) -- the round-1 inversion, kept to cross-check inv() on the device

@@ -280,6 +280,35 @@ k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__re
 // outputs ping-pong between two scratch arrays (per-bucket regions, sized from the bucket offsets);
 // once a bucket is down to CUT points the rest is a short XYZZ chain.  Exceptional pairs are exact:
 // P + P takes the tangent (denominator 2y), P + (-P) and infinite operands use denominator 1.
+// The affine kernel's warps are spread over different phases (prefix products, inversion, peel-off,
+// final chain), so its instruction working set is the whole kernel: with the 600-instruction Montgomery
+// product inlined at ~20 sites it thrashed the instruction cache (ncu: 2.1 "no instruction" stalls per
+// issue).  Everything in this kernel therefore multiplies through ONE out-of-line body.
+template <class F> struct Shared {
+    B200_DEV static F mul(const F &a, const F &b) { return a * b; }                 // Fp2 / 24-limb: already out of line
+};
+template <class P> struct Shared<Fp<P>> {
+    B200_DEV static Fp<P> mul(const Fp<P> &a, const Fp<P> &b) { return Fp<P>::mul_outline(a, b); }
+};
+// this += (px, py), XYZZ mixed addition built on the shared product (see XYZZ::madd for the formulas)
+template <class F>
+__device__ __noinline__ XYZZ<F> xyzz_madd_shared(XYZZ<F> a, F px, F py) {
+    using S = Shared<F>;
+    if (a.is_inf()) return {px, py, F::one(), F::one()};
+    F p = S::mul(px, a.zz) - a.x;
+    F r = S::mul(py, a.zzz) - a.y;
+    if (p.is_zero()) return r.is_zero() ? XYZZ<F>::dbl_affine(px, py) : XYZZ<F>::inf();
+    F pp = S::mul(p, p);
+    F ppp = S::mul(p, pp);
+    F q = S::mul(a.x, pp);
+    XYZZ<F> o;
+    o.x = S::mul(r, r) - ppp - q.dbl();
+    o.y = S::mul(r, q - o.x) - S::mul(a.y, ppp);
+    o.zz = S::mul(a.zz, pp);
+    o.zzz = S::mul(a.zzz, ppp);
+    return o;
+}
+
 template <class F>
 B200_DEV F aff_denominator(const Affine<F> &a, const Affine<F> &b) {
     if (a.is_inf() || b.is_inf()) return F::one();
@@ -295,14 +324,14 @@ B200_DEV Affine<F> aff_add_with_inverse(const Affine<F> &a, const Affine<F> &b, 
     F dx = b.x - a.x, num;
     if (dx.is_zero()) {
         if ((a.y + b.y).is_zero()) return {F::zero(), F::zero()};
-        F xx = a.x.sqr();
+        F xx = Shared<F>::mul(a.x, a.x);
         num = xx.dbl() + xx;                         // tangent: 3 x^2 / (2 y)
     } else {
         num = b.y - a.y;
     }
-    F lam = num * inv;
-    F x3 = lam.sqr() - a.x - b.x;
-    return {x3, lam * (a.x - x3) - a.y};
+    F lam = Shared<F>::mul(num, inv);
+    F x3 = Shared<F>::mul(lam, lam) - a.x - b.x;
+    return {x3, Shared<F>::mul(lam, a.x - x3) - a.y};
 }
 
 // every thread passes the product `run` of its own denominators (non-zero) and gets 1 / run back:
@@ -318,8 +347,8 @@ B200_DEV F block_inverse(const F &run, typename F::Mem *sm) {
     for (int o = 1; o < 32; o <<= 1) {
         F up = incl.shfl(0xffffffffu, lane >= o ? lane - o : lane);
         F dn = sufx.shfl(0xffffffffu, lane + o < 32 ? lane + o : lane);
-        if (lane >= o) incl = incl * up;
-        if (lane + o < 32) sufx = sufx * dn;
+        if (lane >= o) incl = Shared<F>::mul(incl, up);
+        if (lane + o < 32) sufx = Shared<F>::mul(sufx, dn);
     }
     if (lane == 31) sm[warp] = incl.store();
     __syncthreads();
@@ -327,21 +356,24 @@ B200_DEV F block_inverse(const F &run, typename F::Mem *sm) {
 #pragma unroll 1
     for (int v = 0; v < NW; v++) {
         F wv = F::load(sm[v]);
-        total = total * wv;
-        if (v != warp) others = others * wv;
+        total = Shared<F>::mul(total, wv);
+        if (v != warp) others = Shared<F>::mul(others, wv);
     }
     __syncthreads();
     if (threadIdx.x == 0) sm[NW] = FieldInv<F>::inv(total).store();
     __syncthreads();
-    F r = F::load(sm[NW]) * others;
+    F r = Shared<F>::mul(F::load(sm[NW]), others);
     F pe = incl.shfl(0xffffffffu, lane ? lane - 1 : 0), se = sufx.shfl(0xffffffffu, lane < 31 ? lane + 1 : 31);
-    if (lane) r = r * pe;
-    if (lane < 31) r = r * se;
+    if (lane) r = Shared<F>::mul(r, pe);
+    if (lane < 31) r = Shared<F>::mul(r, se);
     __syncthreads();
     return r;
 }
 
-template <class F, int THREADS, int MIN_BLOCKS, int B, int CUT>
+// BLOCKINV = false: every thread inverts its own running product (32 independent safegcd inversions
+// cost a warp the instructions of one; they are mostly ALU-pipe work beside the other warps' multiplier
+// work) -- no scans, no block barriers, warps stay independent as in k_bucket_accumulate.
+template <class F, int THREADS, int MIN_BLOCKS, int B, int CUT, bool BLOCKINV>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_bucket_accumulate_affine(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                            const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
@@ -372,23 +404,23 @@ k_bucket_accumulate_affine(const AffineMem<F> *__restrict__ bases, const uint32_
         return Affine<F>::load(src[j]);
     };
     typename F::Mem prefix[B];
-    while (__syncthreads_or(cnt > (uint32_t)CUT)) {
+    while (BLOCKINV ? __syncthreads_or(cnt > (uint32_t)CUT) : cnt > (uint32_t)CUT) {
         const uint32_t pairs = cnt > (uint32_t)CUT ? cnt >> 1 : 0u;
         AffineMem<F> *dst = (level & 1) ? reg_b : reg_a;           // outputs of level L are the inputs of level L + 1
-        for (uint32_t j0 = 0; __syncthreads_or(j0 < pairs); j0 += B) {
+        for (uint32_t j0 = 0; BLOCKINV ? __syncthreads_or(j0 < pairs) : j0 < pairs; j0 += B) {
             const int nb = j0 < pairs ? (int)min((uint32_t)B, pairs - j0) : 0;
             F run = F::one();
 #pragma unroll 1
             for (int j = 0; j < nb; j++) {
-                run = run * aff_denominator(point(level, 2 * (j0 + j)), point(level, 2 * (j0 + j) + 1));
+                run = Shared<F>::mul(run, aff_denominator(point(level, 2 * (j0 + j)), point(level, 2 * (j0 + j) + 1)));
                 prefix[j] = run.store();
             }
-            F inv = block_inverse<F, THREADS>(run, sm_inv);
+            F inv = BLOCKINV ? block_inverse<F, THREADS>(run, sm_inv) : FieldInv<F>::inv(run);
 #pragma unroll 1
             for (int j = nb - 1; j >= 0; j--) {
                 Affine<F> p1 = point(level, 2 * (j0 + j)), p2 = point(level, 2 * (j0 + j) + 1);
-                F di = j ? inv * F::load(prefix[j - 1]) : inv;
-                inv = inv * aff_denominator(p1, p2);
+                F di = j ? Shared<F>::mul(inv, F::load(prefix[j - 1])) : inv;
+                inv = Shared<F>::mul(inv, aff_denominator(p1, p2));
                 dst[j0 + j] = aff_add_with_inverse(p1, p2, di).store();
             }
         }
@@ -402,7 +434,7 @@ k_bucket_accumulate_affine(const AffineMem<F> *__restrict__ bases, const uint32_
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t j = 0; j < cnt; j++) {
         Affine<F> p = point(level, j);
-        if (!p.is_inf()) acc.madd(p.x, p.y);
+        if (!p.is_inf()) acc = xyzz_madd_shared(acc, p.x, p.y);
     }
     buckets[id] = acc.store();
 }
