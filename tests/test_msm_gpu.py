@@ -242,3 +242,40 @@ def test_sharded_run_batch_single_rank(eng):
     eng.sync()
     for i in range(5):
         assert L.jacobian_compressed(out[i].cpu().numpy().tobytes()) == sets[i & 1][2]
+
+
+def test_config4_bw6_761_large_linearity_and_c_oracle(eng):
+    """BASELINE config 4's curve at sizes the Python oracle cannot reach: BW6-761 G1, n = 2^18 against
+    the C oracle, and n = 2^20 through linearity MSM(b, s) + MSM(b, t) == MSM(b, s + t) (no reduction of
+    s + t: the seeded base point need not lie in the prime-order subgroup; s, t < 2^376 so the sum fits)."""
+    import torch
+    name = "bw6_761_g1"
+    L = C.LAYOUTS[name]
+    dev = torch.device("cuda:0")
+    n = 1 << 20
+    rng = O.SplitMix64(4)
+    g = H.generator(name, rng)
+    ks = H.random_scalars_array(L, n, 321)
+    d_gen = torch.from_numpy(L.affine_records([g], L.packed_stride).copy()).to(dev)
+    d_ks = torch.from_numpy(ks.view(np.int64)).to(dev)
+    d_bases = torch.empty((n, L.packed_stride), dtype=torch.uint8, device=dev)
+    eng.fixed_base_mul_device(L.id, d_gen.data_ptr(), d_ks.data_ptr(), n, d_bases.data_ptr())
+    eng.sync()
+    m = 1 << 18
+    bases_m = d_bases[:m].cpu().numpy()
+    s = H.random_scalars_array(L, n, 11)
+    t = H.random_scalars_array(L, n, 12)
+    st = L.scalars_array([a + b for a, b in zip(L.scalars_from_array(s), L.scalars_from_array(t))])
+    d_out = torch.empty(4 * L.jac_bytes, dtype=torch.uint8, device=dev)
+    keep = []
+    jobs = []
+    for j, (arr, cnt) in enumerate(((s, n), (t, n), (st, n), (s, m))):
+        d_sc = torch.from_numpy(arr.view(np.int64)).to(dev)
+        keep.append(d_sc)
+        jobs.append((d_bases.data_ptr(), d_sc.data_ptr(), cnt, d_out.data_ptr() + j * L.jac_bytes))
+    eng.msm_batch_device(L.id, jobs)                    # the four MSMs as one pipelined batch
+    eng.sync()
+    raw = d_out.cpu().numpy().tobytes()
+    pts = [L.jacobian_to_affine(raw[j * L.jac_bytes:(j + 1) * L.jac_bytes]) for j in range(4)]
+    assert L.curve.padd(pts[0], pts[1]) == pts[2]
+    assert pts[3] == L.jacobian_to_affine(C.msm(L, bases_m, s[:m]))

@@ -97,3 +97,30 @@ def test_sharded_pairing_wrapper_single_rank(eng):
     eng.sync()
     ok, want = eng.multi_pairing(L1.affine_records(g1), L2.affine_records(g2))
     assert gt.cpu().numpy().tobytes() == want and bool(flag.item()) == ok is True
+
+
+def test_config2_full_size_4096_signatures(eng):
+    """BASELINE config 2 at full size: 4096 signatures -> a 4097-pair product.  Size-independent
+    properties: the valid batch verifies, one corrupted message hash does not, and the product over
+    two halves of the pairs (as two GPUs would compute it) gives the same GT bytes."""
+    import torch
+    n = 4096
+    g1, g2 = H.signature_batch(n, 2026)
+    r1, r2 = L1.affine_records(g1), L2.affine_records(g2)
+    ok, gt = eng.multi_pairing(r1, r2)
+    assert ok is True and gt == C.fq12_to_ark_bytes(O.FQ12_ONE)
+    g1b, g2b = H.signature_batch(n, 2026, corrupt=1234)
+    bad, _ = eng.multi_pairing(L1.affine_records(g1b), L2.affine_records(g2b), want_gt=False)
+    assert bad is False
+    dev = torch.device("cuda:0")
+    p1 = torch.from_numpy(L1.affine_records(g1b, L1.packed_stride).copy()).to(dev)
+    p2 = torch.from_numpy(L2.affine_records(g2b, L2.packed_stride).copy()).to(dev)
+    parts = torch.zeros((2, 576), dtype=torch.uint8, device=dev)
+    out = torch.zeros(576, dtype=torch.uint8, device=dev)
+    k = 2001
+    eng.miller_product_device(p1.data_ptr(), p2.data_ptr(), k, parts[0].data_ptr())
+    eng.miller_product_device(p1[k:].data_ptr(), p2[k:].data_ptr(), n + 1 - k, parts[1].data_ptr())
+    eng.final_exp_device(parts.data_ptr(), 2, out.data_ptr())
+    eng.sync()
+    _, gt_bad = eng.multi_pairing(L1.affine_records(g1b), L2.affine_records(g2b))
+    assert out.cpu().numpy().tobytes() == gt_bad != gt
