@@ -20,6 +20,11 @@ static MsmPlan make_plan(size_t n) {
         double nb = (double)(1u << (c - 1));
         // 10.5 ~ mixed add, 2*14 running-sum adds + ~20 for the segment scalar-mul / tree share
         double cost = windows * ((double)n * 10.5 + nb * 48.0);
+        // a top window holding only a few scalar bits piles all n points into a handful of buckets: those
+        // go through the block-per-bucket paths at a fraction of the machine (measured: BW6-761, n = 2^20,
+        // c = 15 -> 3 top bits: 57 ms against 45 / 47 ms for c = 14 / 16)
+        int top_bits = C::SCALAR_BITS + 1 - (windows - 1) * c;
+        if (top_bits <= 6 && top_bits < c - 4 && n >= 4096) cost += (double)n * 10.5 * 3.0;
         // starve penalty: fewer bucket-threads than the machine holds means idle SMs
         double threads = windows * nb;
         if (threads < 148.0 * 384.0) cost *= 1.0 + 0.35 * (148.0 * 384.0 / threads - 1.0);
@@ -243,8 +248,10 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
 // `count` independent MSMs (native packed bases), software-pipelined: the sort of job i+1 and the tail
 // of job i-1 run on their own streams beside the accumulation of job i (workspace sets alternate).
 // Everything is ordered after `st`'s prior work and joined back into `st` before returning.
+// ready (optional): ready[i] is recorded (on any stream) once job i's inputs are in place; the
+// sort of job i waits for it.  Used by the host-pointer API to overlap H2D copies with compute.
 template <class C>
-int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st) {
+int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st, const cudaEvent_t *ready) {
     using F = typename C::F;
     int rc;
     std::vector<MsmPlan> plans(count);
@@ -271,6 +278,7 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
         }
         const int w = (int)(k & 1);
         MsmWs &W = E.ws[w];
+        if (ready) CUDA_TRY(cudaStreamWaitEvent(s_sort, ready[i], 0));
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(s_sort, E.ev_acc[w], 0));      // sort buffers of job k-2 consumed
         if ((rc = msm_stage_sort<C>(E, W, plans[i], jobs[i].d_scalars, jobs[i].n, s_sort))) return rc;
         CUDA_TRY(cudaEventRecord(E.ev_sorted[w], s_sort));
@@ -366,7 +374,7 @@ int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStre
     template int msm_device<C>(Engine &, const void *, size_t, const void *, size_t, void *, cudaStream_t);       \
     template int pack_bases<C>(const void *, size_t, size_t, void *, cudaStream_t);                               \
     template int msm_native<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);               \
-    template int msm_batch<C>(Engine &, const b200_msm_job *, size_t, cudaStream_t);                              \
+    template int msm_batch<C>(Engine &, const b200_msm_job *, size_t, cudaStream_t, const cudaEvent_t *);         \
     template int sum_jacobian<C>(const void *, size_t, void *, cudaStream_t);                                     \
     template int fixed_base_mul<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);           \
     template int batch_to_affine<C>(const void *, size_t, void *, cudaStream_t);                                  \

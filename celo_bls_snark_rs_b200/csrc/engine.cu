@@ -87,6 +87,8 @@ int b200_init(int device) {
         for (cudaEvent_t *ev : {&E->ev_fork, &E->ev_join, &E->ev_sorted[0], &E->ev_sorted[1], &E->ev_acc[0], &E->ev_acc[1],
                                 &E->ev_tail[0], &E->ev_tail[1]})
             CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &ev : E->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     g_engine = E;
     return B200_OK;
@@ -115,6 +117,9 @@ void b200_shutdown(void) {
         if (ev) cudaEventDestroy(ev);
     for (cudaStream_t s : E->pipe_stream)
         if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t ev : E->ev_chunk)
+        if (ev) cudaEventDestroy(ev);
+    if (E->copy_stream) cudaStreamDestroy(E->copy_stream);
     cudaStreamDestroy(E->stream);
     delete E;
     g_engine = nullptr;
@@ -155,7 +160,7 @@ int b200_msm_batch_device(int curve, const b200_msm_job *jobs, size_t count, voi
     if (count == 0) return B200_OK;
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    return DISPATCH_CURVE(curve, msm_batch, E, jobs, count, st);
+    return DISPATCH_CURVE(curve, msm_batch, E, jobs, count, st, nullptr);
 }
 
 int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, int src_on_device, void *d_dst_packed,
@@ -175,6 +180,11 @@ int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, 
     return DISPATCH_CURVE(curve, pack_bases, dsrc, stride, n, d_dst_packed, st);
 }
 
+// Large inputs are cut into chunks: chunk c + 1 crosses PCIe (copy stream) while chunk c is being
+// multiplied -- each chunk is one job of the pipelined batch, gated by its `ready` event -- and the
+// chunk results are summed on the device.  Small inputs take the single-MSM path.
+constexpr size_t HOST_CHUNK_MIN = (size_t)1 << 18;
+
 int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian) {
     CurveInfo ci;
     if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
@@ -182,18 +192,48 @@ int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalar
     REQUIRE_ENGINE();
     cudaStream_t st = E.stream;
     int rc;
-    if ((rc = E.result.reserve(ci.jac_bytes))) return rc;
-    const void *d_bases = nullptr;
+    const size_t packed = 2 * ci.coord_bytes;
+    if ((rc = E.result.reserve((Engine::MAX_CHUNKS + 1) * ci.jac_bytes))) return rc;
+    char *res = E.result.as<char>();
     if (n) {
-        if (stride % 4 || stride < 2 * ci.coord_bytes) return fail(B200_ERR_ARG, "bad base stride %zu", stride);
+        if (stride % 4 || stride < packed) return fail(B200_ERR_ARG, "bad base stride %zu", stride);
         if ((rc = E.scalars.reserve(n * ci.scalar_bytes)) || (rc = E.h2d_bases.reserve(n * stride))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(E.scalars.p, scalars, n * ci.scalar_bytes, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bases, n * stride, cudaMemcpyHostToDevice, st));
-        d_bases = E.h2d_bases.p;
+        if (stride != packed && (rc = E.native_bases.reserve(n * packed))) return rc;
     }
-    rc = DISPATCH_CURVE(curve, msm_device, E, d_bases, stride, E.scalars.p, n, E.result.p, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_jacobian, E.result.p, ci.jac_bytes, cudaMemcpyDeviceToHost, st));
+    static const bool no_chunks = getenv("B200_HOST_NOCHUNK") != nullptr;
+    const int chunks = (n < HOST_CHUNK_MIN || no_chunks) ? 1 : (n < ((size_t)1 << 22) ? 2 : Engine::MAX_CHUNKS);
+    if (chunks == 1) {
+        const void *d_bases = nullptr;
+        if (n) {
+            CUDA_TRY(cudaMemcpyAsync(E.scalars.p, scalars, n * ci.scalar_bytes, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bases, n * stride, cudaMemcpyHostToDevice, st));
+            d_bases = E.h2d_bases.p;
+        }
+        rc = DISPATCH_CURVE(curve, msm_device, E, d_bases, stride, E.scalars.p, n, res, st);
+        if (rc) return rc;
+    } else {
+        b200_msm_job jobs[Engine::MAX_CHUNKS];
+        cudaStream_t cs = E.copy_stream;
+        if (E.has_pending) CUDA_TRY(cudaStreamWaitEvent(cs, E.done, 0));      // staging buffers may still feed a prior MSM
+        const char *hb = reinterpret_cast<const char *>(bases), *hs = reinterpret_cast<const char *>(scalars);
+        char *db = E.h2d_bases.as<char>(), *ds = E.scalars.as<char>(), *dn = E.native_bases.as<char>();
+        for (int c = 0; c < chunks; c++) {
+            const size_t lo = n * c / chunks, cnt = n * (c + 1) / chunks - lo;
+            CUDA_TRY(cudaMemcpyAsync(ds + lo * ci.scalar_bytes, hs + lo * ci.scalar_bytes, cnt * ci.scalar_bytes,
+                                     cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(db + lo * stride, hb + lo * stride, cnt * stride, cudaMemcpyHostToDevice, cs));
+            const void *chunk_bases = db + lo * stride;
+            if (stride != packed) {
+                if ((rc = DISPATCH_CURVE(curve, pack_bases, db + lo * stride, stride, cnt, dn + lo * packed, cs))) return rc;
+                chunk_bases = dn + lo * packed;
+            }
+            CUDA_TRY(cudaEventRecord(E.ev_chunk[c], cs));
+            jobs[c] = {chunk_bases, ds + lo * ci.scalar_bytes, cnt, res + (size_t)(c + 1) * ci.jac_bytes};
+        }
+        if ((rc = DISPATCH_CURVE(curve, msm_batch, E, jobs, (size_t)chunks, st, E.ev_chunk))) return rc;
+        if ((rc = DISPATCH_CURVE(curve, sum_jacobian, res + ci.jac_bytes, (size_t)chunks, res, st))) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(out_jacobian, res, ci.jac_bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return B200_OK;
 }

@@ -75,6 +75,10 @@ struct Engine {
     // software pipeline of b200_msm_batch_device: sort / accumulate / tail streams and their hand-over events
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sorted[2] = {}, ev_acc[2] = {}, ev_tail[2] = {};
+    // host-pointer MSM: chunked H2D copies on their own stream, one `ready` event per chunk
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int MAX_CHUNKS = 4;
+    cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
     // staging for the host-pointer API
     Buffer h2d_bases, native_bases, scalars, result;
     // multi-pairing: Miller values, packed G2 staging
@@ -100,7 +104,7 @@ inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 // per-curve entry points; each is instantiated in its own translation unit (inst_*.cu)
 template <class C> int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
 template <class C> int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
-template <class C> int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st);
+template <class C> int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st, const cudaEvent_t *ready = nullptr);
 template <class C> int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStream_t st);
 template <class C> int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st);
 template <class C> int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st);

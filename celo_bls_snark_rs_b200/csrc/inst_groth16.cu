@@ -69,9 +69,9 @@ static int groth16_prove_t(Engine &E, int field, const b200_groth16_pk *pk, cons
                                      {pk->h_query, E.g16_h.p, n - 1, tmp + 2 * J1},
                                      {bq + sizeof(AffineMem<F2>), assign, num_assign, tmp + 3 * J1}};
     if constexpr (std::is_same<G1, G2>::value) {
-        if ((rc = msm_batch<G1>(E, g1_jobs, 4, st))) return rc;
+        if ((rc = msm_batch<G1>(E, g1_jobs, 4, st, nullptr))) return rc;
     } else {
-        if ((rc = msm_batch<G1>(E, g1_jobs, 3, st))) return rc;
+        if ((rc = msm_batch<G1>(E, g1_jobs, 3, st, nullptr))) return rc;
         if ((rc = msm_native<G2>(E, g1_jobs[3].d_bases_packed, assign, num_assign, tmp + 3 * J1, st))) return rc;
     }
     k_proof_coeff<F1><<<1, 1, 0, st>>>(reinterpret_cast<const AffineMem<F1> *>(aq), reinterpret_cast<const JacobianMem<F1> *>(tmp),
