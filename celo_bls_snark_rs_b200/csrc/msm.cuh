@@ -439,6 +439,41 @@ k_bucket_accumulate_affine(const AffineMem<F> *__restrict__ bases, const uint32_
     buckets[id] = acc.store();
 }
 
+// k_bucket_accumulate with every product through the shared out-of-line body: code size 117 KB -> ~12 KB
+// against ~8 % call overhead; the default for the 12-limb field (B200_MSM_SHAREDMUL=0 selects the inlined kernel)
+template <class F, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+k_bucket_accumulate_shared(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                           const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
+                           uint32_t big, XYZZMem<F> *__restrict__ buckets) {
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    if (t >= total_buckets) return;
+    uint32_t id = order[t];
+    uint32_t k = offsets[id], end = offsets[id + 1];
+    if (end - k >= big) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (k < end) {
+        uint32_t e = __ldg(sorted + k);
+        AffineMem<F> img = ldg_mem(bases + (e & 0x7fffffffu));
+        for (;;) {
+            ++k;
+            uint32_t e_next = 0;
+            AffineMem<F> img_next;
+            bool more = k < end;
+            if (more) {
+                e_next = __ldg(sorted + k);
+                img_next = ldg_mem(bases + (e_next & 0x7fffffffu));
+            }
+            Affine<F> pt = Affine<F>::load(img);
+            if (!pt.is_inf()) acc = xyzz_madd_shared(acc, pt.x, pt.y.cneg(e >> 31));
+            if (!more) break;
+            e = e_next;
+            img = img_next;
+        }
+    }
+    buckets[id] = acc.store();
+}
+
 // block-wide sum of XYZZ values held one per thread (smem tree); result valid in thread 0
 template <class F, int THREADS>
 B200_DEV XYZZ<F> block_sum(XYZZ<F> acc, XYZZMem<F> *sm) {
