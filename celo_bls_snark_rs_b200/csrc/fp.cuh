@@ -257,7 +257,80 @@ struct Fp {
             return mul_outline(a, b);
         }
     }
-    B200_DEV Fp sqr() const { return *this * *this; }
+    B200_DEV Fp sqr() const;                       // dedicated squaring, defined below
+
+    // ---- dedicated squaring -----------------------------------------------------------------------
+    // a^2 = sum_i a_i 2^(32 i) * w_i with w_i = a_i + 2 * (a >> 32 (i + 1)) << 32: row i of the
+    // interleaved product multiplies a_i by the limbs j >= i of w_i only (the products with j < i are
+    // the ones already counted by doubling), so N (N - 1) / 2 of the N^2 operand products disappear
+    // (66 of 144 for 12 limbs; the reduction products stay): 222 wide multiply-adds instead of 288.
+    // Where the general row shifts the odd accumulator inside a product chain, skipped products become
+    // plain add-with-carry moves (ALU pipe, not the multiplier).  Requires a < 2^(32 N - 1): true for
+    // all three moduli (377 / 761 / 253 bits), so doubling never carries out of the top limb.
+    template <int ROW>
+    B200_DEV static uint32_t sq_limb(const uint32_t (&a)[N], int j) {             // limb j >= ROW of w_ROW
+        return j == ROW ? a[j] : (j == ROW + 1 ? a[j] << 1 : __funnelshift_l(a[j - 1], a[j], 1));
+    }
+    template <int ROW>
+    B200_DEV static void mont_row_sq(uint32_t (&even)[N], uint32_t (&odd)[N], const uint32_t (&a)[N], uint32_t inv) {
+        const uint32_t bi = a[ROW];
+        if (ROW == 0) {
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                mul_wide(odd[j], odd[j + 1], sq_limb<ROW>(a, j + 1), bi);
+                mul_wide(even[j], even[j + 1], sq_limb<ROW>(a, j), bi);
+            }
+        } else {
+            add_cc(even[0], even[0], odd[1]);
+#pragma unroll
+            for (int j = 0; j < N - 2; j += 2) {
+                if (j + 1 >= ROW) {
+                    madc_wide_cc(odd[j], odd[j + 1], sq_limb<ROW>(a, j + 1), bi, odd[j + 2], odd[j + 3]);
+                } else {                                                          // skipped product: shift with carry
+                    addc_cc(odd[j], odd[j + 2], 0);
+                    addc_cc(odd[j + 1], odd[j + 3], 0);
+                }
+            }
+            madc_wide_top(odd[N - 2], odd[N - 1], sq_limb<ROW>(a, N - 1), bi);     // N - 1 >= ROW always
+            // even chain: starts at the first limb index >= ROW of its parity, nothing to add below it
+            constexpr int J0 = (ROW + 1) & ~1;                                    // first even j >= ROW
+            if (J0 < N) {
+                mad_wide_cc(even[J0], even[J0 + 1], sq_limb<ROW>(a, J0), bi);
+#pragma unroll
+                for (int j = J0 + 2; j < N; j += 2) madc_wide_cc(even[j], even[j + 1], sq_limb<ROW>(a, j), bi);
+                addc(odd[N - 1], odd[N - 1], 0);
+            }
+        }
+        uint32_t m = even[0] * inv;
+        mad_wide_cc(odd[0], odd[1], P::mod(1), m);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(odd[j], odd[j + 1], P::mod(j + 1), m);
+        mad_wide_cc(even[0], even[1], P::mod(0), m);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) madc_wide_cc(even[j], even[j + 1], P::mod(j), m);
+        addc(odd[N - 1], odd[N - 1], 0);
+    }
+    template <int ROW>
+    B200_DEV static void sq_rows(uint32_t (&even)[N], uint32_t (&odd)[N], const uint32_t (&a)[N], uint32_t inv) {
+        if constexpr (ROW < N) {
+            mont_row_sq<ROW>(even, odd, a, inv);
+            mont_row_sq<ROW + 1>(odd, even, a, inv);
+            sq_rows<ROW + 2>(even, odd, a, inv);
+        }
+    }
+    B200_DEV static Fp sqr_inline(const Fp &a) {
+        const uint32_t inv = c_mont_inv[P::INV_SLOT];
+        uint32_t even[N], odd[N];
+        sq_rows<0>(even, odd, a.l, inv);
+        Fp r;
+        add_cc(r.l[0], even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) addc_cc(r.l[i], even[i], odd[i + 1]);
+        addc(r.l[N - 1], even[N - 1], 0);
+        r.reduce_once();
+        return r;
+    }
+    __device__ __noinline__ static Fp sqr_outline(Fp a) { return sqr_inline(a); }
 
     // ---- inversion; inv(0) = 0.  Cold path: out of line. -------------------------------------------
     // Bernstein-Yang "safegcd" division steps on signed 30-bit limbs (the modinv32 scheme): 30 division
@@ -415,6 +488,16 @@ struct Fp {
         return acc;
     }
 };
+
+// same inlining policy as operator*: 12 limbs and fewer inline, the 24-limb body shared
+template <class P>
+B200_DEV Fp<P> Fp<P>::sqr() const {
+    if constexpr (N <= 12) {
+        return sqr_inline(*this);
+    } else {
+        return sqr_outline(*this);
+    }
+}
 
 using Fq377 = Fp<Fq377Params>;
 using Fq761 = Fp<Fq761Params>;

@@ -285,10 +285,12 @@ k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__re
 // product inlined at ~20 sites it thrashed the instruction cache (ncu: 2.1 "no instruction" stalls per
 // issue).  Everything in this kernel therefore multiplies through ONE out-of-line body.
 template <class F> struct Shared {
-    B200_DEV static F mul(const F &a, const F &b) { return a * b; }                 // Fp2 / 24-limb: already out of line
+    B200_DEV static F mul(const F &a, const F &b) { return a * b; }                 // Fp2: already out of line
+    B200_DEV static F sqr(const F &a) { return a.sqr(); }
 };
 template <class P> struct Shared<Fp<P>> {
     B200_DEV static Fp<P> mul(const Fp<P> &a, const Fp<P> &b) { return Fp<P>::mul_outline(a, b); }
+    B200_DEV static Fp<P> sqr(const Fp<P> &a) { return Fp<P>::sqr_outline(a); }      // dedicated squaring (fp.cuh)
 };
 // this += (px, py), XYZZ mixed addition built on the shared product (see XYZZ::madd for the formulas)
 template <class F>
@@ -298,11 +300,11 @@ __device__ __noinline__ XYZZ<F> xyzz_madd_shared(XYZZ<F> a, F px, F py) {
     F p = S::mul(px, a.zz) - a.x;
     F r = S::mul(py, a.zzz) - a.y;
     if (p.is_zero()) return r.is_zero() ? XYZZ<F>::dbl_affine(px, py) : XYZZ<F>::inf();
-    F pp = S::mul(p, p);
+    F pp = S::sqr(p);
     F ppp = S::mul(p, pp);
     F q = S::mul(a.x, pp);
     XYZZ<F> o;
-    o.x = S::mul(r, r) - ppp - q.dbl();
+    o.x = S::sqr(r) - ppp - q.dbl();
     o.y = S::mul(r, q - o.x) - S::mul(a.y, ppp);
     o.zz = S::mul(a.zz, pp);
     o.zzz = S::mul(a.zzz, ppp);
@@ -324,13 +326,13 @@ B200_DEV Affine<F> aff_add_with_inverse(const Affine<F> &a, const Affine<F> &b, 
     F dx = b.x - a.x, num;
     if (dx.is_zero()) {
         if ((a.y + b.y).is_zero()) return {F::zero(), F::zero()};
-        F xx = Shared<F>::mul(a.x, a.x);
+        F xx = Shared<F>::sqr(a.x);
         num = xx.dbl() + xx;                         // tangent: 3 x^2 / (2 y)
     } else {
         num = b.y - a.y;
     }
     F lam = Shared<F>::mul(num, inv);
-    F x3 = Shared<F>::mul(lam, lam) - a.x - b.x;
+    F x3 = Shared<F>::sqr(lam) - a.x - b.x;
     return {x3, Shared<F>::mul(lam, a.x - x3) - a.y};
 }
 
@@ -792,7 +794,7 @@ __global__ void __launch_bounds__(64) k_field_op(int op, const typename F::Mem *
     case FOP_ADD: r = x + y; break;
     case FOP_SUB: r = x - y; break;
     case FOP_MUL: r = x * y; break;
-    case FOP_SQR: r = x.sqr(); break;
+    case FOP_SQR: r = Shared<F>::sqr(x); break;      // the dedicated squaring where the field has one
     case FOP_INV: r = FieldInv<F>::inv(x); break;
     case FOP_NEG: r = x.neg(); break;
     default: r = x.dbl(); break;
