@@ -51,7 +51,8 @@ static MsmPlan make_plan(size_t n) {
     }
     best.segs = best.nb / best.seg_len;
     // block-summed buckets: a few times the mean population of a bucket (uniform digits)
-    best.big = (uint32_t)std::min<size_t>(SIZE_BINS - 1, std::max<size_t>(64, 4 * (n / best.nb) + 32));
+    // (8x: the top window of a 253-bit scalar at c = 15 holds 13 bits, its buckets are 4x the mean by design)
+    best.big = (uint32_t)std::min<size_t>(SIZE_BINS - 1, std::max<size_t>(64, 8 * (n / best.nb) + 64));
     return best;
 }
 
