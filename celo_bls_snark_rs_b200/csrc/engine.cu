@@ -331,6 +331,51 @@ int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2,
     return B200_OK;
 }
 
+int b200_multi_pairing_bw6_761(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
+                               void *out_fq6, int *out_is_one) {
+    if (n && (!g1 || !g2)) return fail(B200_ERR_ARG, "null pointer");
+    if (!out_fq6 && !out_is_one) return fail(B200_ERR_ARG, "no output requested");
+    REQUIRE_ENGINE();
+    return bw6_multi_pairing_host(E, g1, stride1, g2, stride2, n, out_fq6, out_is_one);
+}
+
+int b200_miller_values_bw6_761_device(const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out_vals,
+                                      void *stream) {
+    if (n && (!d_g1_packed || !d_g2_packed || !d_out_vals)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    int rc = bw6_miller_values(E, d_g1_packed, d_g2_packed, n, d_out_vals, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(E.done, st));
+    E.has_pending = true;
+    return B200_OK;
+}
+
+int b200_final_exp_bw6_761_device(const void *d_vals, size_t count, void *d_out_fq6, int *d_is_one, void *stream) {
+    if (!d_vals || count == 0) return fail(B200_ERR_ARG, "null pointer / empty input");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    int rc = bw6_final_exp(E, d_vals, count, d_out_fq6, d_is_one, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(E.done, st));
+    E.has_pending = true;
+    return B200_OK;
+}
+
+int b200_groth16_verify_bw6_761(const b200_groth16_vk *vk, const void *proof_a, const void *proof_b, const void *proof_c,
+                                const uint64_t *public_inputs, size_t num_inputs, int *out_verified) {
+    if (!vk || !proof_a || !proof_b || !proof_c || !out_verified || !vk->alpha_g1 || !vk->beta_g2 || !vk->gamma_g2 ||
+        !vk->delta_g2 || !vk->gamma_abc_g1 || (num_inputs && !public_inputs))
+        return fail(B200_ERR_ARG, "null pointer");
+    if (num_inputs + 1 != vk->num_gamma_abc)
+        return fail(B200_ERR_ARG, "malformed verifying key: %zu public inputs against %zu gamma_abc entries", num_inputs,
+                    vk->num_gamma_abc);
+    REQUIRE_ENGINE();
+    return bw6_groth16_verify(E, vk, proof_a, proof_b, proof_c, public_inputs, num_inputs, out_verified);
+}
+
 int b200_batch_verify_hashes(const void *signature, const void *pubkeys, const void *message_hashes, size_t n,
                              int *out_verified) {
     if (!signature || !out_verified || (n && (!pubkeys || !message_hashes))) return fail(B200_ERR_ARG, "null pointer");

@@ -121,6 +121,13 @@ int witness_map(Engine &E, int field, void *a, void *b, void *c, int log_n, void
 // Groth16 prover arithmetic (inst_groth16.cu)
 int groth16_prove(Engine &E, int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
                   size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_proof, cudaStream_t st);
+// BW6-761 pairing / Groth16 verification (inst_bw6_pairing.cu)
+int bw6_miller_values(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_vals, cudaStream_t st);
+int bw6_final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_is_one, cudaStream_t st);
+int bw6_multi_pairing_host(Engine &E, const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n, void *out_fq6,
+                           int *out_is_one);
+int bw6_groth16_verify(Engine &E, const b200_groth16_vk *vk, const void *proof_a, const void *proof_b, const void *proof_c,
+                       const uint64_t *inputs, size_t num_inputs, int *out_verified);
 // batch-verification flows (inst_verify.cu)
 int batch_verify_hashes(Engine &E, const void *signature, const void *pubkeys, const void *hashes, size_t n, int *out_verified);
 int batch_verify_strict_hash(Engine &E, const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,

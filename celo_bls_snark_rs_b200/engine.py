@@ -33,12 +33,20 @@ EXPORTS = [
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
     "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
     "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_msm_batch_device",
+    "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
+    "b200_groth16_verify_bw6_761",
 ]
 
 
 class Groth16Pk(ctypes.Structure):
     """b200_groth16_pk: device pointers to the packed proving-key queries."""
     _fields_ = [(k, ctypes.c_void_p) for k in ("a_query", "b_g2_query", "h_query", "l_query", "alpha_g1", "beta_g2")]
+
+
+class Groth16Vk(ctypes.Structure):
+    """b200_groth16_vk: host pointers to the arkworks VerifyingKey<BW6_761> members."""
+    _fields_ = [(k, ctypes.c_void_p) for k in ("alpha_g1", "beta_g2", "gamma_g2", "delta_g2", "gamma_abc_g1")] + [
+        ("num_gamma_abc", ctypes.c_size_t), ("stride", ctypes.c_size_t)]
 
 
 class MsmJob(ctypes.Structure):
@@ -78,6 +86,10 @@ def load() -> ctypes.CDLL:
     lib.b200_multi_pairing_bls12_377.argtypes = [vp, sz, vp, sz, sz, vp, ctypes.POINTER(i32)]
     lib.b200_miller_product_bls12_377_device.argtypes = [vp, vp, sz, vp, vp]
     lib.b200_final_exp_bls12_377_device.argtypes = [vp, sz, vp, vp, vp]
+    lib.b200_multi_pairing_bw6_761.argtypes = [vp, sz, vp, sz, sz, vp, ctypes.POINTER(i32)]
+    lib.b200_miller_values_bw6_761_device.argtypes = [vp, vp, sz, vp, vp]
+    lib.b200_final_exp_bw6_761_device.argtypes = [vp, sz, vp, vp, vp]
+    lib.b200_groth16_verify_bw6_761.argtypes = [ctypes.POINTER(Groth16Vk), vp, vp, vp, vp, sz, ctypes.POINTER(i32)]
     lib.b200_batch_verify_hashes.argtypes = [vp, vp, vp, sz, ctypes.POINTER(i32)]
     lib.b200_batch_verify_strict_hash.argtypes = [vp, vp, vp, sz, vp, ctypes.POINTER(i32)]
     lib.b200_ntt_device.argtypes = [i32, vp, ctypes.c_uint, i32, i32, vp]
@@ -201,6 +213,48 @@ def miller_product_device(d_g1: int, d_g2: int, n: int, d_out: int, stream: int 
 
 def final_exp_device(d_vals: int, count: int, d_out: int, d_is_one: int = 0, stream: int = 0):
     _check(load().b200_final_exp_bls12_377_device(d_vals, count, d_out or None, d_is_one or None, stream or None))
+
+
+FQ6_BW6_BYTES = 576
+
+
+def multi_pairing_bw6(g1: np.ndarray, g2: np.ndarray, n: Optional[int] = None, want_gt: bool = True):
+    """Host-pointer product of pairings over BW6-761 (b200_multi_pairing_bw6_761).
+    g1, g2: uint8 [n, 200 | 192].  Returns (is_one, fq6_bytes | None)."""
+    g1 = np.ascontiguousarray(g1)
+    g2 = np.ascontiguousarray(g2)
+    if n is None:
+        n = min(len(g1), len(g2))
+    s1 = g1.strides[0] if n else 200
+    s2 = g2.strides[0] if n else 200
+    out = np.zeros(FQ6_BW6_BYTES, dtype=np.uint8)
+    flag = ctypes.c_int(0)
+    _check(load().b200_multi_pairing_bw6_761(_hptr(g1), s1, _hptr(g2), s2, n, _hptr(out) if want_gt else None,
+                                             ctypes.byref(flag)))
+    return bool(flag.value), (out.tobytes() if want_gt else None)
+
+
+def miller_values_bw6_device(d_g1: int, d_g2: int, n: int, d_out: int, stream: int = 0):
+    _check(load().b200_miller_values_bw6_761_device(d_g1 or None, d_g2 or None, n, d_out or None, stream or None))
+
+
+def final_exp_bw6_device(d_vals: int, count: int, d_out: int, d_is_one: int = 0, stream: int = 0):
+    _check(load().b200_final_exp_bw6_761_device(d_vals, count, d_out or None, d_is_one or None, stream or None))
+
+
+def groth16_verify_bw6(alpha_g1: np.ndarray, beta_g2: np.ndarray, gamma_g2: np.ndarray, delta_g2: np.ndarray,
+                       gamma_abc_g1: np.ndarray, proof_a: np.ndarray, proof_b: np.ndarray, proof_c: np.ndarray,
+                       public_inputs: np.ndarray) -> bool:
+    """ark-groth16 verify_proof over BW6-761 (b200_groth16_verify_bw6_761).  Points are uint8 records of one
+    common stride (200 arkworks / 192 packed), gamma_abc_g1 is [k, stride]; public_inputs uint64 [k - 1, 6]."""
+    arrs = [np.ascontiguousarray(a) for a in (alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1, proof_a, proof_b, proof_c)]
+    abc = arrs[4].reshape(-1, arrs[4].shape[-1])
+    inputs = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 6)
+    vk = Groth16Vk(_hptr(arrs[0]), _hptr(arrs[1]), _hptr(arrs[2]), _hptr(arrs[3]), _hptr(abc), len(abc), abc.shape[-1])
+    flag = ctypes.c_int(0)
+    _check(load().b200_groth16_verify_bw6_761(ctypes.byref(vk), _hptr(arrs[5]), _hptr(arrs[6]), _hptr(arrs[7]),
+                                              _hptr(inputs) if len(inputs) else None, len(inputs), ctypes.byref(flag)))
+    return bool(flag.value)
 
 
 FR_BLS12_377, FR_BW6_761 = 0, 1

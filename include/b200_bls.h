@@ -196,6 +196,44 @@ int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void 
                               size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_proof,
                               void *stream);
 
+/* ---- BW6-761 product of pairings and Groth16 verification -------------------------------------------
+ * Replaces BW6_761::product_of_pairings as reached from ark-groth16 0.1.0 verify_proof at
+ * crates/epoch-snark/src/api/verifier.rs:35 (C-ABI caller: `verify`, crates/bls-snark-sys/src/snark/mod.rs:23-45).
+ * G1 (y^2 = x^3 - 1) and G2 (y^2 = x^3 + 4) are both over Fq761: records are x | y [| flag] at `stride`
+ * bytes (200 arkworks GroupAffine / 192 packed), Montgomery residues, 12 x u64 per coordinate.
+ * The pairing is the optimal ate pairing e(P, Q) = (f_{u+1,Q}(P) f_{u^3-u^2-u,Q}(P)^q)^((q^6-1)/r).
+ * out_fq6 (may be NULL) receives the value as arkworks' Fq6 image (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1,
+ * c1.c2; 576 bytes) for the plain exponent (q^6 - 1) / r -- upstream's addition-chain hard part raises to
+ * a fixed multiple of it, which changes the representative of GT but not any comparison with one, the only
+ * thing verify_proof observes.  out_is_one (may be NULL): 1 iff the product of pairings is one. */
+int b200_multi_pairing_bw6_761(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
+                               void *out_fq6, int *out_is_one);
+/* Device-pointer halves (packed 192-byte records): d_out_vals receives 2 n Fq6 images (power-basis
+ * coefficient order, an engine-internal layout), whose product is the Miller value of the n pairs; the
+ * final exponentiation multiplies `count` such images first (pairs may be split across streams or GPUs). */
+int b200_miller_values_bw6_761_device(const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out_vals,
+                                      void *stream);
+int b200_final_exp_bw6_761_device(const void *d_vals, size_t count, void *d_out_fq6, int *d_is_one, void *stream);
+
+/* ark-groth16 verify_proof over BW6-761 (host pointers, arkworks memory images):
+ *   g_ic = gamma_abc_g1[0] + sum_i public_inputs[i] * gamma_abc_g1[i + 1]
+ *   e(A, B) * e(g_ic, -gamma_g2) * e(C, -delta_g2) == e(alpha_g1, beta_g2)
+ * The struct mirrors VerifyingKey<BW6_761>: single points are one record each, gamma_abc_g1 is
+ * num_gamma_abc records at `stride` bytes.  public_inputs: canonical scalars, 6 x u64 each (what
+ * into_repr() yields); num_inputs + 1 != num_gamma_abc is upstream's MalformedVerifyingKey error and
+ * returns B200_ERR_ARG.  *out_verified = 1 iff verify_proof would return Ok(true). */
+typedef struct {
+    const void *alpha_g1;
+    const void *beta_g2;
+    const void *gamma_g2;
+    const void *delta_g2;
+    const void *gamma_abc_g1;
+    size_t num_gamma_abc;
+    size_t stride;
+} b200_groth16_vk;
+int b200_groth16_verify_bw6_761(const b200_groth16_vk *vk, const void *proof_a, const void *proof_b, const void *proof_c,
+                                const uint64_t *public_inputs, size_t num_inputs, int *out_verified);
+
 /* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
  * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),
  * 6 double(a).  Exists so the field layer can be checked against the oracle directly. */
