@@ -376,6 +376,67 @@ int b200_groth16_verify_bw6_761(const b200_groth16_vk *vk, const void *proof_a, 
     return bw6_groth16_verify(E, vk, proof_a, proof_b, proof_c, public_inputs, num_inputs, out_verified);
 }
 
+int b200_deserialize_points(int kind, const void *bytes, size_t n, int check_subgroup, void *out_packed, int *out_status) {
+    if (n && (!bytes || (!out_packed && !out_status))) return fail(B200_ERR_ARG, "null pointer");
+    if (kind < 0 || kind > 2) return fail(B200_ERR_ARG, "unknown point kind %d", kind);
+    REQUIRE_ENGINE();
+    return decode_points_host(E, kind, bytes, n, check_subgroup, out_packed, out_status);
+}
+
+void b200_blake2s_personal(const uint8_t *data, size_t len, const uint8_t *personal8, uint8_t *out32) {
+    blake2s_personal(data, len, personal8, out32);
+}
+
+int b200_verify_epochs(const uint8_t *vk, size_t vk_len, const uint8_t *proof, size_t proof_len, const void *first_epoch,
+                       const void *last_epoch, int *out_ok) {
+    if (!out_ok || !first_epoch || !last_epoch) return fail(B200_ERR_ARG, "null pointer");
+    *out_ok = 0;
+    if (!g_engine) {                                  // the reference's init() is optional: bind on first use
+        int rc = b200_init(-1);
+        if (rc) return rc;
+    }
+    REQUIRE_ENGINE();
+    std::string why;
+    int rc = epoch_verify(E, vk, vk_len, proof, proof_len, *reinterpret_cast<const EpochBlockFFI *>(first_epoch),
+                          *reinterpret_cast<const EpochBlockFFI *>(last_epoch), out_ok, &why);
+    if (rc == B200_OK && !*out_ok) fail(B200_OK, "verify: %s", why.c_str());      // keep the reason readable
+    return rc;
+}
+
+int b200_epoch_public_inputs(const void *first_epoch, const void *last_epoch, uint64_t *out_inputs, size_t capacity,
+                             size_t *out_count, int *out_ok) {
+    if (!out_ok || !out_count || !first_epoch || !last_epoch) return fail(B200_ERR_ARG, "null pointer");
+    *out_ok = 0;
+    *out_count = 0;
+    if (!g_engine) {
+        int rc = b200_init(-1);
+        if (rc) return rc;
+    }
+    REQUIRE_ENGINE();
+    std::string why;
+    std::vector<uint64_t> inputs;
+    int rc = epoch_public_inputs(E, *reinterpret_cast<const EpochBlockFFI *>(first_epoch),
+                                 *reinterpret_cast<const EpochBlockFFI *>(last_epoch), &inputs, out_ok, &why);
+    if (rc) return rc;
+    if (!*out_ok) {
+        fail(B200_OK, "epoch blocks: %s", why.c_str());
+        return B200_OK;
+    }
+    *out_count = inputs.size() / 6;
+    if (*out_count > capacity || (inputs.size() && !out_inputs)) return fail(B200_ERR_ARG, "output holds %zu scalars, %zu needed", capacity, *out_count);
+    memcpy(out_inputs, inputs.data(), inputs.size() * sizeof(uint64_t));
+    return B200_OK;
+}
+
+// bls-snark-sys' own entry point (crates/bls-snark-sys/src/snark/mod.rs:23-45): bool, errors logged and mapped to false
+bool verify(const uint8_t *vk, uint32_t vk_len, const uint8_t *proof, uint32_t proof_len, EpochBlockFFI first_epoch,
+            EpochBlockFFI last_epoch) {
+    int ok = 0;
+    int rc = b200_verify_epochs(vk, vk_len, proof, proof_len, &first_epoch, &last_epoch, &ok);
+    if (rc != B200_OK || !ok) fprintf(stderr, "[b200] verify -> false: %s\n", b200_last_error());
+    return rc == B200_OK && ok;
+}
+
 int b200_batch_verify_hashes(const void *signature, const void *pubkeys, const void *message_hashes, size_t n,
                              int *out_verified) {
     if (!signature || !out_verified || (n && (!pubkeys || !message_hashes))) return fail(B200_ERR_ARG, "null pointer");

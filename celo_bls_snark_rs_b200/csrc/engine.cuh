@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/b200_bls.h"
+#include "../../include/bls_snark_sys_compat.h"
 #include "msm.cuh"
 
 namespace b200 {
@@ -128,6 +129,14 @@ int bw6_multi_pairing_host(Engine &E, const void *g1, size_t stride1, const void
                            int *out_is_one);
 int bw6_groth16_verify(Engine &E, const b200_groth16_vk *vk, const void *proof_a, const void *proof_b, const void *proof_c,
                        const uint64_t *inputs, size_t num_inputs, int *out_verified);
+int bw6_groth16_verify_core(Engine &E, char *d_packed, size_t nabc, const void *d_scalars, int *out_verified);
+// point decoding and the bls-snark-sys `verify` entry point (inst_epoch_verify.cu)
+int decode_points_host(Engine &E, int kind, const void *bytes, size_t n, int subgroup, void *out_packed, int *out_status);
+int epoch_verify(Engine &E, const uint8_t *vk, size_t vk_len, const uint8_t *proof, size_t proof_len, const EpochBlockFFI &first,
+                 const EpochBlockFFI &last, int *out_ok, std::string *why);
+int epoch_public_inputs(Engine &E, const EpochBlockFFI &first, const EpochBlockFFI &last, std::vector<uint64_t> *inputs, int *ok,
+                        std::string *why);
+void blake2s_personal(const uint8_t *data, size_t len, const uint8_t personal[8], uint8_t out[32]);
 // batch-verification flows (inst_verify.cu)
 int batch_verify_hashes(Engine &E, const void *signature, const void *pubkeys, const void *hashes, size_t n, int *out_verified);
 int batch_verify_strict_hash(Engine &E, const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,

@@ -86,6 +86,7 @@ template <class P>
 struct Fp {
     static constexpr int N = P::N;
     static constexpr int NW = P::N;
+    using Params = P;
     using Mem = FpMem<NW>;
     uint32_t l[N];
 

@@ -73,6 +73,30 @@ int bw6_multi_pairing_host(Engine &E, const void *g1, size_t stride1, const void
     return B200_OK;
 }
 
+// The device part of verify_proof.  d_packed: packed affine records [A, (slot for g_ic), C, alpha] [B, gamma, delta, beta]
+// [gamma_abc_0 .. gamma_abc_{nabc-1}]; d_scalars: nabc canonical scalars [1, input_0, ...].  alpha, gamma and delta are
+// negated in place.
+int bw6_groth16_verify_core(Engine &E, char *d_packed, size_t nabc, const void *d_scalars, int *out_verified) {
+    cudaStream_t st = E.stream;
+    int rc;
+    if ((rc = E.result.reserve(FQ6_BYTES + 16 + 3 * sizeof(BImg))) || (rc = E.miller.reserve(8 * FQ6_BYTES))) return rc;
+    char *res = E.result.as<char>();
+    char *gic_jac = res + FQ6_BYTES + 16;                        // 288 B Jacobian image
+    if ((rc = msm_native<G_761>(E, d_packed + 8 * AFF, d_scalars, nabc, gic_jac, st))) return rc;
+    if ((rc = batch_to_affine<G_761>(gic_jac, 1, d_packed + 1 * AFF, st))) return rc;
+    // negate alpha (record 3), gamma (5), delta (6)
+    k_bw6_negate_y<<<1, 32, 0, st>>>(reinterpret_cast<AffineMem<BFq> *>(d_packed), 8, (1u << 3) | (1u << 5) | (1u << 6));
+    LAUNCH_CHECK();
+    char *vals = E.miller.as<char>();
+    if ((rc = bw6_miller_values(E, d_packed, d_packed + 4 * AFF, 4, vals, st))) return rc;
+    if ((rc = bw6_final_exp(E, vals, 8, nullptr, reinterpret_cast<int *>(res + FQ6_BYTES), st))) return rc;
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, res + FQ6_BYTES, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *out_verified = flag;
+    return B200_OK;
+}
+
 // ark-groth16 verify_proof over BW6-761, all arithmetic on the device:
 //   g_ic = gamma_abc[0] + sum_i input_i gamma_abc[i + 1]            (MSM with a leading unit scalar)
 //   e(A, B) e(g_ic, -gamma) e(C, -delta) e(-alpha, beta) == 1
@@ -85,8 +109,7 @@ int bw6_groth16_verify(Engine &E, const b200_groth16_vk *vk, const void *proof_a
     // staging: 4 G1 records [A, g_ic, C, alpha], 4 G2 records [B, gamma, delta, beta], then gamma_abc
     const size_t raw_bytes = (8 + nabc) * stride, packed_bytes = (8 + nabc) * AFF;
     if ((rc = E.h2d_bases.reserve(raw_bytes)) || (rc = E.native_bases.reserve(packed_bytes)) ||
-        (rc = E.scalars.reserve(nabc * 48)) || (rc = E.result.reserve(FQ6_BYTES + 16 + 3 * sizeof(BImg))) ||
-        (rc = E.miller.reserve(8 * FQ6_BYTES)))
+        (rc = E.scalars.reserve(nabc * 48)))
         return rc;
     std::vector<unsigned char> host(raw_bytes, 0);
     const void *g1s[4] = {proof_a, nullptr, proof_c, vk->alpha_g1};
@@ -106,21 +129,7 @@ int bw6_groth16_verify(Engine &E, const b200_groth16_vk *vk, const void *proof_a
     // the host vectors must outlive the copies: pageable memory is staged synchronously by the runtime, but
     // do not rely on it
     CUDA_TRY(cudaStreamSynchronize(st));
-    char *res = E.result.as<char>();
-    char *gic_jac = res + FQ6_BYTES + 16;                        // 288 B Jacobian image
-    if ((rc = msm_native<G_761>(E, packed + 8 * AFF, E.scalars.p, nabc, gic_jac, st))) return rc;
-    if ((rc = batch_to_affine<G_761>(gic_jac, 1, packed + 1 * AFF, st))) return rc;
-    // negate alpha (record 3), gamma (5), delta (6)
-    k_bw6_negate_y<<<1, 32, 0, st>>>(reinterpret_cast<AffineMem<BFq> *>(packed), 8, (1u << 3) | (1u << 5) | (1u << 6));
-    LAUNCH_CHECK();
-    char *vals = E.miller.as<char>();
-    if ((rc = bw6_miller_values(E, packed, packed + 4 * AFF, 4, vals, st))) return rc;
-    if ((rc = bw6_final_exp(E, vals, 8, nullptr, reinterpret_cast<int *>(res + FQ6_BYTES), st))) return rc;
-    int flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, res + FQ6_BYTES, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    *out_verified = flag;
-    return B200_OK;
+    return bw6_groth16_verify_core(E, packed, nabc, E.scalars.p, out_verified);
 }
 
 }  // namespace b200

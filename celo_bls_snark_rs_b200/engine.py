@@ -34,8 +34,11 @@ EXPORTS = [
     "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
     "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_msm_batch_device",
     "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
-    "b200_groth16_verify_bw6_761",
+    "b200_groth16_verify_bw6_761", "b200_deserialize_points", "b200_verify_epochs", "b200_epoch_public_inputs",
+    "b200_blake2s_personal",
 ]
+# the reference's own symbols re-exported by the library (include/bls_snark_sys_compat.h)
+COMPAT_EXPORTS = ["verify"]
 
 
 class Groth16Pk(ctypes.Structure):
@@ -47,6 +50,13 @@ class Groth16Vk(ctypes.Structure):
     """b200_groth16_vk: host pointers to the arkworks VerifyingKey<BW6_761> members."""
     _fields_ = [(k, ctypes.c_void_p) for k in ("alpha_g1", "beta_g2", "gamma_g2", "delta_g2", "gamma_abc_g1")] + [
         ("num_gamma_abc", ctypes.c_size_t), ("stride", ctypes.c_size_t)]
+
+
+class EpochBlockFFI(ctypes.Structure):
+    """bls-snark-sys EpochBlockFFI (crates/bls-snark-sys/src/snark/epoch_block.rs:109-127), #[repr(C)], 56 bytes."""
+    _fields_ = [("index", ctypes.c_uint16), ("round", ctypes.c_uint8), ("epoch_entropy", ctypes.c_void_p),
+                ("parent_entropy", ctypes.c_void_p), ("pubkeys", ctypes.c_void_p), ("pubkeys_num", ctypes.c_size_t),
+                ("maximum_non_signers", ctypes.c_uint32), ("maximum_validators", ctypes.c_size_t)]
 
 
 class MsmJob(ctypes.Structure):
@@ -90,6 +100,15 @@ def load() -> ctypes.CDLL:
     lib.b200_miller_values_bw6_761_device.argtypes = [vp, vp, sz, vp, vp]
     lib.b200_final_exp_bw6_761_device.argtypes = [vp, sz, vp, vp, vp]
     lib.b200_groth16_verify_bw6_761.argtypes = [ctypes.POINTER(Groth16Vk), vp, vp, vp, vp, sz, ctypes.POINTER(i32)]
+    lib.b200_deserialize_points.argtypes = [i32, vp, sz, i32, vp, vp]
+    lib.b200_verify_epochs.argtypes = [vp, sz, vp, sz, ctypes.POINTER(EpochBlockFFI), ctypes.POINTER(EpochBlockFFI),
+                                       ctypes.POINTER(i32)]
+    lib.b200_epoch_public_inputs.argtypes = [ctypes.POINTER(EpochBlockFFI), ctypes.POINTER(EpochBlockFFI), vp, sz,
+                                             ctypes.POINTER(sz), ctypes.POINTER(i32)]
+    lib.b200_blake2s_personal.argtypes = [vp, sz, vp, vp]
+    lib.b200_blake2s_personal.restype = None
+    lib.verify.argtypes = [vp, ctypes.c_uint32, vp, ctypes.c_uint32, EpochBlockFFI, EpochBlockFFI]
+    lib.verify.restype = ctypes.c_bool
     lib.b200_batch_verify_hashes.argtypes = [vp, vp, vp, sz, ctypes.POINTER(i32)]
     lib.b200_batch_verify_strict_hash.argtypes = [vp, vp, vp, sz, vp, ctypes.POINTER(i32)]
     lib.b200_ntt_device.argtypes = [i32, vp, ctypes.c_uint, i32, i32, vp]
@@ -255,6 +274,73 @@ def groth16_verify_bw6(alpha_g1: np.ndarray, beta_g2: np.ndarray, gamma_g2: np.n
     _check(load().b200_groth16_verify_bw6_761(ctypes.byref(vk), _hptr(arrs[5]), _hptr(arrs[6]), _hptr(arrs[7]),
                                               _hptr(inputs) if len(inputs) else None, len(inputs), ctypes.byref(flag)))
     return bool(flag.value)
+
+
+POINTS_BLS12_377_G2, POINTS_BW6_761_G1, POINTS_BW6_761_G2 = 0, 1, 2
+DECODE_OK, DECODE_INFINITY, DECODE_BAD_COORD, DECODE_NOT_ON_CURVE, DECODE_NOT_IN_SUBGROUP = 0, 1, 2, 3, 4
+
+
+def deserialize_points(kind: int, data: bytes, check_subgroup: bool = True):
+    """Compressed arkworks points (96 bytes each) -> (packed affine records uint8 [n, 192], status int32 [n])
+    (b200_deserialize_points; ark-serialize GroupAffine::deserialize on the device)."""
+    raw = np.frombuffer(bytes(data), dtype=np.uint8)
+    assert len(raw) % 96 == 0
+    n = len(raw) // 96
+    out = np.zeros((n, 192), dtype=np.uint8)
+    status = np.zeros(n, dtype=np.int32)
+    _check(load().b200_deserialize_points(kind, _hptr(raw) if n else None, n, int(check_subgroup), _hptr(out) if n else None,
+                                          _hptr(status) if n else None))
+    return out, status
+
+
+class EpochBlock:
+    """Owner of the buffers an EpochBlockFFI points at (what a cgo caller keeps alive across the call)."""
+
+    def __init__(self, index: int, round_: int, epoch_entropy: Optional[bytes], parent_entropy: Optional[bytes],
+                 maximum_non_signers: int, maximum_validators: int, pubkeys: bytes):
+        assert len(pubkeys) % 96 == 0
+        self._keep = [np.frombuffer(bytes(b), dtype=np.uint8).copy() if b is not None else None
+                      for b in (epoch_entropy, parent_entropy, pubkeys)]
+        ptr = lambda a: _hptr(a) if a is not None and len(a) else None
+        self.ffi = EpochBlockFFI(index, round_, ptr(self._keep[0]), ptr(self._keep[1]), ptr(self._keep[2]),
+                                 len(pubkeys) // 96, maximum_non_signers, maximum_validators)
+
+
+def verify_epochs(vk: bytes, proof: bytes, first: EpochBlock, last: EpochBlock) -> bool:
+    """bls-snark-sys `verify` (crates/bls-snark-sys/src/snark/mod.rs:23-45) through the library's export of that
+    very symbol: structs by value, bool result."""
+    vk_a, proof_a = np.frombuffer(bytes(vk), dtype=np.uint8), np.frombuffer(bytes(proof), dtype=np.uint8)
+    return bool(load().verify(_hptr(vk_a), len(vk_a), _hptr(proof_a), len(proof_a), first.ffi, last.ffi))
+
+
+def verify_epochs_status(vk: bytes, proof: bytes, first: EpochBlock, last: EpochBlock):
+    """b200_verify_epochs: (ok, reason) -- engine failures raise."""
+    vk_a, proof_a = np.frombuffer(bytes(vk), dtype=np.uint8), np.frombuffer(bytes(proof), dtype=np.uint8)
+    ok = ctypes.c_int(0)
+    _check(load().b200_verify_epochs(_hptr(vk_a), len(vk_a), _hptr(proof_a), len(proof_a), ctypes.byref(first.ffi),
+                                     ctypes.byref(last.ffi), ctypes.byref(ok)))
+    return bool(ok.value), load().b200_last_error().decode()
+
+
+def epoch_public_inputs(first: EpochBlock, last: EpochBlock):
+    """b200_epoch_public_inputs: list of canonical scalars (ints), or None when a block does not decode."""
+    out = np.zeros((8, 6), dtype=np.uint64)
+    count, ok = ctypes.c_size_t(0), ctypes.c_int(0)
+    _check(load().b200_epoch_public_inputs(ctypes.byref(first.ffi), ctypes.byref(last.ffi), _hptr(out), 8, ctypes.byref(count),
+                                           ctypes.byref(ok)))
+    if not ok.value:
+        return None
+    return [sum(int(v) << (64 * j) for j, v in enumerate(row)) for row in out[:count.value]]
+
+
+def blake2s_personal(data: bytes, personal: bytes) -> bytes:
+    """Host helper of the verifier (no GPU needed): Blake2s-256 with an 8-byte personalisation."""
+    assert len(personal) == 8
+    d = np.frombuffer(bytes(data), dtype=np.uint8)
+    p = np.frombuffer(bytes(personal), dtype=np.uint8)
+    out = np.zeros(32, dtype=np.uint8)
+    load().b200_blake2s_personal(_hptr(d) if len(d) else None, len(d), _hptr(p), _hptr(out))
+    return out.tobytes()
 
 
 FR_BLS12_377, FR_BW6_761 = 0, 1

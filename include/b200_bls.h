@@ -234,6 +234,33 @@ typedef struct {
 int b200_groth16_verify_bw6_761(const b200_groth16_vk *vk, const void *proof_a, const void *proof_b, const void *proof_c,
                                 const uint64_t *public_inputs, size_t num_inputs, int *out_verified);
 
+/* ---- point decoding: replaces ark-serialize 0.1.0 GroupAffine::deserialize (compressed form) ------------
+ *   crates/bls-snark-sys/src/snark/epoch_block.rs:154-196 (read_slice::<VerifyingKey / Proof>, read_pubkeys)
+ * kind: 0 = BLS12-377 G2 (96 B: x.c0 | x.c1), 1 = BW6-761 G1, 2 = BW6-761 G2 (96 B: x); flags in the top two
+ * bits of the last byte (bit 7: y is the larger root, bit 6: infinity).  Host pointers.  out_packed (may be
+ * NULL): n packed affine records (192 B, Montgomery, (0, 0) for infinity or a rejected point); out_status: n
+ * ints, 0 ok, 1 infinity, 2 coordinate >= modulus, 3 x not on the curve, 4 not in the prime-order subgroup
+ * (only tested when check_subgroup != 0, as deserialize does; deserialize_unchecked does not). */
+enum { B200_POINTS_BLS12_377_G2 = 0, B200_POINTS_BW6_761_G1 = 1, B200_POINTS_BW6_761_G2 = 2 };
+int b200_deserialize_points(int kind, const void *bytes, size_t n, int check_subgroup, void *out_packed, int *out_status);
+
+/* The reference's SNARK verifier entry point with a status code: same arguments as `verify`
+ * (include/bls_snark_sys_compat.h, which this library also exports under that name), blocks passed by
+ * pointer (const EpochBlockFFI *).  *out_ok = 1 iff the reference returns true; the return value is non-zero
+ * only for engine failures (no CUDA device, runtime error) -- malformed inputs are *out_ok = 0. */
+int b200_verify_epochs(const uint8_t *vk, size_t vk_len, const uint8_t *proof, size_t proof_len, const void *first_epoch,
+                       const void *last_epoch, int *out_ok);
+
+/* The public inputs epoch_snark::verify derives from the two blocks (verifier.rs:30-33): pack(hash(first) |
+ * hash(last with aggregated key)), canonical scalars of 6 x u64; two of them for the Blake2s edge hashes.
+ * Keys are decoded, checked and aggregated on the device; *out_ok = 0 when a block does not decode. */
+int b200_epoch_public_inputs(const void *first_epoch, const void *last_epoch, uint64_t *out_inputs, size_t capacity,
+                             size_t *out_count, int *out_ok);
+
+/* Host helper of the verifier (no GPU): Blake2s, 32-byte digest, 8-byte personalisation
+ * (crates/epoch-snark/src/epoch_block.rs:226-236 hashes the encoded blocks with "ULforout"). */
+void b200_blake2s_personal(const uint8_t *data, size_t len, const uint8_t *personal8, uint8_t *out32);
+
 /* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
  * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),
  * 6 double(a).  Exists so the field layer can be checked against the oracle directly. */
