@@ -166,11 +166,13 @@ __device__ __noinline__ bool fq2_377_sqrt(CFq2 a, CFq2 *out) {
 }
 
 // ---- decoding kernels ----------------------------------------------------------------------------------
-// BW6-761 G1 (y^2 = x^3 - 1, g2 = 0) or G2 (y^2 = x^3 + 4, g2 = 1): n x 96 bytes -> packed affine + status
-__global__ void __launch_bounds__(64) k_bw6_decompress(const uint32_t *__restrict__ src, uint32_t n, int g2,
+// BW6-761: n x 96 bytes -> packed affine + status.  Records [g2_lo, g2_hi) are G2 points (y^2 = x^3 + 4), the
+// others G1 (y^2 = x^3 - 1): a verifying key and a proof mix both and are decoded by one launch.
+__global__ void __launch_bounds__(64) k_bw6_decompress(const uint32_t *__restrict__ src, uint32_t n, uint32_t g2_lo, uint32_t g2_hi,
                                                        AffineMem<Fq761> *__restrict__ out, int *__restrict__ status) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const bool g2 = i >= g2_lo && i < g2_hi;
     uint32_t w[24];
 #pragma unroll
     for (int k = 0; k < 24; k++) w[k] = src[24 * (size_t)i + k];

@@ -164,7 +164,7 @@ int decode_points(int kind, const void *d_src, size_t n, int subgroup, void *d_o
             LAUNCH_CHECK();
         }
     } else if (kind == 1 || kind == 2) {
-        k_bw6_decompress<<<blocks, 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)n, kind == 2,
+        k_bw6_decompress<<<blocks, 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)n, 0u, kind == 2 ? (uint32_t)n : 0u,
                                                 reinterpret_cast<AffineMem<Fq761> *>(d_out), d_status);
         LAUNCH_CHECK();
         if (subgroup) {
@@ -201,34 +201,43 @@ static const char *decode_reason(int st) {
                                         : "a coordinate is not below the field modulus";
 }
 
-int epoch_public_inputs(Engine &E, const EpochBlockFFI &first, const EpochBlockFFI &last, std::vector<uint64_t> *inputs, int *ok,
-                        std::string *why) {
+// asynchronous half: uploads, decodes, checks and aggregates the keys on `st`; results stay in E.g2_packed
+struct KeyWork {
+    size_t n1 = 0, n2 = 0;
+    int *d_status = nullptr;
+    uint32_t *d_agg = nullptr;
+};
+static int epoch_keys_launch(Engine &E, const EpochBlockFFI &first, const EpochBlockFFI &last, KeyWork *kw, cudaStream_t st) {
+    const size_t n1 = first.pubkeys_num, n2 = last.pubkeys_num, nkeys = n1 + n2;
+    int rc;
+    const size_t status_off = (nkeys + 1) * 192, agg_off = status_off + (nkeys + 1) * sizeof(int);
+    if ((rc = E.h2d_g2.reserve((nkeys + 1) * 96)) || (rc = E.g2_packed.reserve(agg_off + 32 * sizeof(uint32_t)))) return rc;
+    char *d_src = E.h2d_g2.as<char>(), *d_pts = E.g2_packed.as<char>();
+    kw->n1 = n1;
+    kw->n2 = n2;
+    kw->d_status = reinterpret_cast<int *>(d_pts + status_off);
+    kw->d_agg = reinterpret_cast<uint32_t *>(d_pts + agg_off);
+    if (n1) CUDA_TRY(cudaMemcpyAsync(d_src, first.pubkeys, 96 * n1, cudaMemcpyHostToDevice, st));
+    if (n2) CUDA_TRY(cudaMemcpyAsync(d_src + 96 * n1, last.pubkeys, 96 * n2, cudaMemcpyHostToDevice, st));
+    if ((rc = decode_points(0, d_src, nkeys, 1, d_pts, kw->d_status, st))) return rc;      // G2Affine::deserialize per key
+    k_g2_377_aggregate_emit<<<1, 32, 0, st>>>(reinterpret_cast<const AffineMem<CFq2> *>(d_pts + n1 * 192), kw->d_status + n1,
+                                              (uint32_t)n2, kw->d_agg);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+// host half, after the stream has been synchronised: statuses -> encodings -> hashes -> packed inputs
+static int epoch_keys_finish(const KeyWork &kw, const EpochBlockFFI &first, const EpochBlockFFI &last, std::vector<uint64_t> *inputs,
+                             int *ok, std::string *why) {
     *ok = 0;
     auto reject = [&](const char *msg) {
         if (why) *why = msg;
         return B200_OK;
     };
-    if ((first.pubkeys_num && !first.pubkeys) || (last.pubkeys_num && !last.pubkeys)) return reject("null public-key array");
-    const size_t n1 = first.pubkeys_num, n2 = last.pubkeys_num, nkeys = n1 + n2;
-    if (nkeys > (1u << 20)) return reject("too many public keys");
-    cudaStream_t st = E.stream;
-    int rc;
-    const size_t status_off = (nkeys + 1) * 192, agg_off = status_off + (nkeys + 1) * sizeof(int);
-    if ((rc = E.h2d_g2.reserve((nkeys + 1) * 96)) || (rc = E.g2_packed.reserve(agg_off + 32 * sizeof(uint32_t)))) return rc;
-    char *d_src = E.h2d_g2.as<char>(), *d_pts = E.g2_packed.as<char>();
-    int *d_status = reinterpret_cast<int *>(d_pts + status_off);
-    uint32_t *d_agg = reinterpret_cast<uint32_t *>(d_pts + agg_off);
-    if (n1) CUDA_TRY(cudaMemcpyAsync(d_src, first.pubkeys, 96 * n1, cudaMemcpyHostToDevice, st));
-    if (n2) CUDA_TRY(cudaMemcpyAsync(d_src + 96 * n1, last.pubkeys, 96 * n2, cudaMemcpyHostToDevice, st));
-    if ((rc = decode_points(0, d_src, nkeys, 1, d_pts, d_status, st))) return rc;          // G2Affine::deserialize per key
-    k_g2_377_aggregate_emit<<<1, 32, 0, st>>>(reinterpret_cast<const AffineMem<CFq2> *>(d_pts + n1 * 192), d_status + n1,
-                                              (uint32_t)n2, d_agg);
-    LAUNCH_CHECK();
+    const size_t nkeys = kw.n1 + kw.n2;
     std::vector<int> status(nkeys);
     uint32_t agg[26];
-    if (nkeys) CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, nkeys * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(agg, d_agg, sizeof(agg), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (nkeys) CUDA_TRY(cudaMemcpy(status.data(), kw.d_status, nkeys * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(agg, kw.d_agg, sizeof(agg), cudaMemcpyDeviceToHost));
     // an infinite validator key has no CIP22 encoding worth reproducing: rejected like an invalid one
     for (int s : status)
         if (s != DECODE_OK) return reject(decode_reason(s));
@@ -244,6 +253,20 @@ int epoch_public_inputs(Engine &E, const EpochBlockFFI &first, const EpochBlockF
     return B200_OK;
 }
 
+int epoch_public_inputs(Engine &E, const EpochBlockFFI &first, const EpochBlockFFI &last, std::vector<uint64_t> *inputs, int *ok,
+                        std::string *why) {
+    *ok = 0;
+    if ((first.pubkeys_num && !first.pubkeys) || (last.pubkeys_num && !last.pubkeys) || first.pubkeys_num + last.pubkeys_num > (1u << 20)) {
+        if (why) *why = "null or oversized public-key array";
+        return B200_OK;
+    }
+    KeyWork kw;
+    int rc;
+    if ((rc = epoch_keys_launch(E, first, last, &kw, E.stream))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(E.stream));
+    return epoch_keys_finish(kw, first, last, inputs, ok, why);
+}
+
 // ---- verify ----------------------------------------------------------------------------------------------
 // *out_ok = 1 iff the reference's `verify` would return true.  A non-zero return code is an engine failure
 // (no device, CUDA error); malformed inputs are *out_ok = 0 with rc = 0, as the reference turns them into `false`.
@@ -255,10 +278,8 @@ int epoch_verify(Engine &E, const uint8_t *vk, size_t vk_len, const uint8_t *pro
         return B200_OK;
     };
     int rc, ok = 0;
-    // EpochBlock::try_from x 2 comes first in the reference (snark/mod.rs:37-38), then the key and the proof
-    std::vector<uint64_t> inputs;
-    if ((rc = epoch_public_inputs(E, first, last, &inputs, &ok, why))) return rc;
-    if (!ok) return B200_OK;
+    if ((first.pubkeys_num && !first.pubkeys) || (last.pubkeys_num && !last.pubkeys) || first.pubkeys_num + last.pubkeys_num > (1u << 20))
+        return reject("null or oversized public-key array");
     // VerifyingKey<BW6_761>: alpha_g1 | beta_g2 | gamma_g2 | delta_g2 | u64 len | gamma_abc_g1[len]; Proof: A | B | C
     if (!vk || vk_len < 392) return reject("verifying key shorter than its fixed part");
     uint64_t nabc = 0;
@@ -271,20 +292,33 @@ int epoch_verify(Engine &E, const uint8_t *vk, size_t vk_len, const uint8_t *pro
     const uint8_t *order[8] = {proof, proof, proof + 192, vk, proof + 96, vk + 192, vk + 288, vk + 96};
     for (int i = 0; i < 8; i++) memcpy(host.data() + 96 * i, order[i], 96);
     memcpy(host.data() + 96 * 8, vk + 392, 96 * nabc);
-    cudaStream_t st = E.stream;
+    cudaStream_t st = E.stream, side = E.pipe_stream[1];
     const size_t status_off = nbw * 192;
     if ((rc = E.h2d_bases.reserve(host.size())) || (rc = E.native_bases.reserve(status_off + nbw * sizeof(int)))) return rc;
     char *d_src = E.h2d_bases.as<char>(), *d_pts = E.native_bases.as<char>();
     int *d_status = reinterpret_cast<int *>(d_pts + status_off);
+    // the two decodings are independent chains of single-thread field arithmetic: the validator keys (BLS12-377 G2) go to a
+    // side stream, the key and the proof (BW6-761) stay on the main one
+    CUDA_TRY(cudaEventRecord(E.ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(side, E.ev_fork, 0));
+    KeyWork kw;
+    if ((rc = epoch_keys_launch(E, first, last, &kw, side))) return rc;
+    CUDA_TRY(cudaEventRecord(E.ev_join, side));
     CUDA_TRY(cudaMemcpyAsync(d_src, host.data(), host.size(), cudaMemcpyHostToDevice, st));
-    // G1Affine / G2Affine::deserialize over BW6-761: on the curve, in the subgroup
-    if ((rc = decode_points(1, d_src, 4, 1, d_pts, d_status, st)) ||
-        (rc = decode_points(2, d_src + 4 * 96, 4, 1, d_pts + 4 * 192, d_status + 4, st)) ||
-        (rc = decode_points(1, d_src + 8 * 96, nabc, 1, d_pts + 8 * 192, d_status + 8, st)))
-        return rc;
+    // G1Affine / G2Affine::deserialize over BW6-761: on the curve, in the subgroup (one launch: records 4..7 are G2)
+    k_bw6_decompress<<<ceil_div(nbw, 64), 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)nbw, 4u, 8u,
+                                                       reinterpret_cast<AffineMem<Fq761> *>(d_pts), d_status);
+    LAUNCH_CHECK();
+    k_subgroup_check<Fq761, Fq377Params><<<ceil_div(nbw, 64), 64, 0, st>>>(reinterpret_cast<const AffineMem<Fq761> *>(d_pts), (uint32_t)nbw,
+                                                                          d_status);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaStreamWaitEvent(st, E.ev_join, 0));
     std::vector<int> status(nbw);
     CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, nbw * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<uint64_t> inputs;
+    if ((rc = epoch_keys_finish(kw, first, last, &inputs, &ok, why))) return rc;
+    if (!ok) return B200_OK;
     // an infinite element of the key / proof is a legal encoding: it decodes and simply fails the pairing check
     for (int s : status)
         if (s != DECODE_OK && s != DECODE_INFINITY) return reject(decode_reason(s));

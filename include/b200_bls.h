@@ -203,9 +203,10 @@ int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void 
  * bytes (200 arkworks GroupAffine / 192 packed), Montgomery residues, 12 x u64 per coordinate.
  * The pairing is the optimal ate pairing e(P, Q) = (f_{u+1,Q}(P) f_{u^3-u^2-u,Q}(P)^q)^((q^6-1)/r).
  * out_fq6 (may be NULL) receives the value as arkworks' Fq6 image (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1,
- * c1.c2; 576 bytes) for the plain exponent (q^6 - 1) / r -- upstream's addition-chain hard part raises to
- * a fixed multiple of it, which changes the representative of GT but not any comparison with one, the only
- * thing verify_proof observes.  out_is_one (may be NULL): 1 iff the product of pairings is one. */
+ * c1.c2; 576 bytes) for the exponent c (q^6 - 1) / r with a fixed 191-bit c prime to r (the hard part is
+ * computed as f^R0(u) (f^q)^R1(u), csrc/pairing_bw6.cuh).  Upstream's addition chain raises to another fixed
+ * multiple; the multiple changes the representative of GT but not any comparison with one, the only thing
+ * verify_proof observes.  out_is_one (may be NULL): 1 iff the product of pairings is one. */
 int b200_multi_pairing_bw6_761(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
                                void *out_fq6, int *out_is_one);
 /* Device-pointer halves (packed 192-byte records): d_out_vals receives 2 n Fq6 images (power-basis

@@ -14,8 +14,8 @@ This file restates that pairing with the data layout of the CUDA kernels (csrc/p
   * G2 on the M-twist E': y^2 = x^3 + 4 over F_q, untwisted by (x, y) -> (x / w^2, y / w^3);
   * the running point T in Jacobian coordinates, lines scaled by elements of F_q and by w^3 (both vanish in
     the final exponentiation): a line is (c0, c2, c3), the coefficients of 1, w^2, w^3;
-  * final exponentiation = easy part (q^3 - 1)(q + 1), then the hard part (q^2 - q + 1) / r by plain
-    square-and-multiply.
+  * final exponentiation = easy part (q^3 - 1)(q + 1), then the hard part raised to HARD_MULTIPLE = c (q^2 - q + 1) / r
+    (see below; here by plain square-and-multiply, on the device as f^R0 (f^q)^R1).
 
 PINNING.  The value is pinned three ways in tests/test_oracle_bw6_ate.py: bilinearity and non-degeneracy on
 the reference's own verifying key, agreement of the Groth16 verification boolean with the independent reduced
@@ -37,6 +37,15 @@ assert (LOOP_1 + Q * LOOP_2) % R == 0
 
 HARD_EXP = (Q * Q - Q + 1) // R
 assert (Q * Q - Q + 1) % R == 0
+# The device raises to a multiple of the hard part that splits into two short polynomials of the seed:
+# R0(u) + q R1(u) = c (q^2 - q + 1) / r, c a 191-bit integer prime to r -- still a non-degenerate bilinear pairing
+# (e^c, e the pairing with the plain exponent), and f^R0 (f^q)^R1 is one joint square-and-multiply of 575 steps.
+HARD_R0 = -103 * U**7 + 70 * U**6 + 269 * U**5 - 197 * U**4 - 314 * U**3 - 73 * U**2 - 263 * U - 220
+HARD_R1 = 103 * U**9 - 276 * U**8 + 77 * U**7 + 492 * U**6 - 445 * U**5 - 65 * U**4 + 452 * U**3 - 181 * U**2 + 34 * U + 229
+HARD_MULTIPLE = HARD_R0 + Q * HARD_R1
+assert HARD_MULTIPLE % HARD_EXP == 0 and HARD_MULTIPLE > 0
+HARD_COFACTOR = HARD_MULTIPLE // HARD_EXP
+assert HARD_COFACTOR % R != 0 and HARD_COFACTOR.bit_length() == 191
 
 GAMMA = pow(-4 % Q, (Q - 1) // 6, Q)      # w^q = GAMMA * w
 assert pow(GAMMA, 3, Q) == Q - 1           # -4 is a non-residue: w^(q^3) = -w
@@ -181,7 +190,7 @@ def miller_loop(p: Optional[Tuple[int, int]], q2: Optional[Tuple[int, int]]):
 def final_exponentiation(f):
     r = f6_mul(f6_conj(f), f6_inv(f))          # f^(q^3 - 1)
     r = f6_mul(f6_frob(r, 1), r)               # ^(q + 1)
-    return f6_pow(r, HARD_EXP)
+    return f6_pow(r, HARD_MULTIPLE)
 
 
 def product_of_pairings(pairs):
