@@ -48,6 +48,28 @@ vec = {
     "epoch_block_encoding_with_entropy": {"cite": "crates/epoch-snark/src/epoch_block.rs:243",
                                           "hex": const_str(epoch, "EXPECTED_ENCODING_WITH_ENTROPY")},
 }
+
+
+def test_fn_hex(path, fn_name):
+    """All hex literals (>= 4 digits) inside one #[test] function body."""
+    src = open(path).read()
+    body = src[src.index("fn " + fn_name + "("):]
+    nxt = body.find("#[test]")
+    body = body if nxt < 0 else body[:nxt]
+    return re.findall(r'"([0-9a-f]{4,})"', body)
+
+
+direct = f"{REF}/bls-crypto/src/hashers/direct.rs"
+composite = f"{REF}/bls-crypto/src/hashers/composite.rs"
+for label, path, cite in (("direct", direct, "crates/bls-crypto/src/hashers/direct.rs:87-171"),
+                          ("composite", composite, "crates/bls-crypto/src/hashers/composite.rs:104-189")):
+    fns = ["test_crh_empty", "test_crh_random", "test_xof_random_96", "test_hash_random"]
+    if label == "composite":
+        fns += ["test_xof_random_768", "test_xof_random_769"]
+    else:
+        fns += ["test_blake2s_test_vectors"]
+    vec["hasher_kats_" + label] = {"cite": cite, "hex": {fn: test_fn_hex(path, fn) for fn in fns}}
+
 for k, v in vec.items():
     if isinstance(v, dict):
         n = len(v["hex"]) if isinstance(v["hex"], list) else len(v["hex"]) // 2
