@@ -76,6 +76,33 @@ def _batch(curve: int, exponents: Sequence[int], images: Sequence[bytes]) -> Opt
     return d_out.cpu().numpy().tobytes()
 
 
+SIG_DOMAIN, POP_DOMAIN = b"ULforxof", b"ULforpop"      # crates/bls-crypto/src/lib.rs:75-78
+
+
+class HashToG1:
+    """HashToCurve<Output = G1Projective> (hash_to_curve/mod.rs:8-17) over the CUDA engine; `hash_many` is the
+    batched form the verification flows use (one launch for all messages)."""
+
+    def __init__(self, hasher: int, cip22: bool = False, compat: bool = True):
+        self.hasher, self.cip22, self.compat = hasher, cip22, compat
+
+    def hash_many(self, domain: bytes, inputs):
+        return E.hash_to_g1(self.hasher, domain, list(inputs), compat=self.compat, cip22=self.cip22)[0]
+
+    def hash(self, domain: bytes, message: bytes, extra_data: bytes = b"") -> bytes:
+        return self.hash_many(domain, [(message, extra_data)])[0]
+
+    def hash_with_attempt(self, domain: bytes, message: bytes, extra_data: bytes = b""):
+        images, attempts = E.hash_to_g1(self.hasher, domain, [(message, extra_data)], compat=self.compat, cip22=self.cip22)
+        return images[0], attempts[0]
+
+
+# try_and_increment.rs:29-38, try_and_increment_cip22.rs:24-33
+COMPOSITE_HASH_TO_G1 = HashToG1(E.HASHER_COMPOSITE)
+DIRECT_HASH_TO_G1 = HashToG1(E.HASHER_DIRECT)
+COMPOSITE_HASH_TO_G1_CIP22 = HashToG1(E.HASHER_COMPOSITE, cip22=True)
+
+
 class Signature:
     """A BLS signature on G1 (signature.rs:17): wraps a G1Projective image."""
 
@@ -91,6 +118,12 @@ class Signature:
     def batch(exponents: Sequence[int], signatures: Sequence["Signature"]) -> Optional["Signature"]:
         out = _batch(E.BLS12_377_G1, exponents, [s.image for s in signatures])
         return None if out is None else Signature(out)
+
+    def batch_verify(self, pubkeys: Sequence["PublicKey"], domain: bytes, messages, hash_to_g1: HashToG1) -> None:
+        """signature.rs:101-117: messages = [(message, extra_data)], hashed on the device in one launch."""
+        if len(pubkeys) != len(messages):
+            raise UnevenNumKeysMessages()
+        self.batch_verify_hashes(pubkeys, hash_to_g1.hash_many(domain, messages))
 
     def batch_verify_hashes(self, pubkeys: Sequence["PublicKey"], message_hashes: Sequence[bytes]) -> None:
         """Raises VerificationFailed / UnevenNumKeysMessages; returns None on success (Ok(()))."""
@@ -123,6 +156,14 @@ class PublicKey:
     def batch(exponents: Sequence[int], public_keys: Sequence["PublicKey"]) -> Optional["PublicKey"]:
         out = _batch(E.BLS12_377_G2, exponents, [p.image for p in public_keys])
         return None if out is None else PublicKey(out)
+
+    def verify(self, message: bytes, extra_data: bytes, signature: Signature, hash_to_g1: HashToG1) -> None:
+        """public.rs:70-79 (SIG_DOMAIN)."""
+        self.verify_hash(hash_to_g1.hash(SIG_DOMAIN, message, extra_data), signature)
+
+    def verify_pop(self, message: bytes, signature: Signature, hash_to_g1: HashToG1) -> None:
+        """public.rs:85-92 (POP_DOMAIN, no extra data)."""
+        self.verify_hash(hash_to_g1.hash(POP_DOMAIN, message, b""), signature)
 
     def verify_hash(self, message_hash: bytes, signature: Signature) -> None:
         """verify_sig after hashing (public.rs:94-120): e(sig, -g2) * e(H, pk) == 1."""

@@ -14,6 +14,8 @@
 #include "pairing_params_gen.cuh"
 #include "pairing_bw6_params_gen.cuh"
 
+// Non-template kernels and out-of-line functions below are `static`: this header is included by more than one
+// translation unit (inst_epoch_verify.cu, inst_hash.cu).
 namespace b200 {
 
 // local names: pairing.cuh (which defines CFq / CFq2 next to non-template kernels) is not included here
@@ -100,7 +102,7 @@ B200_DEV bool fq761_sqrt(const Fq761 &a, Fq761 &out) {
     return s.sqr() == a;
 }
 // BLS12-377 Fq: p - 1 = 2^46 t, Tonelli-Shanks with the 2^46-th root of unity (-5)^t
-__device__ __noinline__ bool fq377_sqrt(Fq377 a, Fq377 *out) {
+static __device__ __noinline__ bool fq377_sqrt(Fq377 a, Fq377 *out) {
     if (a.is_zero()) {
         *out = a;
         return true;
@@ -136,7 +138,7 @@ __device__ __noinline__ bool fq377_sqrt(Fq377 a, Fq377 *out) {
     return x.sqr() == a;
 }
 // Fq2 = Fq[u] / (u^2 + 5): norm trick (any root; the caller picks the sign)
-__device__ __noinline__ bool fq2_377_sqrt(CFq2 a, CFq2 *out) {
+static __device__ __noinline__ bool fq2_377_sqrt(CFq2 a, CFq2 *out) {
     if (a.is_zero()) {
         *out = a;
         return true;
@@ -168,7 +170,7 @@ __device__ __noinline__ bool fq2_377_sqrt(CFq2 a, CFq2 *out) {
 // ---- decoding kernels ----------------------------------------------------------------------------------
 // BW6-761: n x 96 bytes -> packed affine + status.  Records [g2_lo, g2_hi) are G2 points (y^2 = x^3 + 4), the
 // others G1 (y^2 = x^3 - 1): a verifying key and a proof mix both and are decoded by one launch.
-__global__ void __launch_bounds__(64) k_bw6_decompress(const uint32_t *__restrict__ src, uint32_t n, uint32_t g2_lo, uint32_t g2_hi,
+static __global__ void __launch_bounds__(64) k_bw6_decompress(const uint32_t *__restrict__ src, uint32_t n, uint32_t g2_lo, uint32_t g2_hi,
                                                        AffineMem<Fq761> *__restrict__ out, int *__restrict__ status) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(64) k_bw6_decompress(const uint32_t *__restric
 }
 
 // BLS12-377 G2 (Fq2 coordinates, y^2 = x^3 + (0, -1/5)): n x 96 bytes -> packed affine + status
-__global__ void __launch_bounds__(64) k_g2_377_decompress(const uint32_t *__restrict__ src, uint32_t n,
+static __global__ void __launch_bounds__(64) k_g2_377_decompress(const uint32_t *__restrict__ src, uint32_t n,
                                                           AffineMem<CFq2> *__restrict__ out, int *__restrict__ status) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(64) k_subgroup_check(const AffineMem<F> *__res
 // sum of the block's G2 keys, then what encode_public_key (encoding.rs:23-47) needs of it: canonical x.c0, x.c1 and the
 // "y over half" bit.  One warp: lanes sum strided subsets, a shuffle tree folds them, lane 0 normalises.
 // out: 24 words of canonical x (c0 | c1), word 24 = y bit, word 25 = 1 if the sum is the point at infinity.
-__global__ void __launch_bounds__(32) k_g2_377_aggregate_emit(const AffineMem<CFq2> *__restrict__ pts, const int *__restrict__ status,
+static __global__ void __launch_bounds__(32) k_g2_377_aggregate_emit(const AffineMem<CFq2> *__restrict__ pts, const int *__restrict__ status,
                                                               uint32_t n, uint32_t *__restrict__ out) {
     const int lane = threadIdx.x;
     XYZZ<CFq2> acc = XYZZ<CFq2>::inf();

@@ -105,7 +105,7 @@ void b200_shutdown(void) {
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->bh_table, &E->hash_ws})
         b->release();
     for (NttDomain &d : E->ntt)
         for (Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
@@ -450,6 +450,13 @@ int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, c
         return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     return batch_verify_strict_hash(E, pubkeys, signatures, exponents, n, message_hash, out_verified);
+}
+
+int b200_hash_to_g1(int hasher, int flags, const uint8_t *domain, size_t domain_len, const b200_hash_input *inputs, size_t n,
+                    void *out_jacobian, uint32_t *out_attempts) {
+    if ((n && (!inputs || !out_jacobian)) || (domain_len && !domain)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    return hash_to_g1(E, hasher, flags, domain, domain_len, inputs, n, out_jacobian, out_attempts);
 }
 
 int b200_ntt_device(int field, void *d_data, unsigned log_n, int inverse, int coset, void *stream) {

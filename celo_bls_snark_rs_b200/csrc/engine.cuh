@@ -90,6 +90,9 @@ struct Engine {
     Buffer g16_h, g16_tmp;
     // batch-verification composites (inst_verify.cu)
     Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff;
+    // hash-to-G1 (inst_hash.cu): affine multiples of the Bowe-Hopwood generators (built at first use), per-call staging
+    Buffer bh_table, hash_ws;
+    bool bh_ready = false;
     // optional timing of the dominant kernel (b200_profile_*): event pairs around k_bucket_accumulate
     bool profile = false;
     static constexpr int PROF_SLOTS = 256;
@@ -137,6 +140,9 @@ int epoch_verify(Engine &E, const uint8_t *vk, size_t vk_len, const uint8_t *pro
 int epoch_public_inputs(Engine &E, const EpochBlockFFI &first, const EpochBlockFFI &last, std::vector<uint64_t> *inputs, int *ok,
                         std::string *why);
 void blake2s_personal(const uint8_t *data, size_t len, const uint8_t personal[8], uint8_t out[32]);
+// batched hash-to-G1 (inst_hash.cu)
+int hash_to_g1(Engine &E, int hasher, int flags, const uint8_t *domain, size_t domain_len, const b200_hash_input *inputs, size_t n,
+               void *out, uint32_t *out_attempts);
 // batch-verification flows (inst_verify.cu)
 int batch_verify_hashes(Engine &E, const void *signature, const void *pubkeys, const void *hashes, size_t n, int *out_verified);
 int batch_verify_strict_hash(Engine &E, const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,

@@ -35,7 +35,7 @@ EXPORTS = [
     "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_msm_batch_device",
     "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
     "b200_groth16_verify_bw6_761", "b200_deserialize_points", "b200_verify_epochs", "b200_epoch_public_inputs",
-    "b200_blake2s_personal",
+    "b200_blake2s_personal", "b200_hash_to_g1",
 ]
 # the reference's own symbols re-exported by the library (include/bls_snark_sys_compat.h)
 COMPAT_EXPORTS = ["verify"]
@@ -57,6 +57,12 @@ class EpochBlockFFI(ctypes.Structure):
     _fields_ = [("index", ctypes.c_uint16), ("round", ctypes.c_uint8), ("epoch_entropy", ctypes.c_void_p),
                 ("parent_entropy", ctypes.c_void_p), ("pubkeys", ctypes.c_void_p), ("pubkeys_num", ctypes.c_size_t),
                 ("maximum_non_signers", ctypes.c_uint32), ("maximum_validators", ctypes.c_size_t)]
+
+
+class HashInput(ctypes.Structure):
+    """b200_hash_input"""
+    _fields_ = [("message", ctypes.c_char_p), ("message_len", ctypes.c_size_t), ("extra_data", ctypes.c_char_p),
+                ("extra_data_len", ctypes.c_size_t)]
 
 
 class MsmJob(ctypes.Structure):
@@ -115,6 +121,7 @@ def load() -> ctypes.CDLL:
     lib.b200_witness_map_device.argtypes = [i32, vp, vp, vp, ctypes.c_uint, vp, vp]
     lib.b200_groth16_prove_device.argtypes = [i32, ctypes.POINTER(Groth16Pk), vp, sz, sz, vp, vp, vp, ctypes.c_uint, vp, vp]
     lib.b200_msm_batch_device.argtypes = [i32, ctypes.POINTER(MsmJob), sz, vp]
+    lib.b200_hash_to_g1.argtypes = [i32, i32, ctypes.c_char_p, sz, ctypes.POINTER(HashInput), sz, vp, vp]
     lib.b200_sync.argtypes = [vp]
     lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
     lib.b200_launch_count.restype = ctypes.c_uint64
@@ -345,6 +352,32 @@ def blake2s_personal(data: bytes, personal: bytes) -> bytes:
 
 FR_BLS12_377, FR_BW6_761 = 0, 1
 FR_BYTES = {0: 32, 1: 48}
+
+
+HASHER_DIRECT, HASHER_COMPOSITE = 0, 1
+HASH_COMPAT, HASH_CIP22, HASH_CRH_ONLY = 1, 2, 4
+
+
+def hash_to_g1(hasher: int, domain: bytes, inputs, compat: bool = True, cip22: bool = False):
+    """HashToCurve::hash for every (message, extra_data) of `inputs` in one launch ->
+    (n x 144-byte G1Projective images, attempts)."""
+    n = len(inputs)
+    arr = (HashInput * max(n, 1))(*[HashInput(m, len(m), e, len(e)) for m, e in inputs])
+    out = np.zeros(n * 144, dtype=np.uint8)
+    att = np.zeros(max(n, 1), dtype=np.uint32)
+    flags = (HASH_COMPAT if compat else 0) | (HASH_CIP22 if cip22 else 0)
+    _check(load().b200_hash_to_g1(hasher, flags, domain, len(domain), arr, n, _hptr(out), _hptr(att)))
+    return [out[144 * i:144 * (i + 1)].tobytes() for i in range(n)], att[:n].tolist()
+
+
+def hash_crh(hasher: int, domain: bytes, messages):
+    """Hasher::crh of each message (composite: 48 bytes; direct: 32 bytes)."""
+    n = len(messages)
+    arr = (HashInput * max(n, 1))(*[HashInput(m, len(m), b"", 0) for m in messages])
+    out = np.zeros(max(n, 1) * 48, dtype=np.uint8)
+    _check(load().b200_hash_to_g1(hasher, HASH_CRH_ONLY, domain, len(domain), arr, n, _hptr(out), None))
+    size = 48 if hasher == HASHER_COMPOSITE else 32
+    return [out[48 * i:48 * i + size].tobytes() for i in range(n)]
 
 
 def ntt_device(field: int, d_data: int, log_n: int, inverse: bool = False, coset: bool = False, stream: int = 0):

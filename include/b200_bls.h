@@ -154,6 +154,33 @@ int b200_batch_verify_hashes(const void *signature, const void *pubkeys, const v
 int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,
                                   const void *message_hash, int *out_verified);
 
+/* ---- batched hash-to-G1 ------------------------------------------------------------------------------
+ * Replaces HashToCurve::hash for BLS12-377 G1 -- the step before the multi-pairing in
+ * PublicKey::verify / Signature::batch_verify (crates/bls-crypto/src/bls/signature.rs:111-114):
+ *   B200_HASHER_DIRECT     DIRECT_HASH_TO_G1    (hash_to_curve/try_and_increment.rs:36-38; hashers/direct.rs:20-80)
+ *   B200_HASHER_COMPOSITE  COMPOSITE_HASH_TO_G1 (try_and_increment.rs:29-31; hashers/composite.rs:15-95: Bowe-Hopwood
+ *                          CRH over ed-on-bw6-761 with the reference's ChaCha20-seeded generators, then the XOF)
+ * flags: B200_HASH_COMPAT = the `compat` cargo feature's sign-bit rule (the reference's default,
+ *   try_and_increment.rs:103-117); B200_HASH_CIP22 = TryAndIncrementCIP22 (try_and_increment_cip22.rs:60-134);
+ *   B200_HASH_CRH_ONLY = Hasher::crh of each message alone: out receives n x 48 bytes (the composite CRH's 48-byte
+ *   x coordinate, or the direct CRH's 32 bytes followed by zeros) instead of points.
+ * domain: at most 8 bytes (BLSError::DomainTooLarge otherwise -> B200_ERR_ARG).  Each input is hashed as
+ * counter | extra_data | message for counter = 0..254 until a candidate decodes to a point whose cofactor multiple
+ * is not zero; out_jacobian receives n G1Projective memory images (144 B, what HashToCurve::hash returns),
+ * out_attempts (may be NULL) the successful counters (hash_with_attempt).  All n inputs run in one launch,
+ * one warp per input.  An input larger than the CRH's 156 240 bits, or one with no point in 255 attempts
+ * (BLSError::HashToCurveError), fails the call with B200_ERR_ARG. */
+enum { B200_HASHER_DIRECT = 0, B200_HASHER_COMPOSITE = 1 };
+enum { B200_HASH_COMPAT = 1, B200_HASH_CIP22 = 2, B200_HASH_CRH_ONLY = 4 };
+typedef struct {
+    const uint8_t *message;
+    size_t message_len;
+    const uint8_t *extra_data;
+    size_t extra_data_len;
+} b200_hash_input;
+int b200_hash_to_g1(int hasher, int flags, const uint8_t *domain, size_t domain_len, const b200_hash_input *inputs, size_t n,
+                    void *out_jacobian, uint32_t *out_attempts);
+
 /* ---- radix-2 NTT and the Groth16 witness map ------------------------------------------------------
  * Replaces ark-poly 0.1.0 Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place and the
  * transform chain of ark-groth16 0.1.0 R1CStoQAP::witness_map, which create_proof_no_zk runs right

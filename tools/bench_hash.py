@@ -1,0 +1,47 @@
+"""Batched hash-to-G1 (b200_hash_to_g1): the messages of a 4096-signature batch
+(BASELINE config 2) hashed in one launch, timed through the host-pointer C-ABI (host messages in, 144-byte
+G1Projective images out), next to the Python oracle on a small sample.  Not the headline bench; one JSON line.
+    PYTHONPATH=. python tools/bench_hash.py [--n 4096] [--steps 5]"""
+import argparse
+import json
+import time
+
+from celo_bls_snark_rs_b200 import engine as E
+from oracle import hash_to_curve as H
+from oracle import oracle as O
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=5)
+    args = ap.parse_args()
+    E.init(0)
+    rng = O.SplitMix64(5)
+    res = {"tool": "bench_hash", "n": args.n, "steps": args.steps, "cases": []}
+    t0 = time.perf_counter()
+    E.hash_crh(E.HASHER_COMPOSITE, b"", [b"x"])             # builds the CRH table (first use)
+    res["crh_table_setup_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
+    for msg_len in (32, 1024):
+        inputs = [(bytes(rng.below(256) for _ in range(msg_len)), b"\x01\x02") for _ in range(args.n)]
+        for name, hasher, oh, cip22 in (("direct", E.HASHER_DIRECT, H.DIRECT, False),
+                                        ("composite", E.HASHER_COMPOSITE, H.COMPOSITE, False),
+                                        ("composite_cip22", E.HASHER_COMPOSITE, H.COMPOSITE, True)):
+            E.hash_to_g1(hasher, b"ULforxof", inputs, cip22=cip22)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                _, att = E.hash_to_g1(hasher, b"ULforxof", inputs, cip22=cip22)
+            ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            sample = inputs[:4]
+            t0 = time.perf_counter()
+            for m, e in sample:
+                H.try_and_increment(O.G1, oh, b"ULforxof", m, e, compat=True, cip22=cip22)
+            cpu_ms = (time.perf_counter() - t0) * 1e3 / len(sample)
+            res["cases"].append({"hasher": name, "message_bytes": msg_len, "e2e_ms": round(ms, 3),
+                                 "hashes_per_s": round(args.n / ms * 1e3), "max_attempt": max(att),
+                                 "python_oracle_ms_per_hash": round(cpu_ms, 2)})
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
