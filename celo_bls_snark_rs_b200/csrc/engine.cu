@@ -105,7 +105,7 @@ void b200_shutdown(void) {
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->bh_table, &E->hash_ws})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
         b->release();
     for (NttDomain &d : E->ntt)
         for (Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();

@@ -91,8 +91,8 @@ struct Engine {
     // batch-verification composites (inst_verify.cu)
     Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff;
     // hash-to-G1 (inst_hash.cu): affine multiples of the Bowe-Hopwood generators (built at first use), per-call staging
-    Buffer bh_table, hash_ws;
-    bool bh_ready = false;
+    Buffer bh_table, hash_ws, sqrt_tables;
+    bool bh_ready = false, sqrt_ready = false;
     // optional timing of the dominant kernel (b200_profile_*): event pairs around k_bucket_accumulate
     bool profile = false;
     static constexpr int PROF_SLOTS = 256;

@@ -13,8 +13,9 @@
 //     process in affine form (30 MB in HBM); the 32 lanes add strided chunks (7 products per mixed addition) and a
 //     shuffle tree folds them.  In the non-CIP22 flow the counter only touches chunks 0..2, so the rest of the sum is
 //     computed once and each attempt adds three points;
-//   * Blake2s (CRH of the direct hasher and both XOF blocks), the candidate decoding, the Tonelli-Shanks square root
-//     and the cofactor multiplication run on lane 0 -- chains of dependent field products; the batch is the parallelism.
+//   * the 32 lanes then try 32 consecutive counters at once -- Blake2s (CRH of the direct hasher and both XOF blocks),
+//     candidate decoding and the Tonelli-Shanks square root per lane; a ballot picks the lowest successful counter and
+//     the warp multiplies that point by the cofactor with quad-cooperative XYZZ steps.
 // The generators are derived at first use exactly as `setup_crh` does (composite.rs:53-72): ChaCha20 on the host
 // (byte work; the stream positions do not depend on curve arithmetic), the candidate points tested on the device.
 #include "codec.cuh"
@@ -26,6 +27,7 @@ using HFq = Fq377;
 
 enum : int { BH_WINDOW = 93, BH_WINDOWS = 560, BH_CHUNKS = BH_WINDOW * BH_WINDOWS, BH_SETUP_ATTEMPTS = 2048 };
 enum : uint32_t { HASH_FAILED = 0xffffffffu };
+enum : int { HASH_DEFAULT_OCC = 8 };
 
 struct EdExt {
     HFq x, y, z, t;
@@ -244,6 +246,73 @@ B200_DEV void ed_x_bytes(const EdExt &p, uint32_t *out12) {
     for (int k = 0; k < 12; k++) out12[k] = x.l[k];
 }
 
+// ---- square root by a windowed discrete logarithm in the 2-Sylow subgroup --------------------------------------
+// p - 1 = 2^46 t.  With x0 = a^((t+1)/2) and b = a^t = root^e (root of order 2^46; e is even iff a is a square),
+// sqrt(a) = x0 root^(-e/2).  Tonelli-Shanks (codec.cuh) finds e one bit per round at ~46 squarings a round, and
+// with 32 lanes on different branches the warp pays the longest chain (~1000 squarings).  Here e is read six bits
+// at a time: digit i is identified by raising b (digits below i already cancelled) to 2^(46 - 6(i+1)) and looking
+// the result up among the 64 powers of root^(2^40); x and b are then corrected from a table.  154 squarings, 16
+// products and 8 look-ups per root, the same on every lane.
+enum : int { TS_S = Fq377Params::TWO_ADICITY, TS_W = 6, TS_WINDOWS = (TS_S + TS_W - 1) / TS_W, TS_DIGITS = 1 << TS_W };
+struct alignas(16) SqrtTables {
+    HFq::Mem lookup[TS_DIGITS];                          // (root^(2^(46 - 6)))^d
+    HFq::Mem half[TS_WINDOWS][TS_DIGITS];                // root^(-d 2^(6 i) / 2)   (window 0: even d only)
+};
+// one thread per (window, digit) plus one block row for the look-up powers
+__global__ void __launch_bounds__(TS_DIGITS) k_sqrt_tables(SqrtTables *__restrict__ t) {
+    const int d = threadIdx.x, i = blockIdx.x;
+    HFq root;
+#pragma unroll
+    for (int k = 0; k < 12; k++) root.l[k] = Fq377Params::root(k);
+    HFq base;
+    int e;
+    if (i == TS_WINDOWS) {                               // look-up row
+        base = root;
+        for (int k = 0; k < TS_S - TS_W; k++) base = base.sqr();
+        e = d;
+    } else {
+        base = root.inv();
+        for (int k = 0; k < TS_W * i - 1; k++) base = base.sqr();
+        e = i == 0 ? d / 2 : d;
+    }
+    HFq acc = HFq::one();
+#pragma unroll 1
+    for (int k = 0; k < e; k++) acc = acc * base;
+    if (i == TS_WINDOWS) t->lookup[d] = acc.store();
+    else t->half[i][d] = acc.store();
+}
+__device__ __noinline__ bool fq377_sqrt_tab(HFq a, HFq *out, const SqrtTables *__restrict__ t) {
+    if (a.is_zero()) {
+        *out = a;
+        return true;
+    }
+    HFq z = fp_pow_words<HFq>(a, FQ377_TS_EXP, FQ377_TS_EXP_BITS);              // a^((t - 1) / 2)
+    HFq x = a * z;                                                              // a^((t + 1) / 2)
+    HFq b = x * z;                                                              // a^t = root^e
+#pragma unroll 1
+    for (int i = 0; i < TS_WINDOWS; i++) {
+        const int width = (i + 1) * TS_W <= TS_S ? TS_W : TS_S - i * TS_W;      // the last window holds 4 bits
+        HFq c = b;
+#pragma unroll 1
+        for (int k = 0; k < TS_S - i * TS_W - width; k++) c = c.sqr();
+        // c = lookup[d << (6 - width)]
+        int d = -1;
+#pragma unroll 1
+        for (int j = 0; j < (1 << width) && d < 0; j++) {
+            const HFq::Mem &m = t->lookup[j << (TS_W - width)];
+            if (m.w[0] != c.l[0] || m.w[1] != c.l[1]) continue;
+            if (HFq::load(m) == c) d = j;
+        }
+        if (d < 0 || (i == 0 && (d & 1))) return false;   // e odd: a is not a square (d < 0 cannot happen)
+        if (d == 0) continue;
+        const HFq h = HFq::load(t->half[i][d]);
+        x = x * h;
+        b = b * h.sqr();
+    }
+    *out = x;
+    return x.sqr() == a;
+}
+
 // ---- the try-and-increment loop ------------------------------------------------------------------------------
 enum : int { HASHER_DIRECT = 0, HASHER_COMPOSITE = 1 };
 enum : int { HASH_FLAG_COMPAT = 1, HASH_FLAG_CIP22 = 2, HASH_FLAG_CRH_ONLY = 4 };
@@ -251,9 +320,11 @@ enum : int { HASH_FLAG_COMPAT = 1, HASH_FLAG_CIP22 = 2, HASH_FLAG_CRH_ONLY = 4 }
 // cofactor of BLS12-377 G1, (x - 1)^2 / 3 = 0x170b5d44300000000000000000000000 (125 bits)
 static __device__ const uint32_t G1_COFACTOR[4] = {0x00000000u, 0x00000000u, 0x30000000u, 0x170b5d44u};
 
-__global__ void __launch_bounds__(32) k_hash_to_g1(const uint8_t *__restrict__ data, const HashMsg *__restrict__ msgs, uint32_t n,
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(32, MIN_BLOCKS) k_hash_to_g1(const uint8_t *__restrict__ data, const HashMsg *__restrict__ msgs, uint32_t n,
                                                    int hasher, int flags, uint32_t pers0, uint32_t pers1,
-                                                   const EdTabMem *__restrict__ table, JacobianMem<HFq> *__restrict__ out,
+                                                   const EdTabMem *__restrict__ table, const SqrtTables *__restrict__ sqrt_tables,
+                                                   JacobianMem<HFq> *__restrict__ out,
                                                    uint32_t *__restrict__ attempts, uint32_t *__restrict__ crh_out) {
     const uint32_t i = blockIdx.x;
     const int lane = threadIdx.x;
@@ -286,54 +357,76 @@ __global__ void __launch_bounds__(32) k_hash_to_g1(const uint8_t *__restrict__ d
             for (int k = 0; k < 12; k++) crh_out[12 * (size_t)i + k] = (composite || k < 8) ? inner[k] : 0u;
         return;
     }
-    if (lane != 0) return;
+    // The 32 lanes try 32 consecutive counters at once (a lone lane would cost the same issue slots); the lowest
+    // successful counter wins, exactly as the sequential loop of the reference would find it.
     const uint32_t inner_len = composite ? 48 : 32;
-    uint32_t result = HASH_FAILED;
+    const unsigned full = 0xffffffffu;
+    if (composite && !cip22)
+        rest = {rest.x.shfl(full, 0), rest.y.shfl(full, 0), rest.z.shfl(full, 0), rest.t.shfl(full, 0)};
+    const Quad Q;
+    bool done = false;
 #pragma unroll 1
-    for (uint32_t c = 0; c < 255; c++) {                  // NUM_TRIES, try_and_increment.rs:26
-        uint32_t crh[12];
-        ByteSrc xin;
-        if (cip22) {
-            xin = {1, (uint8_t)c, extra, hm.extra_len, reinterpret_cast<const uint8_t *>(inner), inner_len};
-        } else {
-            if (composite) {
-                EdExt s = rest;
-                for (uint32_t k = 0; k < 3; k++) s = bh_add_chunk(s, k, 1, c, extra, body_len, table);
-                ed_x_bytes(s, crh);
+    for (uint32_t first = 0; first < 255 && !done; first += 32) {          // NUM_TRIES, try_and_increment.rs:26
+        const uint32_t c = first + lane;
+        bool ok = false;
+        HFq x = HFq::zero(), y = HFq::zero();
+        if (c < 255) {
+            uint32_t crh[12];
+            ByteSrc xin;
+            if (cip22) {
+                xin = {1, (uint8_t)c, extra, hm.extra_len, reinterpret_cast<const uint8_t *>(inner), inner_len};
             } else {
-                ByteSrc src = {1, (uint8_t)c, extra, body_len, nullptr, 0};
-                blake2s_dev(crh, src, 0x01010020u, 0, 0, HB, pers0, pers1);
+                if (composite) {
+                    EdExt s = rest;
+                    for (uint32_t k = 0; k < 3; k++) s = bh_add_chunk(s, k, 1, c, extra, body_len, table);
+                    ed_x_bytes(s, crh);
+                } else {
+                    ByteSrc src = {1, (uint8_t)c, extra, body_len, nullptr, 0};
+                    blake2s_dev(crh, src, 0x01010020u, 0, 0, HB, pers0, pers1);
+                }
+                xin = {0, 0, reinterpret_cast<const uint8_t *>(crh), inner_len, nullptr, 0};
             }
-            xin = {0, 0, reinterpret_cast<const uint8_t *>(crh), inner_len, nullptr, 0};
+            // XOF (direct.rs:41-79): two 32-byte blocks, fanout 0, depth 0, leaf 32, inner 32, node offset = block index
+            uint32_t h0[8], h1[8], w[12];
+            blake2s_dev(h0, xin, 32u, 32u, 0u, HB | (32u << 24), pers0, pers1);
+            blake2s_dev(h1, xin, 32u, 32u, 1u, HB | (32u << 24), pers0, pers1);
+            for (int k = 0; k < 8; k++) w[k] = h0[k];
+            for (int k = 0; k < 4; k++) w[8 + k] = h1[k];
+            // from_random_bytes: byte 47 carries the flags (bit 7 sign, bit 6 infinity); `compat` moves bit 1 into bit 7
+            const bool positive = compat ? (w[11] >> 25) & 1u : (w[11] >> 31) & 1u;
+            const bool infinity = (w[11] >> 30) & 1u;
+            w[11] &= 0x01ffffffu;
+            if (fp_words_lt_modulus<HFq>(w)) {
+                x = fp_from_canonical<HFq>(w);
+                // (0, infinity flag) is the zero point, whose cofactor multiple is zero -> next counter
+                if (!(x.is_zero() && infinity) && fq377_sqrt_tab(x.sqr() * x + HFq::one(), &y, sqrt_tables)) {
+                    if (fp_canonical_over_half(fp_to_canonical(y)) != positive) y = y.neg();
+                    ok = true;
+                }
+            }
         }
-        // XOF (direct.rs:41-79): two 32-byte blocks, fanout 0, depth 0, leaf 32, inner 32, node offset = block index
-        uint32_t h0[8], h1[8], w[12];
-        blake2s_dev(h0, xin, 32u, 32u, 0u, HB | (32u << 24), pers0, pers1);
-        blake2s_dev(h1, xin, 32u, 32u, 1u, HB | (32u << 24), pers0, pers1);
-        for (int k = 0; k < 8; k++) w[k] = h0[k];
-        for (int k = 0; k < 4; k++) w[8 + k] = h1[k];
-        // from_random_bytes: byte 47 carries the flags (bit 7 sign, bit 6 infinity); `compat` moves bit 1 into bit 7
-        const bool positive = compat ? (w[11] >> 25) & 1u : (w[11] >> 31) & 1u;
-        const bool infinity = (w[11] >> 30) & 1u;
-        w[11] &= 0x01ffffffu;
-        if (!fp_words_lt_modulus<HFq>(w)) continue;
-        HFq x = fp_from_canonical<HFq>(w), y;
-        if (x.is_zero() && infinity) continue;            // the zero point: scale_by_cofactor gives zero -> next counter
-        if (!fq377_sqrt(x.sqr() * x + HFq::one(), &y)) continue;
-        if (fp_canonical_over_half(fp_to_canonical(y)) != positive) y = y.neg();
-        XYZZ<HFq> acc = XYZZ<HFq>::inf();
-        acc.madd(x, y);
+        unsigned winners = __ballot_sync(full, ok);
 #pragma unroll 1
-        for (int b = 123; b >= 0; b--) {
-            acc.dbl();
-            if ((G1_COFACTOR[b >> 5] >> (b & 31)) & 1u) acc.madd(x, y);
+        while (winners && !done) {
+            const int win = __ffs(winners) - 1;
+            winners &= winners - 1;
+            // scale_by_cofactor on every quad of the warp at once (quad-cooperative XYZZ steps, ec.cuh)
+            const XYZZ<HFq> base = {x.shfl(full, win), y.shfl(full, win), HFq::one(), HFq::one()};
+            XYZZ<HFq> acc = base;
+#pragma unroll 1
+            for (int b = 123; b >= 0; b--) {
+                quad_dbl(Q, acc);
+                if ((G1_COFACTOR[b >> 5] >> (b & 31)) & 1u) quad_add(Q, acc, base);
+            }
+            if (acc.is_inf()) continue;                   // scaled.is_zero(): the reference moves on to the next counter
+            if (lane == 0) {
+                out[i] = acc.to_jacobian().to_ark();
+                attempts[i] = first + win;
+            }
+            done = true;
         }
-        if (acc.is_inf()) continue;
-        out[i] = acc.to_jacobian().to_ark();
-        result = c;
-        break;
     }
-    attempts[i] = result;
+    if (!done && lane == 0) attempts[i] = HASH_FAILED;
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
@@ -459,6 +552,12 @@ int hash_to_g1(Engine &E, int hasher, int flags, const uint8_t *domain, size_t d
     }
     int rc;
     if (composite && (rc = ensure_bh_table(E, st))) return rc;
+    if (!E.sqrt_ready) {
+        if ((rc = E.sqrt_tables.reserve(sizeof(SqrtTables)))) return rc;
+        k_sqrt_tables<<<TS_WINDOWS + 1, TS_DIGITS, 0, st>>>(E.sqrt_tables.as<SqrtTables>());
+        LAUNCH_CHECK();
+        E.sqrt_ready = true;
+    }
     const size_t meta_off = (blob.size() + 15) & ~(size_t)15, out_off = meta_off + n * sizeof(HashMsg), att_off = out_off + n * 144,
                  crh_off = att_off + ((n * 4 + 15) & ~(size_t)15);
     if ((rc = E.hash_ws.reserve(crh_off + n * 48))) return rc;
@@ -469,10 +568,18 @@ int hash_to_g1(Engine &E, int hasher, int flags, const uint8_t *domain, size_t d
     memcpy(pers, personal, 8);
     CUDA_TRY(cudaMemcpyAsync(base, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(base + meta_off, metas.data(), n * sizeof(HashMsg), cudaMemcpyHostToDevice, st));
-    k_hash_to_g1<<<(unsigned)n, 32, 0, st>>>(reinterpret_cast<const uint8_t *>(base), reinterpret_cast<const HashMsg *>(base + meta_off),
-                                             (uint32_t)n, hasher, flags, pers[0], pers[1], E.bh_table.as<EdTabMem>(),
-                                             reinterpret_cast<JacobianMem<HFq> *>(base + out_off),
-                                             reinterpret_cast<uint32_t *>(base + att_off), reinterpret_cast<uint32_t *>(base + crh_off));
+    // resident warps per SM: the loop is a chain of dependent 377-bit products, so throughput comes from warps in
+    // flight; the register cap that pays for them is chosen by measurement (profiles/r1_hash_to_g1.md)
+    static const int occ = getenv("B200_HASH_OCC") ? atoi(getenv("B200_HASH_OCC")) : HASH_DEFAULT_OCC;
+    auto launch = [&](auto kernel) {
+        kernel<<<(unsigned)n, 32, 0, st>>>(reinterpret_cast<const uint8_t *>(base), reinterpret_cast<const HashMsg *>(base + meta_off),
+                                           (uint32_t)n, hasher, flags, pers[0], pers[1], E.bh_table.as<EdTabMem>(),
+                                           E.sqrt_tables.as<SqrtTables>(), reinterpret_cast<JacobianMem<HFq> *>(base + out_off),
+                                           reinterpret_cast<uint32_t *>(base + att_off), reinterpret_cast<uint32_t *>(base + crh_off));
+    };
+    if (occ >= 16) launch(k_hash_to_g1<16>);
+    else if (occ >= 12) launch(k_hash_to_g1<12>);
+    else launch(k_hash_to_g1<8>);
     LAUNCH_CHECK();
     if (crh_only) {
         CUDA_TRY(cudaMemcpyAsync(out, base + crh_off, n * 48, cudaMemcpyDeviceToHost, st));

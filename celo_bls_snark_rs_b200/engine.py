@@ -358,16 +358,30 @@ HASHER_DIRECT, HASHER_COMPOSITE = 0, 1
 HASH_COMPAT, HASH_CIP22, HASH_CRH_ONLY = 1, 2, 4
 
 
+class HashBatch:
+    """The b200_hash_input array of a batch plus its output buffers, built once and reusable across calls (the
+    marshalling of thousands of small Python byte strings is host work outside the C-ABI)."""
+
+    def __init__(self, inputs):
+        self.inputs = list(inputs)                       # keeps the byte strings alive
+        self.n = len(self.inputs)
+        self.arr = (HashInput * max(self.n, 1))(*[HashInput(m, len(m), e, len(e)) for m, e in self.inputs])
+        self.out = np.zeros(max(self.n, 1) * 144, dtype=np.uint8)
+        self.att = np.zeros(max(self.n, 1), dtype=np.uint32)
+
+    def run(self, hasher: int, domain: bytes, flags: int):
+        _check(load().b200_hash_to_g1(hasher, flags, domain, len(domain), self.arr, self.n, _hptr(self.out), _hptr(self.att)))
+
+    def results(self):
+        return [self.out[144 * i:144 * (i + 1)].tobytes() for i in range(self.n)], self.att[:self.n].tolist()
+
+
 def hash_to_g1(hasher: int, domain: bytes, inputs, compat: bool = True, cip22: bool = False):
     """HashToCurve::hash for every (message, extra_data) of `inputs` in one launch ->
     (n x 144-byte G1Projective images, attempts)."""
-    n = len(inputs)
-    arr = (HashInput * max(n, 1))(*[HashInput(m, len(m), e, len(e)) for m, e in inputs])
-    out = np.zeros(n * 144, dtype=np.uint8)
-    att = np.zeros(max(n, 1), dtype=np.uint32)
-    flags = (HASH_COMPAT if compat else 0) | (HASH_CIP22 if cip22 else 0)
-    _check(load().b200_hash_to_g1(hasher, flags, domain, len(domain), arr, n, _hptr(out), _hptr(att)))
-    return [out[144 * i:144 * (i + 1)].tobytes() for i in range(n)], att[:n].tolist()
+    batch = inputs if isinstance(inputs, HashBatch) else HashBatch(inputs)
+    batch.run(hasher, domain, (HASH_COMPAT if compat else 0) | (HASH_CIP22 if cip22 else 0))
+    return batch.results()
 
 
 def hash_crh(hasher: int, domain: bytes, messages):
