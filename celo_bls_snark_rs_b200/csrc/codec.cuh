@@ -246,6 +246,83 @@ static __global__ void __launch_bounds__(64) k_g2_377_decompress(const uint32_t 
     status[i] = st;
 }
 
+// BLS12-377 G1 (y^2 = x^3 + 1): n x 48 bytes -> packed affine + status (Signature::deserialize,
+// crates/bls-crypto/src/bls/signature.rs via G1Affine::deserialize)
+static __global__ void __launch_bounds__(64) k_g1_377_decompress(const uint32_t *__restrict__ src, uint32_t n,
+                                                                 AffineMem<CFq> *__restrict__ out, int *__restrict__ status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) w[k] = src[12 * (size_t)i + k];
+    const bool larger = (w[11] >> 31) & 1u, infinity = (w[11] >> 30) & 1u;
+    w[11] &= 0x3fffffffu;
+    AffineMem<CFq> rec;
+    rec.x = CFq::zero().store();
+    rec.y = rec.x;
+    int st = DECODE_OK;
+    if (infinity) {
+        st = DECODE_INFINITY;
+    } else if (!fp_words_lt_modulus<CFq>(w)) {
+        st = DECODE_BAD_COORD;
+    } else {
+        CFq x = fp_from_canonical<CFq>(w), y;
+        if (!fq377_sqrt(x.sqr() * x + CFq::one(), &y)) {
+            st = DECODE_NOT_ON_CURVE;
+        } else {
+            if (fp_canonical_over_half(fp_to_canonical(y)) != larger) y = y.neg();
+            rec.x = x.store();
+            rec.y = y.store();
+        }
+    }
+    out[i] = rec;
+    status[i] = st;
+}
+
+// ---- encoding: GroupProjective memory images -> arkworks compressed bytes (into_affine().serialize()) ------------
+// Signature::serialize / PublicKey::serialize (crates/bls-crypto/src/bls/signature.rs, public.rs:123-135).
+// One thread per point: one inversion, canonical x, the "y is the larger root" bit; z = 0 -> the infinity encoding.
+static __global__ void __launch_bounds__(64) k_g1_377_compress(const JacobianMem<CFq> *__restrict__ pts, uint32_t n, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CFq X = CFq::from_ark(pts[i].x), Y = CFq::from_ark(pts[i].y), Z = CFq::from_ark(pts[i].z);
+    uint32_t w[12] = {0};
+    if (Z.is_zero()) {
+        w[11] = 1u << 30;
+    } else {
+        const CFq zi = Z.inv(), zi2 = zi.sqr();
+        const CFq x = fp_to_canonical(X * zi2), y = Y * zi2 * zi;
+#pragma unroll
+        for (int k = 0; k < 12; k++) w[k] = x.l[k];
+        if (fp_canonical_over_half(fp_to_canonical(y))) w[11] |= 1u << 31;
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[12 * (size_t)i + k] = w[k];
+}
+static __global__ void __launch_bounds__(64) k_g2_377_compress(const JacobianMem<CFq2> *__restrict__ pts, uint32_t n, uint32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CFq2 X = CFq2::from_ark(pts[i].x), Y = CFq2::from_ark(pts[i].y), Z = CFq2::from_ark(pts[i].z);
+    uint32_t w[24] = {0};
+    if (Z.is_zero()) {
+        w[23] = 1u << 30;
+    } else {
+        const CFq2 zi = cfq2_inv(Z), zi2 = zi.sqr();
+        const CFq2 x = X * zi2, y = Y * zi2 * zi;
+        const CFq c0 = fp_to_canonical(x.c0), c1 = fp_to_canonical(x.c1);
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            w[k] = c0.l[k];
+            w[12 + k] = c1.l[k];
+        }
+        const bool larger = y.c1.is_zero() ? fp_canonical_over_half(fp_to_canonical(y.c0))
+                                           : fp_canonical_over_half(fp_to_canonical(y.c1));
+        if (larger) w[23] |= 1u << 31;
+    }
+#pragma unroll
+    for (int k = 0; k < 24; k++) out[24 * (size_t)i + k] = w[k];
+}
+
 // r * P == O for every decoded point (is_in_correct_subgroup_assuming_on_curve); r = the words of the scalar-field
 // modulus.  One thread per point, XYZZ double-and-add (exceptional cases exact, so the last addition lands on O).
 template <class F, class RP>

@@ -94,6 +94,8 @@ int b200_init(int device) {
     return B200_OK;
 }
 
+int b200_ensure_init(void) { return g_engine ? B200_OK : b200_init(-1); }
+
 void b200_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_engine_mu);
     if (!g_engine) return;
@@ -101,14 +103,14 @@ void b200_shutdown(void) {
     cudaSetDevice(E->device);
     cudaStreamSynchronize(E->stream);
     for (MsmWs &w : E->ws)
-        for (Buffer *b : {&w.counts, &w.offsets, &w.cursor, &w.tile_sums, &w.bins, &w.order, &w.sorted, &w.buckets, &w.partials,
+        for (b200::Buffer *b : {&w.counts, &w.offsets, &w.cursor, &w.tile_sums, &w.bins, &w.order, &w.sorted, &w.buckets, &w.partials,
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
-    for (Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
+    for (b200::Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
                       &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
         b->release();
     for (NttDomain &d : E->ntt)
-        for (Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
+        for (b200::Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
     for (auto &ev : E->prof_ev)
         if (ev) cudaEventDestroy(ev);
     cudaEventDestroy(E->done);
@@ -378,7 +380,7 @@ int b200_groth16_verify_bw6_761(const b200_groth16_vk *vk, const void *proof_a, 
 
 int b200_deserialize_points(int kind, const void *bytes, size_t n, int check_subgroup, void *out_packed, int *out_status) {
     if (n && (!bytes || (!out_packed && !out_status))) return fail(B200_ERR_ARG, "null pointer");
-    if (kind < 0 || kind > 2) return fail(B200_ERR_ARG, "unknown point kind %d", kind);
+    if (kind < 0 || kind > 3) return fail(B200_ERR_ARG, "unknown point kind %d", kind);
     REQUIRE_ENGINE();
     return decode_points_host(E, kind, bytes, n, check_subgroup, out_packed, out_status);
 }
@@ -450,6 +452,12 @@ int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, c
         return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     return batch_verify_strict_hash(E, pubkeys, signatures, exponents, n, message_hash, out_verified);
+}
+
+int b200_serialize_points(int kind, const void *jacobian_images, size_t n, void *out_bytes) {
+    if (n && (!jacobian_images || !out_bytes)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    return encode_points_host(E, kind, jacobian_images, n, out_bytes);
 }
 
 int b200_hash_to_g1(int hasher, int flags, const uint8_t *domain, size_t domain_len, const b200_hash_input *inputs, size_t n,

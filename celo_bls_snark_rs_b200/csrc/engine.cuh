@@ -135,6 +135,7 @@ int bw6_groth16_verify(Engine &E, const b200_groth16_vk *vk, const void *proof_a
 int bw6_groth16_verify_core(Engine &E, char *d_packed, size_t nabc, const void *d_scalars, int *out_verified);
 // point decoding and the bls-snark-sys `verify` entry point (inst_epoch_verify.cu)
 int decode_points_host(Engine &E, int kind, const void *bytes, size_t n, int subgroup, void *out_packed, int *out_status);
+int encode_points_host(Engine &E, int kind, const void *images, size_t n, void *out_bytes);
 int epoch_verify(Engine &E, const uint8_t *vk, size_t vk_len, const uint8_t *proof, size_t proof_len, const EpochBlockFFI &first,
                  const EpochBlockFFI &last, int *out_ok, std::string *why);
 int epoch_public_inputs(Engine &E, const EpochBlockFFI &first, const EpochBlockFFI &last, std::vector<uint64_t> *inputs, int *ok,

@@ -171,6 +171,14 @@ int decode_points(int kind, const void *d_src, size_t n, int subgroup, void *d_o
             k_subgroup_check<Fq761, Fq377Params><<<blocks, 64, 0, st>>>(reinterpret_cast<const AffineMem<Fq761> *>(d_out), (uint32_t)n, d_status);
             LAUNCH_CHECK();
         }
+    } else if (kind == 3) {
+        k_g1_377_decompress<<<blocks, 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)n,
+                                                   reinterpret_cast<AffineMem<CFq> *>(d_out), d_status);
+        LAUNCH_CHECK();
+        if (subgroup) {
+            k_subgroup_check<CFq, Fr253Params><<<blocks, 64, 0, st>>>(reinterpret_cast<const AffineMem<CFq> *>(d_out), (uint32_t)n, d_status);
+            LAUNCH_CHECK();
+        }
     } else {
         return fail(B200_ERR_ARG, "unknown point kind %d", kind);
     }
@@ -181,11 +189,30 @@ int decode_points_host(Engine &E, int kind, const void *bytes, size_t n, int sub
     cudaStream_t st = E.stream;
     int rc;
     if (n == 0) return B200_OK;
-    if ((rc = E.h2d_bases.reserve(n * 96)) || (rc = E.native_bases.reserve(n * 192)) || (rc = E.scalars.reserve(n * sizeof(int)))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bytes, n * 96, cudaMemcpyHostToDevice, st));
+    const size_t enc = kind == 3 ? 48 : 96;                // bytes of one encoding; the packed record is twice that
+    if ((rc = E.h2d_bases.reserve(n * enc)) || (rc = E.native_bases.reserve(n * 2 * enc)) || (rc = E.scalars.reserve(n * sizeof(int)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bytes, n * enc, cudaMemcpyHostToDevice, st));
     if ((rc = decode_points(kind, E.h2d_bases.p, n, subgroup, E.native_bases.p, E.scalars.as<int>(), st))) return rc;
-    if (out_packed) CUDA_TRY(cudaMemcpyAsync(out_packed, E.native_bases.p, n * 192, cudaMemcpyDeviceToHost, st));
+    if (out_packed) CUDA_TRY(cudaMemcpyAsync(out_packed, E.native_bases.p, n * 2 * enc, cudaMemcpyDeviceToHost, st));
     if (out_status) CUDA_TRY(cudaMemcpyAsync(out_status, E.scalars.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+// GroupProjective images (host) -> compressed encodings (host): kind 0 = BLS12-377 G2 (288 B -> 96 B), 3 = G1 (144 B -> 48 B)
+int encode_points_host(Engine &E, int kind, const void *images, size_t n, void *out_bytes) {
+    if (kind != 0 && kind != 3) return fail(B200_ERR_ARG, "unknown point kind %d", kind);
+    if (n == 0) return B200_OK;
+    cudaStream_t st = E.stream;
+    int rc;
+    const size_t enc = kind == 3 ? 48 : 96;
+    if ((rc = E.h2d_bases.reserve(n * 3 * enc)) || (rc = E.native_bases.reserve(n * enc))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, images, n * 3 * enc, cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)ceil_div(n, 64);
+    if (kind == 3) k_g1_377_compress<<<blocks, 64, 0, st>>>(E.h2d_bases.as<JacobianMem<CFq>>(), (uint32_t)n, E.native_bases.as<uint32_t>());
+    else k_g2_377_compress<<<blocks, 64, 0, st>>>(E.h2d_bases.as<JacobianMem<CFq2>>(), (uint32_t)n, E.native_bases.as<uint32_t>());
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out_bytes, E.native_bases.p, n * enc, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return B200_OK;
 }

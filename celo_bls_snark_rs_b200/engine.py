@@ -35,10 +35,12 @@ EXPORTS = [
     "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_msm_batch_device",
     "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
     "b200_groth16_verify_bw6_761", "b200_deserialize_points", "b200_verify_epochs", "b200_epoch_public_inputs",
-    "b200_blake2s_personal", "b200_hash_to_g1",
+    "b200_blake2s_personal", "b200_hash_to_g1", "b200_serialize_points", "b200_ensure_init",
 ]
 # the reference's own symbols re-exported by the library (include/bls_snark_sys_compat.h)
-COMPAT_EXPORTS = ["verify"]
+COMPAT_EXPORTS = ["verify", "deserialize_public_key", "deserialize_signature", "serialize_public_key", "serialize_signature",
+                  "free_vec", "destroy_public_key", "destroy_signature", "aggregate_public_keys", "aggregate_signatures",
+                  "verify_signature", "verify_pop", "batch_verify_signature", "batch_verify_strict"]
 
 
 class Groth16Pk(ctypes.Structure):
@@ -63,6 +65,23 @@ class HashInput(ctypes.Structure):
     """b200_hash_input"""
     _fields_ = [("message", ctypes.c_char_p), ("message_len", ctypes.c_size_t), ("extra_data", ctypes.c_char_p),
                 ("extra_data_len", ctypes.c_size_t)]
+
+
+class FFIBuffer(ctypes.Structure):
+    """bls-snark-sys Buffer (utils.rs:75-82)"""
+    _fields_ = [("ptr", ctypes.c_char_p), ("len", ctypes.c_size_t)]
+
+
+class MessageFFI(ctypes.Structure):
+    """bls-snark-sys MessageFFI (utils.rs:20-32), 48 bytes"""
+    _fields_ = [("data", FFIBuffer), ("extra", FFIBuffer), ("public_key", ctypes.c_void_p), ("sig", ctypes.c_void_p)]
+
+
+class BatchMessageFFI(ctypes.Structure):
+    """bls-snark-sys BatchMessageFFI (utils.rs:58-72), 64 bytes"""
+    _fields_ = [("data", FFIBuffer), ("extra", FFIBuffer), ("public_keys", ctypes.POINTER(ctypes.c_void_p)),
+                ("public_keys_len", ctypes.c_size_t), ("signatures", ctypes.POINTER(ctypes.c_void_p)),
+                ("signatures_len", ctypes.c_size_t)]
 
 
 class MsmJob(ctypes.Structure):
@@ -122,6 +141,17 @@ def load() -> ctypes.CDLL:
     lib.b200_groth16_prove_device.argtypes = [i32, ctypes.POINTER(Groth16Pk), vp, sz, sz, vp, vp, vp, ctypes.c_uint, vp, vp]
     lib.b200_msm_batch_device.argtypes = [i32, ctypes.POINTER(MsmJob), sz, vp]
     lib.b200_hash_to_g1.argtypes = [i32, i32, ctypes.c_char_p, sz, ctypes.POINTER(HashInput), sz, vp, vp]
+    lib.b200_serialize_points.argtypes = [i32, vp, sz, vp]
+    cb, pp, pb, ci = ctypes.c_bool, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_bool), ctypes.c_int
+    for name, args in (("deserialize_public_key", [vp, ci, pp]), ("deserialize_signature", [vp, ci, pp]),
+                       ("serialize_public_key", [vp, pp, ctypes.POINTER(ci)]), ("serialize_signature", [vp, pp, ctypes.POINTER(ci)]),
+                       ("free_vec", [vp, ci]), ("destroy_public_key", [vp]), ("destroy_signature", [vp]),
+                       ("aggregate_public_keys", [pp, ci, pp]), ("aggregate_signatures", [pp, ci, pp]),
+                       ("verify_signature", [vp, vp, ci, vp, ci, vp, cb, cb, pb]), ("verify_pop", [vp, vp, ci, vp, pb]),
+                       ("batch_verify_signature", [ctypes.POINTER(MessageFFI), sz, cb, cb, pb]),
+                       ("batch_verify_strict", [ctypes.POINTER(BatchMessageFFI), sz, cb, cb, pb])):
+        getattr(lib, name).argtypes = args
+        getattr(lib, name).restype = cb
     lib.b200_sync.argtypes = [vp]
     lib.b200_msm_plan.argtypes = [i32, sz, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_uint32)]
     lib.b200_launch_count.restype = ctypes.c_uint64

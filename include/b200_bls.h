@@ -53,6 +53,8 @@ enum {
  * and creates its stream and workspace.  Idempotent per device.
  * Reference analogue: bls-snark-sys `init()` (crates/bls-snark-sys/src/lib.rs:29-34). */
 int b200_init(int device);
+/* b200_init(current device) unless an engine is already bound (the reference's `init()` is optional, lib.rs:29-34). */
+int b200_ensure_init(void);
 void b200_shutdown(void);
 const char *b200_last_error(void);
 
@@ -269,8 +271,13 @@ int b200_groth16_verify_bw6_761(const b200_groth16_vk *vk, const void *proof_a, 
  * NULL): n packed affine records (192 B, Montgomery, (0, 0) for infinity or a rejected point); out_status: n
  * ints, 0 ok, 1 infinity, 2 coordinate >= modulus, 3 x not on the curve, 4 not in the prime-order subgroup
  * (only tested when check_subgroup != 0, as deserialize does; deserialize_unchecked does not). */
-enum { B200_POINTS_BLS12_377_G2 = 0, B200_POINTS_BW6_761_G1 = 1, B200_POINTS_BW6_761_G2 = 2 };
+enum { B200_POINTS_BLS12_377_G2 = 0, B200_POINTS_BW6_761_G1 = 1, B200_POINTS_BW6_761_G2 = 2, B200_POINTS_BLS12_377_G1 = 3 };
 int b200_deserialize_points(int kind, const void *bytes, size_t n, int check_subgroup, void *out_packed, int *out_status);
+/* B200_POINTS_BLS12_377_G1 (Signature::deserialize): 48-byte encodings in, 96-byte packed affine records out.
+ * b200_serialize_points: the inverse for the two BLS12-377 groups -- n GroupProjective memory images (kind 3: 144 B,
+ * kind 0: 288 B; Signature / PublicKey) -> into_affine().serialize(): 48 / 96 bytes each, infinity as the flag byte.
+ *   crates/bls-crypto/src/bls/public.rs:123-135, signature.rs (CanonicalSerialize for PublicKey / Signature) */
+int b200_serialize_points(int kind, const void *jacobian_images, size_t n, void *out_bytes);
 
 /* The reference's SNARK verifier entry point with a status code: same arguments as `verify`
  * (include/bls_snark_sys_compat.h, which this library also exports under that name), blocks passed by

@@ -40,6 +40,69 @@ typedef struct {
 bool verify(const uint8_t *vk, uint32_t vk_len, const uint8_t *proof, uint32_t proof_len, EpochBlockFFI first_epoch,
             EpochBlockFFI last_epoch);
 
+/* ---- signature verification (crates/bls-snark-sys/src/signatures.rs, serialization.rs, utils.rs) ---------------------
+ * Handles are heap objects holding the Rust types' memory images, as in the reference (Box::into_raw):
+ * PublicKey = G2Projective (288 bytes), Signature = G1Projective (144 bytes), Montgomery limbs.  They are created by
+ * deserialize_* / aggregate_* and released by destroy_*; byte buffers returned through out-pointers are released by
+ * free_vec.  A handle made by the reference's library has the same layout and can be passed in as it is. */
+typedef struct PublicKey PublicKey;
+typedef struct Signature Signature;
+
+/* utils.rs:75-82 */
+typedef struct {
+    const uint8_t *ptr;
+    size_t len;
+} Buffer;
+/* utils.rs:20-32 (48 bytes) */
+typedef struct {
+    Buffer data;
+    Buffer extra;
+    const PublicKey *public_key;
+    const Signature *sig;
+} MessageFFI;
+/* utils.rs:58-72 (64 bytes) */
+typedef struct {
+    Buffer data;
+    Buffer extra;
+    const PublicKey *const *public_keys;
+    size_t public_keys_len;
+    const Signature *const *signatures;
+    size_t signatures_len;
+} BatchMessageFFI;
+
+/* serialization.rs:35-43, 81-88: ark-serialize compressed encodings (96 / 48 bytes) with every check of
+ * G2Affine / G1Affine::deserialize (coordinate < modulus, on the curve, prime-order subgroup) -> a new handle. */
+bool deserialize_public_key(const uint8_t *in_public_key_bytes, int in_public_key_bytes_len, PublicKey **out_public_key);
+bool deserialize_signature(const uint8_t *in_signature_bytes, int in_signature_bytes_len, Signature **out_signature);
+/* serialization.rs:63-70, 90-97: into_affine().serialize() -> a new 96 / 48-byte buffer (free_vec). */
+bool serialize_public_key(const PublicKey *in_public_key, uint8_t **out_bytes, int *out_len);
+bool serialize_signature(const Signature *in_signature, uint8_t **out_bytes, int *out_len);
+/* serialization.rs:236-266 */
+bool free_vec(uint8_t *bytes, int len);
+bool destroy_public_key(PublicKey *public_key);
+bool destroy_signature(Signature *signature);
+/* signatures.rs:428-451, 485-505: group sums (PublicKey::aggregate / Signature::aggregate).  The reference's
+ * aggregate_public_keys also consults a process-wide cache (cache.rs); the sum is the same. */
+bool aggregate_public_keys(const PublicKey *const *in_public_keys, int in_public_keys_len, PublicKey **out_public_key);
+bool aggregate_signatures(const Signature *const *in_signatures, int in_signatures_len, Signature **out_signature);
+/* signatures.rs:244-276: PublicKey::verify over SIG_DOMAIN with the selected hash-to-G1:
+ * (composite, cip22) = (true, true) COMPOSITE_HASH_TO_G1_CIP22, (true, false) COMPOSITE_HASH_TO_G1,
+ * (false, false) DIRECT_HASH_TO_G1, (false, true) an error (returns false). */
+bool verify_signature(const PublicKey *in_public_key, const uint8_t *in_message, int in_message_len, const uint8_t *in_extra_data,
+                      int in_extra_data_len, const Signature *in_signature, bool should_use_composite, bool should_use_cip22,
+                      bool *out_verified);
+/* signatures.rs:407-425: PublicKey::verify_pop (POP_DOMAIN, DIRECT_HASH_TO_G1, no extra data). */
+bool verify_pop(const PublicKey *in_public_key, const uint8_t *in_message, int in_message_len, const Signature *in_signature,
+                bool *out_verified);
+/* signatures.rs:290-333: aggregates the messages' signatures and runs Signature::batch_verify --
+ * e(asig, -g2) * prod e(H(data_i, extra_i), pk_i) == 1; all messages are hashed in one launch. */
+bool batch_verify_signature(const MessageFFI *messages_ptr, size_t messages_len, bool should_use_composite, bool should_use_cip22,
+                            bool *verified);
+/* signatures.rs:343-404: per batch Batch::verify (crates/bls-crypto/src/bls/batch.rs:44-84) with fresh random exponents
+ * of byte_count_from_target_batch_size bytes; out_results[i] per batch; returns false unless every batch verified. */
+bool batch_verify_strict(const BatchMessageFFI *in_batches_ptr, size_t in_batches_len, bool should_use_composite, bool should_use_cip22,
+                         bool *out_results);
+
 #ifdef __cplusplus
 }
 #endif
