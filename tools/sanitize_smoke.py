@@ -47,6 +47,27 @@ def main():
         E.ntt_device(f.id, d.data_ptr(), 11, False, True)
         E.sync()
         assert np.array_equal(d.cpu().numpy().view(np.uint64).reshape(-1, f.limbs), f.to_mont_array(N.coset_fft(f, a)))
+    # hash-to-G1 (both hashers, CIP22, ragged inputs) and the bls-snark-sys signature entry points on top of it
+    import ctypes
+    from oracle import hash_to_curve as HC
+    G1L = C.LAYOUTS["bls12_377_g1"]
+    inputs = [(b"", b""), (b"m" * 40, b"x"), (bytes(range(200)), b"extra data")]
+    for hasher, oh, cip22 in ((E.HASHER_DIRECT, HC.DIRECT, False), (E.HASHER_COMPOSITE, HC.COMPOSITE, False),
+                              (E.HASHER_COMPOSITE, HC.COMPOSITE, True)):
+        images, att = E.hash_to_g1(hasher, b"ULforxof", inputs, cip22=cip22)
+        for (m, e), img, a in zip(inputs, images, att):
+            pt, c = HC.try_and_increment(O.G1, oh, b"ULforxof", m, e, compat=True, cip22=cip22)
+            assert G1L.jacobian_compressed(img) == O.serialize_compressed(O.G1, pt) and a == c
+    lib = E.load()
+    sk, msg = 0xC0FFEE1234567, b"sanitizer"
+    pk, sg, ok = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_bool(False)
+    hpt, _ = HC.try_and_increment(O.G1, HC.COMPOSITE, b"ULforxof", msg, b"", compat=True, cip22=True)
+    pkb, sgb = O.serialize_compressed(O.G2, O.G2.pmul(O.G2_GEN, sk)), O.serialize_compressed(O.G1, O.G1.pmul(hpt, sk))
+    assert lib.deserialize_public_key(pkb, 96, ctypes.byref(pk)) and lib.deserialize_signature(sgb, 48, ctypes.byref(sg))
+    assert lib.verify_signature(pk, msg, len(msg), b"", 0, sg, True, True, ctypes.byref(ok)) and ok.value
+    ptr, n = ctypes.c_void_p(), ctypes.c_int()
+    assert lib.serialize_signature(sg, ctypes.byref(ptr), ctypes.byref(n)) and ctypes.string_at(ptr, n.value) == sgb
+    assert lib.free_vec(ptr, n.value) and lib.destroy_public_key(pk) and lib.destroy_signature(sg)
     print("sanitize smoke ok; launches =", E.launch_count())
     E.shutdown()
 
