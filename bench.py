@@ -87,15 +87,24 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self, wait_s: float = 8.0):
+        """Start of the timed region: waits for nvidia-smi's first row (its start-up can outlast a short timed
+        region on a cold box) and remembers where the region's samples begin."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < wait_s:
+            time.sleep(0.02)
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[getattr(self, "first", 0):] or self.rows      # samples taken during the timed region
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -224,6 +233,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     steps(args.warmup)
     barrier()
     # the same MSM one call at a time (no overlap between consecutive MSMs), for reference
@@ -236,9 +248,8 @@ def run_b200(args):
     barrier()
     seq_ms = s0.elapsed_time(s1) / seq_steps
     E.profile_enable(True)
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     launches0 = E.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

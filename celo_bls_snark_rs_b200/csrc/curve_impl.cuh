@@ -236,7 +236,7 @@ template <class C>
 int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
     using F = typename C::F;
     if (n == 0) {
-        k_sum_jacobian<F><<<1, 1, 0, st>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(d_out));
+        k_sum_jacobian<F><<<1, SUM_THREADS, 0, st>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(d_out));
         LAUNCH_CHECK();
         return B200_OK;
     }
@@ -281,7 +281,7 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
     size_t k = 0;
     for (size_t i = 0; i < count; i++) {
         if (jobs[i].n == 0) {
-            k_sum_jacobian<F><<<1, 1, 0, s_tail>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(jobs[i].d_out_jacobian));
+            k_sum_jacobian<F><<<1, SUM_THREADS, 0, s_tail>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(jobs[i].d_out_jacobian));
             LAUNCH_CHECK();
             continue;
         }
@@ -324,7 +324,7 @@ int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scal
 template <class C>
 int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st) {
     using F = typename C::F;
-    k_sum_jacobian<F><<<1, 1, 0, st>>>(reinterpret_cast<const JacobianMem<F> *>(pts), (uint32_t)count,
+    k_sum_jacobian<F><<<1, SUM_THREADS, 0, st>>>(reinterpret_cast<const JacobianMem<F> *>(pts), (uint32_t)count,
                                        reinterpret_cast<JacobianMem<F> *>(out));
     LAUNCH_CHECK();
     return B200_OK;

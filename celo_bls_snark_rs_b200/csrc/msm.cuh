@@ -676,17 +676,32 @@ __global__ void __launch_bounds__(THREADS) k_pack_bases(const uint32_t *__restri
     dst[i] = pt.store();
 }
 
-// out = sum of `count` Jacobian points in arkworks radix (multi-GPU partial combine; tiny)
+// out = sum of `count` Jacobian points in arkworks radix: the multi-GPU partial combine (a handful of points) and
+// Signature::aggregate / PublicKey::aggregate over a batch (thousands).  One block: every thread sums a strided
+// subset, a shared-memory tree folds the 128 partial sums (count / 128 + 7 dependent additions instead of count).
+constexpr int SUM_THREADS = 128;
 template <class F>
-__global__ void k_sum_jacobian(const JacobianMem<F> *__restrict__ pts, uint32_t count, JacobianMem<F> *__restrict__ out) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void __launch_bounds__(SUM_THREADS) k_sum_jacobian(const JacobianMem<F> *__restrict__ pts, uint32_t count,
+                                                              JacobianMem<F> *__restrict__ out) {
+    __shared__ JacobianMem<F> part[SUM_THREADS];
+    const int t = threadIdx.x;
     Jacobian<F> total = Jacobian<F>::inf();
     launder(total);
-    for (uint32_t i = 0; i < count; i++) {
+    for (uint32_t i = t; i < count; i += SUM_THREADS) {
         total.add(Jacobian<F>::from_ark(pts[i]));
         launder(total);
     }
-    *out = total.to_ark();
+    part[t] = total.to_ark();
+    __syncthreads();
+    for (int off = SUM_THREADS / 2; off >= 1; off >>= 1) {
+        if (t < off && (uint32_t)(t + off) < count) {      // partial sums beyond `count` are the identity
+            total.add(Jacobian<F>::from_ark(part[t + off]));
+            launder(total);
+            part[t] = total.to_ark();
+        }
+        __syncthreads();
+    }
+    if (t == 0) *out = total.to_ark();
 }
 
 // out[i] = scalars[i] * base (double-and-add); synthesises benchmark / test bases on device
