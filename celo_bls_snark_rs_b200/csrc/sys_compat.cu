@@ -124,9 +124,63 @@ bool verify_one(const char *fn, const void *pk, const uint8_t *domain, const uin
     return true;
 }
 
+// ---- compress_signature / compress_pubkey: byte and integer work only (no field products), done on the host ----
+// BLS12-377 Fq modulus, little-endian 32-bit words
+const uint32_t FQ_MODULUS[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu,
+                                 0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
+void load_words(const uint8_t *le48, uint32_t w[12]) {
+    for (int i = 0; i < 12; i++) w[i] = (uint32_t)le48[4 * i] | ((uint32_t)le48[4 * i + 1] << 8) | ((uint32_t)le48[4 * i + 2] << 16) | ((uint32_t)le48[4 * i + 3] << 24);
+}
+bool words_less(const uint32_t a[12], const uint32_t b[12]) {
+    for (int i = 11; i >= 0; i--)
+        if (a[i] != b[i]) return a[i] < b[i];
+    return false;
+}
+bool coord_valid(const uint8_t *le48) {                  // Fq::read: canonical integer below the modulus
+    uint32_t w[12];
+    load_words(le48, w);
+    return words_less(w, FQ_MODULUS);
+}
+bool coord_is_zero(const uint8_t *le48) {
+    for (int i = 0; i < 48; i++)
+        if (le48[i]) return false;
+    return true;
+}
+bool coord_over_half(const uint8_t *le48) {              // y > -y  <=>  y > (p - 1) / 2
+    uint32_t w[12], half[12];
+    load_words(le48, w);
+    for (int i = 0; i < 12; i++) half[i] = (FQ_MODULUS[i] >> 1) | (i < 11 ? FQ_MODULUS[i + 1] << 31 : 0u);   // p odd: (p - 1) / 2 = p >> 1
+    return words_less(half, w);
+}
+bool compress_bytes(const char *fn, const uint8_t *in, int len, size_t coords, uint8_t **out, int *out_len) {
+    if (!in || !out || !out_len) return failed(fn, "null pointer");
+    const size_t enc = 48 * coords;
+    if (len < (int)(2 * enc)) return failed(fn, "not enough bytes");
+    for (size_t k = 0; k < 2 * coords; k++)
+        if (!coord_valid(in + 48 * k)) return failed(fn, "coordinate not below the modulus");
+    uint8_t *buf = (uint8_t *)malloc(enc);
+    if (!buf) return failed(fn, "out of memory");
+    memcpy(buf, in, enc);                                 // x, little endian (Fq2: c0 | c1)
+    const uint8_t *y = in + enc;
+    // Fq2 ordering compares c1 first, then c0 (crates/epoch-snark/src/encoding.rs:31-33)
+    const bool larger = coords == 2 && !coord_is_zero(y + 48) ? coord_over_half(y + 48) : coord_over_half(y);
+    if (larger) buf[enc - 1] |= 0x80;
+    *out = buf;
+    *out_len = (int)enc;
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
+
+// serialization.rs:166-215: uncompressed x | y (canonical little-endian coordinates) -> the compressed encoding
+bool compress_signature(const uint8_t *in_signature, int in_signature_len, uint8_t **out_signature, int *out_len) {
+    return compress_bytes("compress_signature", in_signature, in_signature_len, 1, out_signature, out_len);
+}
+bool compress_pubkey(const uint8_t *in_pubkey, int in_pubkey_len, uint8_t **out_pubkey, int *out_len) {
+    return compress_bytes("compress_pubkey", in_pubkey, in_pubkey_len, 2, out_pubkey, out_len);
+}
 
 bool deserialize_public_key(const uint8_t *in_public_key_bytes, int in_public_key_bytes_len, PublicKey **out_public_key) {
     return deserialize_point("deserialize_public_key", B200_POINTS_BLS12_377_G2, 96, in_public_key_bytes, in_public_key_bytes_len,

@@ -40,7 +40,8 @@ EXPORTS = [
 # the reference's own symbols re-exported by the library (include/bls_snark_sys_compat.h)
 COMPAT_EXPORTS = ["verify", "deserialize_public_key", "deserialize_signature", "serialize_public_key", "serialize_signature",
                   "free_vec", "destroy_public_key", "destroy_signature", "aggregate_public_keys", "aggregate_signatures",
-                  "verify_signature", "verify_pop", "batch_verify_signature", "batch_verify_strict"]
+                  "verify_signature", "verify_pop", "batch_verify_signature", "batch_verify_strict", "compress_signature",
+                  "compress_pubkey"]
 
 
 class Groth16Pk(ctypes.Structure):
@@ -145,6 +146,7 @@ def load() -> ctypes.CDLL:
     cb, pp, pb, ci = ctypes.c_bool, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_bool), ctypes.c_int
     for name, args in (("deserialize_public_key", [vp, ci, pp]), ("deserialize_signature", [vp, ci, pp]),
                        ("serialize_public_key", [vp, pp, ctypes.POINTER(ci)]), ("serialize_signature", [vp, pp, ctypes.POINTER(ci)]),
+                       ("compress_signature", [vp, ci, pp, ctypes.POINTER(ci)]), ("compress_pubkey", [vp, ci, pp, ctypes.POINTER(ci)]),
                        ("free_vec", [vp, ci]), ("destroy_public_key", [vp]), ("destroy_signature", [vp]),
                        ("aggregate_public_keys", [pp, ci, pp]), ("aggregate_signatures", [pp, ci, pp]),
                        ("verify_signature", [vp, vp, ci, vp, ci, vp, cb, cb, pb]), ("verify_pop", [vp, vp, ci, vp, pb]),

@@ -77,6 +77,10 @@ bool deserialize_signature(const uint8_t *in_signature_bytes, int in_signature_b
 /* serialization.rs:63-70, 90-97: into_affine().serialize() -> a new 96 / 48-byte buffer (free_vec). */
 bool serialize_public_key(const PublicKey *in_public_key, uint8_t **out_bytes, int *out_len);
 bool serialize_signature(const Signature *in_signature, uint8_t **out_bytes, int *out_len);
+/* serialization.rs:166-215: uncompressed x | y (96 / 192 bytes, canonical little-endian coordinates) -> the
+ * compressed encoding (48 / 96 bytes, free_vec).  Integer comparisons only; runs on the host. */
+bool compress_signature(const uint8_t *in_signature, int in_signature_len, uint8_t **out_signature, int *out_len);
+bool compress_pubkey(const uint8_t *in_pubkey, int in_pubkey_len, uint8_t **out_pubkey, int *out_len);
 /* serialization.rs:236-266 */
 bool free_vec(uint8_t *bytes, int len);
 bool destroy_public_key(PublicKey *public_key);

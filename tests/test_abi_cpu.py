@@ -57,6 +57,28 @@ def test_product_never_imports_the_oracle():
     assert "cpu_ref" not in out
 
 
+def test_compress_entry_points_on_host():
+    """compress_signature / compress_pubkey (crates/bls-snark-sys/src/serialization.rs:166-215) are integer work done
+    on the host: uncompressed oracle encodings in, the oracle's compressed encodings out."""
+    import ctypes
+    from oracle import oracle as O
+    lib = E.load()
+    rng = O.SplitMix64(12)
+    for curve, gen, fn, size in ((O.G1, O.G1_GEN, "compress_signature", 48), (O.G2, O.G2_GEN, "compress_pubkey", 96)):
+        for _ in range(6):
+            pt = curve.pmul(gen, rng.below(O.R - 1) + 1)
+            for p in (pt, curve.pneg(pt)):
+                raw = O.serialize_uncompressed(curve, p)
+                ptr, n = ctypes.c_void_p(), ctypes.c_int()
+                assert getattr(lib, fn)(raw, len(raw), ctypes.byref(ptr), ctypes.byref(n)) and n.value == size
+                assert ctypes.string_at(ptr, n.value) == O.serialize_compressed(curve, p)
+                assert lib.free_vec(ptr, n.value)
+        ptr, n = ctypes.c_void_p(), ctypes.c_int()
+        bad = (O.P).to_bytes(48, "little") * (2 * size // 48)          # coordinate == modulus: Fq::read fails
+        assert not getattr(lib, fn)(bad, len(bad), ctypes.byref(ptr), ctypes.byref(n))
+        assert not getattr(lib, fn)(b"\0" * (2 * size - 1), 2 * size - 1, ctypes.byref(ptr), ctypes.byref(n))
+
+
 def test_plan_is_sane():
     c, w, nb = E.msm_plan(E.BLS12_377_G1, 1 << 20)
     assert nb == 1 << (c - 1) and w * c >= 254
