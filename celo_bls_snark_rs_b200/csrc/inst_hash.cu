@@ -320,6 +320,47 @@ enum : int { HASH_FLAG_COMPAT = 1, HASH_FLAG_CIP22 = 2, HASH_FLAG_CRH_ONLY = 4 }
 // cofactor of BLS12-377 G1, (x - 1)^2 / 3 = 0x170b5d44300000000000000000000000 (125 bits)
 static __device__ const uint32_t G1_COFACTOR[4] = {0x00000000u, 0x00000000u, 0x30000000u, 0x170b5d44u};
 
+// One counter of the try-and-increment loop on one lane: CRH (unless hashed once) -> XOF -> from_random_bytes ->
+// y from x.  Returns false when the reference would move on to the next counter before the cofactor step.
+__device__ __noinline__ bool try_counter(uint32_t c, bool cip22, bool composite, bool compat, const uint8_t *extra, uint32_t extra_len,
+                                         uint32_t body_len, const uint32_t *inner, const EdExt &rest, const EdTabMem *__restrict__ table,
+                                         const SqrtTables *__restrict__ sqrt_tables, uint32_t pers0, uint32_t pers1, HFq &x, HFq &y) {
+    const uint32_t HB = 64;                               // hash_length(48), hash_to_curve/mod.rs:19-23
+    const uint32_t inner_len = composite ? 48 : 32;
+    uint32_t crh[12];
+    ByteSrc xin;
+    if (cip22) {
+        xin = {1, (uint8_t)c, extra, extra_len, reinterpret_cast<const uint8_t *>(inner), inner_len};
+    } else {
+        if (composite) {
+            EdExt s = rest;
+            for (uint32_t k = 0; k < 3; k++) s = bh_add_chunk(s, k, 1, c, extra, body_len, table);
+            ed_x_bytes(s, crh);
+        } else {
+            ByteSrc src = {1, (uint8_t)c, extra, body_len, nullptr, 0};
+            blake2s_dev(crh, src, 0x01010020u, 0, 0, HB, pers0, pers1);
+        }
+        xin = {0, 0, reinterpret_cast<const uint8_t *>(crh), inner_len, nullptr, 0};
+    }
+    // XOF (direct.rs:41-79): two 32-byte blocks, fanout 0, depth 0, leaf 32, inner 32, node offset = block index
+    uint32_t h0[8], h1[8], w[12];
+    blake2s_dev(h0, xin, 32u, 32u, 0u, HB | (32u << 24), pers0, pers1);
+    blake2s_dev(h1, xin, 32u, 32u, 1u, HB | (32u << 24), pers0, pers1);
+    for (int k = 0; k < 8; k++) w[k] = h0[k];
+    for (int k = 0; k < 4; k++) w[8 + k] = h1[k];
+    // from_random_bytes: byte 47 carries the flags (bit 7 sign, bit 6 infinity); `compat` moves bit 1 into bit 7
+    const bool positive = compat ? (w[11] >> 25) & 1u : (w[11] >> 31) & 1u;
+    const bool infinity = (w[11] >> 30) & 1u;
+    w[11] &= 0x01ffffffu;
+    if (!fp_words_lt_modulus<HFq>(w)) return false;
+    x = fp_from_canonical<HFq>(w);
+    // (0, infinity flag) is the zero point, whose cofactor multiple is zero -> next counter
+    if (x.is_zero() && infinity) return false;
+    if (!fq377_sqrt_tab(x.sqr() * x + HFq::one(), &y, sqrt_tables)) return false;
+    if (fp_canonical_over_half(fp_to_canonical(y)) != positive) y = y.neg();
+    return true;
+}
+
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(32, MIN_BLOCKS) k_hash_to_g1(const uint8_t *__restrict__ data, const HashMsg *__restrict__ msgs, uint32_t n,
                                                    int hasher, int flags, uint32_t pers0, uint32_t pers1,
@@ -359,7 +400,6 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) k_hash_to_g1(const uint8_t *__
     }
     // The 32 lanes try 32 consecutive counters at once (a lone lane would cost the same issue slots); the lowest
     // successful counter wins, exactly as the sequential loop of the reference would find it.
-    const uint32_t inner_len = composite ? 48 : 32;
     const unsigned full = 0xffffffffu;
     if (composite && !cip22)
         rest = {rest.x.shfl(full, 0), rest.y.shfl(full, 0), rest.z.shfl(full, 0), rest.t.shfl(full, 0)};
@@ -370,41 +410,8 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) k_hash_to_g1(const uint8_t *__
         const uint32_t c = first + lane;
         bool ok = false;
         HFq x = HFq::zero(), y = HFq::zero();
-        if (c < 255) {
-            uint32_t crh[12];
-            ByteSrc xin;
-            if (cip22) {
-                xin = {1, (uint8_t)c, extra, hm.extra_len, reinterpret_cast<const uint8_t *>(inner), inner_len};
-            } else {
-                if (composite) {
-                    EdExt s = rest;
-                    for (uint32_t k = 0; k < 3; k++) s = bh_add_chunk(s, k, 1, c, extra, body_len, table);
-                    ed_x_bytes(s, crh);
-                } else {
-                    ByteSrc src = {1, (uint8_t)c, extra, body_len, nullptr, 0};
-                    blake2s_dev(crh, src, 0x01010020u, 0, 0, HB, pers0, pers1);
-                }
-                xin = {0, 0, reinterpret_cast<const uint8_t *>(crh), inner_len, nullptr, 0};
-            }
-            // XOF (direct.rs:41-79): two 32-byte blocks, fanout 0, depth 0, leaf 32, inner 32, node offset = block index
-            uint32_t h0[8], h1[8], w[12];
-            blake2s_dev(h0, xin, 32u, 32u, 0u, HB | (32u << 24), pers0, pers1);
-            blake2s_dev(h1, xin, 32u, 32u, 1u, HB | (32u << 24), pers0, pers1);
-            for (int k = 0; k < 8; k++) w[k] = h0[k];
-            for (int k = 0; k < 4; k++) w[8 + k] = h1[k];
-            // from_random_bytes: byte 47 carries the flags (bit 7 sign, bit 6 infinity); `compat` moves bit 1 into bit 7
-            const bool positive = compat ? (w[11] >> 25) & 1u : (w[11] >> 31) & 1u;
-            const bool infinity = (w[11] >> 30) & 1u;
-            w[11] &= 0x01ffffffu;
-            if (fp_words_lt_modulus<HFq>(w)) {
-                x = fp_from_canonical<HFq>(w);
-                // (0, infinity flag) is the zero point, whose cofactor multiple is zero -> next counter
-                if (!(x.is_zero() && infinity) && fq377_sqrt_tab(x.sqr() * x + HFq::one(), &y, sqrt_tables)) {
-                    if (fp_canonical_over_half(fp_to_canonical(y)) != positive) y = y.neg();
-                    ok = true;
-                }
-            }
-        }
+        if (c < 255)
+            ok = try_counter(c, cip22, composite, compat, extra, hm.extra_len, body_len, inner, rest, table, sqrt_tables, pers0, pers1, x, y);
         unsigned winners = __ballot_sync(full, ok);
 #pragma unroll 1
         while (winners && !done) {
@@ -427,6 +434,123 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) k_hash_to_g1(const uint8_t *__
         }
     }
     if (!done && lane == 0) attempts[i] = HASH_FAILED;
+}
+
+// The same loop for large batches, in two launches.
+//  * k_hash_prepare: one warp per message computes the counter-independent part of the CRH (the Bowe-Hopwood sum of
+//    chunks 3.. or, for CIP22, the inner hash) into global memory -- a table walk that wants every warp it can get.
+//  * k_hash_to_g1_packed<PACK>: PACK messages per warp.  A group of 32 / PACK lanes owns one message and tries that
+//    many counters per round; once every message of the warp has a candidate point the groups run the cofactor
+//    multiplication side by side (quad-cooperative steps, each quad on its group's point).  Per message this is
+//    1 / PACK of a warp's square-root rounds and cofactor multiplications instead of one each, at a longer latency
+//    for a single message (so small batches keep k_hash_to_g1).
+struct alignas(16) HashPrep {
+    uint32_t inner[12];                                   // CIP22: the CRH of the message
+    EdExtMem rest;                                        // composite, counter-dependent flow: chunks 3.. of the sum
+};
+__global__ void __launch_bounds__(32) k_hash_prepare(const uint8_t *__restrict__ data, const HashMsg *__restrict__ msgs, uint32_t n,
+                                                     int hasher, int flags, uint32_t pers0, uint32_t pers1,
+                                                     const EdTabMem *__restrict__ table, HashPrep *__restrict__ prep) {
+    const uint32_t i = blockIdx.x;
+    const int lane = threadIdx.x;
+    if (i >= n) return;
+    const bool cip22 = flags & HASH_FLAG_CIP22, composite = hasher == HASHER_COMPOSITE;
+    const HashMsg hm = msgs[i];
+    const uint8_t *extra = data + hm.off, *message = extra + hm.extra_len;
+    const uint32_t body_len = hm.extra_len + hm.msg_len;
+    const HFq d = ed_coeff_d();
+    if (composite) {
+        if (cip22) {
+            EdExt s = bh_warp_sum(0, (8 * hm.msg_len + 2) / 3, 0, message, hm.msg_len, table, d, lane);
+            if (lane == 0) ed_x_bytes(s, prep[i].inner);
+        } else {
+            EdExt r = bh_warp_sum(3, (8 * (body_len + 1) + 2) / 3, 1, extra, body_len, table, d, lane);
+            if (lane == 0) prep[i].rest = {r.x.store(), r.y.store(), r.z.store(), r.t.store()};
+        }
+    } else if (cip22 && lane == 0) {
+        ByteSrc src = {0, 0, message, hm.msg_len, nullptr, 0};
+        uint32_t h[8];
+        blake2s_dev(h, src, 0x01010020u, 0, 0, 64u, pers0, pers1);
+        for (int k = 0; k < 8; k++) prep[i].inner[k] = h[k];
+    }
+}
+
+template <int PACK>
+__global__ void __launch_bounds__(32) k_hash_to_g1_packed(const uint8_t *__restrict__ data, const HashMsg *__restrict__ msgs, uint32_t n,
+                                                          int hasher, int flags, uint32_t pers0, uint32_t pers1,
+                                                          const EdTabMem *__restrict__ table, const SqrtTables *__restrict__ sqrt_tables,
+                                                          const HashPrep *__restrict__ prep, JacobianMem<HFq> *__restrict__ out,
+                                                          uint32_t *__restrict__ attempts) {
+    constexpr int LPM = 32 / PACK;                        // lanes (= counters per round) per message
+    const int lane = threadIdx.x, slot = lane / LPM, q = lane % LPM, group = lane - q;
+    const bool cip22 = flags & HASH_FLAG_CIP22, compat = flags & HASH_FLAG_COMPAT, composite = hasher == HASHER_COMPOSITE;
+    const unsigned full = 0xffffffffu;
+    // group `slot` owns message i; next_c / have / finished are identical on its lanes
+    const uint32_t i = blockIdx.x * PACK + slot;
+    const bool live = i < n;
+    const HashMsg hm = live ? msgs[i] : HashMsg{0, 0, 0, 0};
+    const uint8_t *extra = data + hm.off;
+    const uint32_t body_len = hm.extra_len + hm.msg_len;
+    const HashPrep *mine_prep = prep + (live ? i : 0);
+    EdExt rest = ed_identity();
+    if (live && composite && !cip22)
+        rest = {HFq::load(mine_prep->rest.x), HFq::load(mine_prep->rest.y), HFq::load(mine_prep->rest.z), HFq::load(mine_prep->rest.t)};
+    const Quad Q;
+    const HFq one = HFq::one();
+    uint32_t next_c = 0, cand_c = 0;
+    bool have = false, finished = !live, failed = false;
+    HFq cx = HFq::zero(), cy = HFq::zero();
+#pragma unroll 1
+    for (;;) {
+#pragma unroll 1
+        for (;;) {                                        // rounds of LPM counters per message until each has a candidate
+            const bool need = !finished && !have;
+            if (!__any_sync(full, need)) break;
+            const uint32_t c = next_c + q;
+            bool ok = false;
+            HFq x = HFq::zero(), y = HFq::zero();
+            if (need && c < 255)                          // NUM_TRIES, try_and_increment.rs:26
+                ok = try_counter(c, cip22, composite, compat, extra, hm.extra_len, body_len, mine_prep->inner, rest, table, sqrt_tables, pers0,
+                                 pers1, x, y);
+            const unsigned mine = (__ballot_sync(full, ok) >> group) & ((1u << LPM) - 1u);
+            const int w = mine ? __ffs(mine) - 1 : 0;     // the lowest successful counter of the group
+            const HFq wx = x.shfl(full, group + w), wy = y.shfl(full, group + w);
+            if (need) {
+                if (mine) {
+                    cx = wx;
+                    cy = wy;
+                    cand_c = next_c + w;
+                    have = true;
+                } else {
+                    next_c += LPM;
+                    if (next_c >= 255) finished = failed = true;
+                }
+            }
+        }
+        if (!__any_sync(full, have)) break;
+        // scale_by_cofactor, every group on its own candidate (groups without one carry the identity and fall through)
+        const XYZZ<HFq> base = have ? XYZZ<HFq>{cx, cy, one, one} : XYZZ<HFq>::inf();
+        XYZZ<HFq> acc = base;
+#pragma unroll 1
+        for (int b = 123; b >= 0; b--) {
+            quad_dbl(Q, acc);
+            if ((G1_COFACTOR[b >> 5] >> (b & 31)) & 1u) quad_add(Q, acc, base);
+        }
+        if (have) {
+            have = false;
+            if (acc.is_inf()) {                           // scaled.is_zero(): the reference moves on to the next counter
+                next_c = cand_c + 1;
+                if (next_c >= 255) finished = failed = true;
+            } else {
+                if (q == 0) {
+                    out[i] = acc.to_jacobian().to_ark();
+                    attempts[i] = cand_c;
+                }
+                finished = true;
+            }
+        }
+    }
+    if (live && failed && q == 0) attempts[i] = HASH_FAILED;
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
@@ -559,8 +683,8 @@ int hash_to_g1(Engine &E, int hasher, int flags, const uint8_t *domain, size_t d
         E.sqrt_ready = true;
     }
     const size_t meta_off = (blob.size() + 15) & ~(size_t)15, out_off = meta_off + n * sizeof(HashMsg), att_off = out_off + n * 144,
-                 crh_off = att_off + ((n * 4 + 15) & ~(size_t)15);
-    if ((rc = E.hash_ws.reserve(crh_off + n * 48))) return rc;
+                 crh_off = att_off + ((n * 4 + 15) & ~(size_t)15), prep_off = crh_off + n * 48;
+    if ((rc = E.hash_ws.reserve(prep_off + n * sizeof(HashPrep)))) return rc;
     char *base = E.hash_ws.as<char>();
     uint8_t personal[8] = {0};
     if (domain_len) memcpy(personal, domain, domain_len);
@@ -577,7 +701,28 @@ int hash_to_g1(Engine &E, int hasher, int flags, const uint8_t *domain, size_t d
                                            E.sqrt_tables.as<SqrtTables>(), reinterpret_cast<JacobianMem<HFq> *>(base + out_off),
                                            reinterpret_cast<uint32_t *>(base + att_off), reinterpret_cast<uint32_t *>(base + crh_off));
     };
-    if (occ >= 16) launch(k_hash_to_g1<16>);
+    // large batches: 4 or 8 messages per warp (fewer field products per message); small ones: one message per warp,
+    // 32 counters at once (lowest latency).  B200_HASH_PACKED = 0 / 4 / 8 forces the choice.
+    static const int packed_env = getenv("B200_HASH_PACKED") ? atoi(getenv("B200_HASH_PACKED")) : -1;
+    const size_t wave = (size_t)E.sm_count * 8;           // resident warps of these kernels (register-limited)
+    const int pack = crh_only ? 0 : packed_env >= 0 ? packed_env : n > 4 * wave ? 8 : n > wave ? 4 : 0;
+    if (pack) {
+        HashPrep *d_prep = reinterpret_cast<HashPrep *>(base + prep_off);
+        const HashMsg *d_msgs = reinterpret_cast<const HashMsg *>(base + meta_off);
+        if (cip22 || composite) {
+            k_hash_prepare<<<(unsigned)n, 32, 0, st>>>(reinterpret_cast<const uint8_t *>(base), d_msgs, (uint32_t)n, hasher, flags, pers[0],
+                                                       pers[1], E.bh_table.as<EdTabMem>(), d_prep);
+            LAUNCH_CHECK();
+        }
+        auto launch_packed = [&](auto kernel, int per_warp) {
+            kernel<<<(unsigned)((n + per_warp - 1) / per_warp), 32, 0, st>>>(
+                reinterpret_cast<const uint8_t *>(base), d_msgs, (uint32_t)n, hasher, flags, pers[0], pers[1], E.bh_table.as<EdTabMem>(),
+                E.sqrt_tables.as<SqrtTables>(), d_prep, reinterpret_cast<JacobianMem<HFq> *>(base + out_off),
+                reinterpret_cast<uint32_t *>(base + att_off));
+        };
+        if (pack >= 8) launch_packed(k_hash_to_g1_packed<8>, 8);
+        else launch_packed(k_hash_to_g1_packed<4>, 4);
+    } else if (occ >= 16) launch(k_hash_to_g1<16>);
     else if (occ >= 12) launch(k_hash_to_g1<12>);
     else launch(k_hash_to_g1<8>);
     LAUNCH_CHECK();

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <random>
 #include <vector>
 
@@ -53,18 +54,27 @@ bool hasher_of(bool composite, bool cip22, int *hasher, int *flags) {
     return true;
 }
 
-// sum of Jacobian images on the device (PublicKey::aggregate / Signature::aggregate)
+// sum of Jacobian images on the device (PublicKey::aggregate / Signature::aggregate).  The staging buffer is a
+// process-lifetime, grow-only allocation: cudaMalloc / cudaFree per call cost more than the sum itself.
+std::mutex g_scratch_mu;
+void *g_scratch = nullptr;
+size_t g_scratch_cap = 0;
 bool sum_images(int curve, const std::vector<const void *> &images, size_t bytes, void *out) {
-    const size_t n = images.size();
+    const size_t n = images.size(), need = (n + 1) * bytes;
     std::vector<uint8_t> host(n * bytes + 16);
     for (size_t i = 0; i < n; i++) memcpy(&host[i * bytes], images[i], bytes);
-    void *d = nullptr;
-    if (cudaMalloc(&d, (n + 1) * bytes) != cudaSuccess) return false;
-    bool ok = cudaMemcpy(d, host.data(), n * bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
-              b200_sum_jacobian_device(curve, d, n, (char *)d + n * bytes, nullptr) == B200_OK && b200_sync(nullptr) == B200_OK &&
-              cudaMemcpy(out, (char *)d + n * bytes, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
-    cudaFree(d);
-    return ok;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (need > g_scratch_cap) {
+        if (g_scratch) cudaFree(g_scratch);
+        g_scratch = nullptr;
+        g_scratch_cap = 0;
+        if (cudaMalloc(&g_scratch, need + need / 2) != cudaSuccess) return false;
+        g_scratch_cap = need + need / 2;
+    }
+    char *d = (char *)g_scratch;
+    return cudaMemcpy(d, host.data(), n * bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+           b200_sum_jacobian_device(curve, d, n, d + n * bytes, nullptr) == B200_OK && b200_sync(nullptr) == B200_OK &&
+           cudaMemcpy(out, d + n * bytes, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
 }
 
 // ark_std::log2: ceil(log2(x)), 0 for x <= 1
