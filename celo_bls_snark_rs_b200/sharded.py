@@ -104,3 +104,45 @@ class ShardedPairing:
             vals = self.gathered
         E.final_exp_device(vals.data_ptr(), self.world, self.gt.data_ptr(), self.is_one.data_ptr(), stream)
         return self.gt, self.is_one
+
+
+def gather_ragged(local: torch.Tensor, n: int, record_bytes: int, group=None) -> torch.Tensor:
+    """All-gather of per-rank slices of `n` fixed-size records split by shard_bounds (slice lengths differ by at
+    most one record): every rank pads its slice to the longest one, the padded blocks are all-gathered rank-major and
+    the padding is dropped -> uint8 [n * record_bytes] in record order on every rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    longest = -(-n // world) if n else 0
+    lo, hi = shard_bounds(n, world, rank)
+    assert local.numel() == (hi - lo) * record_bytes
+    block = torch.zeros(max(longest, 1) * record_bytes, dtype=torch.uint8, device=local.device)
+    block[:local.numel()] = local
+    out = torch.empty(world * block.numel(), dtype=torch.uint8, device=local.device)
+    dist.all_gather_into_tensor(out, block, group=group)
+    parts = []
+    for r in range(world):
+        rlo, rhi = shard_bounds(n, world, r)
+        parts.append(out[r * block.numel(): r * block.numel() + (rhi - rlo) * record_bytes])
+    return torch.cat(parts) if parts else out[:0]
+
+
+class ShardedHashToG1:
+    """Message hashing of a batch split over the ranks (independent units, no data-path
+    collective inside the hot loop): rank r hashes messages shard_bounds(n, world, r) with b200_hash_to_g1 and the
+    144-byte results are all-gathered so that every rank holds all n hash points, in message order, for its share
+    of the pairing product (ShardedPairing).  `hash_fn(hasher, domain, inputs, compat, cip22) -> (images, attempts)`
+    defaults to the CUDA engine; the gloo CPU test passes the oracle in its place."""
+
+    def __init__(self, hasher: int, cip22: bool = False, compat: bool = True, device=None, group=None, hash_fn=None):
+        self.hasher, self.cip22, self.compat, self.group = hasher, cip22, compat, group
+        self.device = device if device is not None else torch.device("cpu")
+        self.hash_fn = hash_fn if hash_fn is not None else E.hash_to_g1
+
+    def run(self, domain: bytes, inputs):
+        n = len(inputs)
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lo, hi = shard_bounds(n, world, rank)
+        images, _ = self.hash_fn(self.hasher, domain, list(inputs[lo:hi]), compat=self.compat, cip22=self.cip22)
+        local = torch.frombuffer(bytearray(b"".join(images)), dtype=torch.uint8).to(self.device) if images else \
+            torch.zeros(0, dtype=torch.uint8, device=self.device)
+        flat = gather_ragged(local, n, 144, self.group).cpu().numpy().tobytes()
+        return [flat[144 * i:144 * (i + 1)] for i in range(n)]

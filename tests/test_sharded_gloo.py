@@ -113,3 +113,53 @@ def test_two_rank_gloo_sharded_pairing_product_is_exact():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got == {0: True, 1: True}
+
+
+def _oracle_hash_fn(hasher, domain, inputs, compat=True, cip22=False):
+    """Stands in for engine.hash_to_g1 on CPU: the oracle's hash points as G1Projective images (z = 1)."""
+    from oracle import hash_to_curve as HC
+    L = C.LAYOUTS["bls12_377_g1"]
+    images, attempts = [], []
+    for m, e in inputs:
+        pt, c = HC.try_and_increment(O.G1, HC.DIRECT, domain, m, e, compat=compat, cip22=cip22)
+        images.append(L.fe_to_mont_bytes(pt[0]) + L.fe_to_mont_bytes(pt[1]) + L.fe_to_mont_bytes(1))
+        attempts.append(c)
+    return images, attempts
+
+
+def _hash_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        inputs = [(bytes([i, 7 * i % 251]) * (1 + i % 5), bytes([i]) * (i % 3)) for i in range(n)]
+        job = sharded.ShardedHashToG1(0, hash_fn=_oracle_hash_fn)
+        q.put((rank, job.run(b"ULforxof", inputs)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_ragged_layout_single_process():
+    # world = 1 degenerates to a copy; the ragged arithmetic itself is covered by the two-rank run below
+    for n, world in ((0, 2), (1, 2), (5, 2), (7, 3), (8, 8)):
+        spans = [sharded.shard_bounds(n, world, r) for r in range(world)]
+        assert sum(hi - lo for lo, hi in spans) == n and max(hi - lo for lo, hi in spans) == (-(-n // world) if n else 0)
+
+
+def test_two_rank_gloo_sharded_hash_to_g1_is_in_message_order():
+    """ShardedHashToG1 on CPU: 7 messages over 2 ranks (slices of 4 and 3, so the gather is ragged); every rank ends
+    with all 7 hash points in message order, equal to hashing the batch in one piece."""
+    n, world = 7, 2
+    inputs = [(bytes([i, 7 * i % 251]) * (1 + i % 5), bytes([i]) * (i % 3)) for i in range(n)]
+    want, _ = _oracle_hash_fn(0, b"ULforxof", inputs)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hash_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == want and got[1] == want
