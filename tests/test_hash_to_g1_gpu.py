@@ -135,6 +135,18 @@ def test_batch_of_4096_messages(eng):
         assert [att[i] for i in idx] == want_att
 
 
+def test_batch_beyond_four_waves_uses_eight_messages_per_warp(eng):
+    """n > 4 * 148 * 8 messages select k_hash_to_g1_packed<8> (inst_hash.cu, host dispatch); same checks as above."""
+    n = 4 * 148 * 8 + 300
+    inputs = _inputs(91, n, 48)
+    a, att = eng.hash_to_g1(eng.HASHER_DIRECT, b"ULforxof", inputs)
+    assert all(0 <= c < 255 for c in att)
+    idx = list(range(0, n, 211))
+    want, want_att = _oracle(H.DIRECT, b"ULforxof", [inputs[i] for i in idx], True, False)
+    assert [L1.jacobian_compressed(a[i]) for i in idx] == want
+    assert [att[i] for i in idx] == want_att
+
+
 def test_verify_and_batch_verify_with_raw_messages():
     """public.rs:70-120 / signature.rs:101-117 (test_batch_verify, signature.rs:232-326): the messages are hashed on
     the device, the signatures made by the oracle from the oracle's own hash points."""
