@@ -184,3 +184,165 @@ int cpu_ref_fq_mul(int nl, const uint64_t *a_, const uint64_t *b_, uint64_t *out
     if (nl == 12) { fq761_t a, b; memcpy(&a, a_, sizeof a); memcpy(&b, b_, sizeof b); fq761_mul(&a, &a, &b); memcpy(out, &a, sizeof a); return 0; }
     return -1;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * DIRECT_HASH_TO_G1 in C (test infrastructure; the CPU figure next to the GPU one in tools/bench_hash.py):
+ * crates/bls-crypto/src/hashers/direct.rs:20-80 (Blake2s CRH, Blake2Xs-style XOF),
+ * crates/bls-crypto/src/hash_to_curve/try_and_increment.rs:84-139 (counter | extra | message, `compat` rule),
+ * hash_to_curve/mod.rs:146-156 (from_random_bytes), Tonelli-Shanks square root (2-adicity 46, as ark-ff),
+ * scale_by_cofactor by double-and-add.  Checked against oracle/hash_to_curve.py in tests/test_oracle_cref.py.
+ * ------------------------------------------------------------------------------------------------ */
+static const uint32_t B2S_IV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au, 0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+static const uint8_t B2S_SIGMA[10][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
+static inline uint32_t b2s_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static void b2s_compress(uint32_t h[8], const uint8_t block[64], uint64_t t, int last) {
+    uint32_t m[16], v[16];
+    for (int i = 0; i < 16; i++) memcpy(&m[i], block + 4 * i, 4);
+    for (int i = 0; i < 8; i++) { v[i] = h[i]; v[8 + i] = B2S_IV[i]; }
+    v[12] ^= (uint32_t)t;
+    v[13] ^= (uint32_t)(t >> 32);
+    if (last) v[14] = ~v[14];
+#define B2S_G(a, b, c, d, x, y) \
+    v[a] += v[b] + (x); v[d] = b2s_rotr(v[d] ^ v[a], 16); v[c] += v[d]; v[b] = b2s_rotr(v[b] ^ v[c], 12); \
+    v[a] += v[b] + (y); v[d] = b2s_rotr(v[d] ^ v[a], 8); v[c] += v[d]; v[b] = b2s_rotr(v[b] ^ v[c], 7);
+    for (int r = 0; r < 10; r++) {
+        const uint8_t *s = B2S_SIGMA[r];
+        B2S_G(0, 4, 8, 12, m[s[0]], m[s[1]]) B2S_G(1, 5, 9, 13, m[s[2]], m[s[3]])
+        B2S_G(2, 6, 10, 14, m[s[4]], m[s[5]]) B2S_G(3, 7, 11, 15, m[s[6]], m[s[7]])
+        B2S_G(0, 5, 10, 15, m[s[8]], m[s[9]]) B2S_G(1, 6, 11, 12, m[s[10]], m[s[11]])
+        B2S_G(2, 7, 8, 13, m[s[12]], m[s[13]]) B2S_G(3, 4, 9, 14, m[s[14]], m[s[15]])
+    }
+#undef B2S_G
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[8 + i];
+}
+/* unkeyed Blake2s over up to three concatenated segments; p[0..3] = first four parameter words */
+static void b2s_hash(uint8_t out[32], const uint32_t p[4], const uint8_t personal[8], const uint8_t *seg[3], const size_t seglen[3]) {
+    uint32_t h[8];
+    for (int i = 0; i < 8; i++) h[i] = B2S_IV[i];
+    h[0] ^= p[0]; h[1] ^= p[1]; h[2] ^= p[2]; h[3] ^= p[3];
+    uint32_t pw[2];
+    memcpy(pw, personal, 8);
+    h[6] ^= pw[0]; h[7] ^= pw[1];
+    uint8_t block[64];
+    size_t fill = 0;
+    uint64_t total = 0;
+    for (int s = 0; s < 3; s++)
+        for (size_t i = 0; i < seglen[s]; i++) {
+            if (fill == 64) { total += 64; b2s_compress(h, block, total, 0); fill = 0; }
+            block[fill++] = seg[s][i];
+        }
+    total += fill;
+    memset(block + fill, 0, 64 - fill);
+    b2s_compress(h, block, total, 1);
+    memcpy(out, h, 32);
+}
+
+static fq377_t g_ts_root;                         /* (-5)^t, t = (p - 1) / 2^46: a primitive 2^46-th root of unity */
+static uint64_t g_ts_t[6], g_ts_half_t[6];        /* t and (t - 1) / 2 */
+static int g_ts_inited;
+static void fq377_pow_limbs(fq377_t *r, const fq377_t *a, const uint64_t *e) {
+    fq377_t acc = fq377_R1;
+    for (int i = 64 * 6 - 1; i >= 0; i--) {
+        fq377_sqr(&acc, &acc);
+        if ((e[i / 64] >> (i % 64)) & 1) fq377_mul(&acc, &acc, a);
+    }
+    *r = acc;
+}
+static void ts_init(void) {
+    if (g_ts_inited) return;
+    ensure_init();
+    uint64_t pm1[6];
+    memcpy(pm1, MOD377, sizeof pm1);
+    pm1[0] -= 1;
+    for (int i = 0; i < 6; i++) g_ts_t[i] = (pm1[i] >> 46) | (i < 5 ? pm1[i + 1] << 18 : 0);
+    for (int i = 0; i < 6; i++) g_ts_half_t[i] = (g_ts_t[i] >> 1) | (i < 5 ? g_ts_t[i + 1] << 63 : 0);   /* t odd */
+    fq377_t five, m5;
+    memset(&five, 0, sizeof five);
+    five.l[0] = 5;
+    fq377_to_mont(&five, &five);
+    fq377_neg(&m5, &five);
+    fq377_pow_limbs(&g_ts_root, &m5, g_ts_t);
+    g_ts_inited = 1;
+}
+static int fq377_sqrt(fq377_t *out, const fq377_t *a) {
+    if (fq377_is_zero(a)) { *out = *a; return 1; }
+    fq377_t z, x, b, g = g_ts_root, one = fq377_R1;
+    fq377_pow_limbs(&z, a, g_ts_half_t);
+    fq377_mul(&x, a, &z);
+    fq377_mul(&b, &x, &z);
+    int v = 46;
+    while (!fq377_eq(&b, &one)) {
+        int k = 0;
+        fq377_t b2 = b;
+        while (!fq377_eq(&b2, &one) && k < v) { fq377_sqr(&b2, &b2); k++; }
+        if (k >= v) return 0;
+        fq377_t w = g;
+        for (int i = 0; i < v - k - 1; i++) fq377_sqr(&w, &w);
+        fq377_sqr(&g, &w);
+        fq377_mul(&x, &x, &w);
+        fq377_mul(&b, &b, &g);
+        v = k;
+    }
+    *out = x;
+    return 1;
+}
+static int fq377_over_half(const fq377_t *a_mont) {       /* canonical a > (p - 1) / 2 */
+    fq377_t c;
+    fq377_from_mont(&c, a_mont);
+    for (int i = 5; i >= 0; i--) {
+        const uint64_t half = (MOD377[i] >> 1) | (i < 5 ? MOD377[i + 1] << 63 : 0);
+        if (c.l[i] != half) return c.l[i] > half;
+    }
+    return 0;
+}
+
+int cpu_ref_hash_to_g1_direct(const uint8_t *domain8, const uint8_t *msg, size_t msg_len, const uint8_t *extra, size_t extra_len,
+                              int compat, void *out_jac, uint32_t *out_attempt) {
+    ts_init();
+    static const uint64_t COFACTOR[4] = {0, 0x170b5d4430000000ull, 0, 0};
+    const uint32_t HB = 64;
+    for (uint32_t c = 0; c < 255; c++) {
+        const uint8_t counter = (uint8_t)c;
+        uint8_t crh[32], x0[32], x1[32], cand[48];
+        const uint8_t *seg[3] = {&counter, extra, msg};
+        const size_t len[3] = {1, extra_len, msg_len};
+        const uint32_t pc[4] = {0x01010020u, 0, 0, HB};
+        b2s_hash(crh, pc, domain8, seg, len);
+        const uint8_t *xs[3] = {crh, crh, crh};
+        const size_t xl[3] = {32, 0, 0};
+        const uint32_t p0[4] = {32u, 32u, 0u, HB | (32u << 24)}, p1[4] = {32u, 32u, 1u, HB | (32u << 24)};
+        b2s_hash(x0, p0, domain8, xs, xl);
+        b2s_hash(x1, p1, domain8, xs, xl);
+        memcpy(cand, x0, 32);
+        memcpy(cand + 32, x1, 16);
+        const int positive = compat ? (cand[47] >> 1) & 1 : (cand[47] >> 7) & 1;
+        const int infinity = (cand[47] >> 6) & 1;
+        cand[47] &= 0x01;
+        fq377_t x, y, rhs;
+        memcpy(x.l, cand, 48);
+        if (fq377_geq_mod(x.l)) continue;
+        if (fq377_is_zero(&x) && infinity) continue;
+        fq377_to_mont(&x, &x);
+        fq377_sqr(&rhs, &x);
+        fq377_mul(&rhs, &rhs, &x);
+        fq377_add(&rhs, &rhs, &fq377_R1);
+        if (!fq377_sqrt(&y, &rhs)) continue;
+        if (fq377_over_half(&y) != positive) fq377_neg(&y, &y);
+        g1_377_aff a;
+        memset(&a, 0, sizeof a);
+        a.x = x;
+        a.y = y;
+        g1_377_jac r;
+        g1_377_scalar_mul(&r, &a, COFACTOR);
+        if (g1_377_jac_is_zero(&r)) continue;
+        memcpy(out_jac, &r, sizeof r);
+        if (out_attempt) *out_attempt = c;
+        return 0;
+    }
+    return 1;
+}

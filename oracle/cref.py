@@ -194,3 +194,14 @@ def fq12_from_ark_bytes(raw: bytes):
     vals = [L.fe_from_mont_bytes(raw[48 * i:48 * (i + 1)]) for i in range(12)]
     f2 = [(vals[2 * i], vals[2 * i + 1]) for i in range(6)]
     return ((f2[0], f2[1], f2[2]), (f2[3], f2[4], f2[5]))
+
+
+def hash_to_g1_direct(domain: bytes, message: bytes, extra: bytes, compat: bool = True):
+    """DIRECT_HASH_TO_G1 by the C port (cpu_ref_hash_to_g1_direct) -> (144-byte G1Projective image, attempt)."""
+    out = np.zeros(144, dtype=np.uint8)
+    att = ctypes.c_uint32(0)
+    rc = lib().cpu_ref_hash_to_g1_direct(domain.ljust(8, b"\0"), message, ctypes.c_size_t(len(message)), extra,
+                                         ctypes.c_size_t(len(extra)), int(compat), _ptr(out), ctypes.byref(att))
+    if rc != 0:
+        raise ValueError("hash to curve failed")
+    return out.tobytes(), att.value

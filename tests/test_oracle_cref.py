@@ -76,3 +76,24 @@ def test_batch_exponent_bytes():
     assert O.batch_exponent_bytes(4096) == 18
     assert O.batch_exponent_bytes(20) == 17
     assert O.batch_exponent_bytes(1 << 200) == 31
+
+
+def test_c_direct_hash_to_g1_matches_python_oracle():
+    """The C port of DIRECT_HASH_TO_G1 (the CPU figure of tools/bench_hash.py) against oracle/hash_to_curve.py,
+    which is pinned on the reference's hasher KATs and hash-to-curve vectors."""
+    from oracle import hash_to_curve as HC
+    L = C.LAYOUTS["bls12_377_g1"]
+    rng = O.SplitMix64(404)
+    seen = set()
+    for i in range(24):
+        msg = bytes(rng.below(256) for _ in range(rng.below(200) if i else 0))
+        extra = bytes(rng.below(256) for _ in range(rng.below(30) if i > 1 else 0))
+        for compat in (True, False):
+            image, att = C.hash_to_g1_direct(b"ULforxof", msg, extra, compat)
+            pt, want_att = HC.try_and_increment(O.G1, HC.DIRECT, b"ULforxof", msg, extra, compat=compat)
+            assert L.jacobian_compressed(image) == O.serialize_compressed(O.G1, pt) and att == want_att
+            seen.add(att)
+    assert len(seen) >= 3
+    image, _ = C.hash_to_g1_direct(b"abc", b"short domain", b"")
+    pt, _ = HC.try_and_increment(O.G1, HC.DIRECT, b"abc", b"short domain", b"")
+    assert L.jacobian_compressed(image) == O.serialize_compressed(O.G1, pt)

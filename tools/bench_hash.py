@@ -7,6 +7,7 @@ import json
 import time
 
 from celo_bls_snark_rs_b200 import engine as E
+from oracle import cref as C
 from oracle import hash_to_curve as H
 from oracle import oracle as O
 
@@ -41,9 +42,17 @@ def main():
             for m, e in sample:
                 H.try_and_increment(O.G1, oh, b"ULforxof", m, e, compat=True, cip22=cip22)
             cpu_ms = (time.perf_counter() - t0) * 1e3 / max(len(sample), 1)
-            res["cases"].append({"hasher": name, "message_bytes": msg_len, "e2e_ms": round(ms, 3),
+            c_ms = None
+            if name == "direct":                           # C port of DIRECT_HASH_TO_G1 (oracle/cpu_ref.c), one host thread
+                t0 = time.perf_counter()
+                for m, e in inputs[:256]:
+                    C.hash_to_g1_direct(b"ULforxof", m, e, True)
+                c_ms = round((time.perf_counter() - t0) * 1e3 / 256, 4)
+            res["cases"].append({"hasher": name, "message_bytes": msg_len, "e2e_ms": round(ms, 3), "cpu_c_port_ms_per_hash_1_thread": c_ms,
                                  "hashes_per_s": round(args.n / ms * 1e3), "max_attempt": max(att),
                                  "python_oracle_ms_per_hash": None if args.no_oracle else round(cpu_ms, 2)})
+    import os
+    res["host_cores"] = os.cpu_count()
     print(json.dumps(res))
 
 
