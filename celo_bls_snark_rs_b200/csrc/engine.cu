@@ -96,6 +96,8 @@ int b200_init(int device) {
 
 int b200_ensure_init(void) { return g_engine ? B200_OK : b200_init(-1); }
 
+int b200_bound_device(void) { return g_engine ? g_engine->device : -1; }
+
 void b200_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_engine_mu);
     if (!g_engine) return;

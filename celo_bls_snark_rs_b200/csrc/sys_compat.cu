@@ -59,13 +59,18 @@ bool hasher_of(bool composite, bool cip22, int *hasher, int *flags) {
 std::mutex g_scratch_mu;
 void *g_scratch = nullptr;
 size_t g_scratch_cap = 0;
+int g_scratch_device = -1;
 bool sum_images(int curve, const std::vector<const void *> &images, size_t bytes, void *out) {
     const size_t n = images.size(), need = (n + 1) * bytes;
     std::vector<uint8_t> host(n * bytes + 16);
     for (size_t i = 0; i < n; i++) memcpy(&host[i * bytes], images[i], bytes);
     std::lock_guard<std::mutex> lk(g_scratch_mu);
-    if (need > g_scratch_cap) {
+    // the engine may be bound to a device that is not this thread's current one (b200_init binds its caller only)
+    const int device = b200_bound_device();
+    if (device < 0 || cudaSetDevice(device) != cudaSuccess) return false;
+    if (need > g_scratch_cap || device != g_scratch_device) {
         if (g_scratch) cudaFree(g_scratch);
+        g_scratch_device = device;
         g_scratch = nullptr;
         g_scratch_cap = 0;
         if (cudaMalloc(&g_scratch, need + need / 2) != cudaSuccess) return false;

@@ -35,7 +35,7 @@ EXPORTS = [
     "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_msm_batch_device",
     "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
     "b200_groth16_verify_bw6_761", "b200_deserialize_points", "b200_verify_epochs", "b200_epoch_public_inputs",
-    "b200_blake2s_personal", "b200_hash_to_g1", "b200_serialize_points", "b200_ensure_init",
+    "b200_blake2s_personal", "b200_hash_to_g1", "b200_serialize_points", "b200_ensure_init", "b200_bound_device",
 ]
 # the reference's own symbols re-exported by the library (include/bls_snark_sys_compat.h)
 COMPAT_EXPORTS = ["verify", "deserialize_public_key", "deserialize_signature", "serialize_public_key", "serialize_signature",

@@ -55,6 +55,9 @@ enum {
 int b200_init(int device);
 /* b200_init(current device) unless an engine is already bound (the reference's `init()` is optional, lib.rs:29-34). */
 int b200_ensure_init(void);
+/* The device the engine is bound to, or -1.  Callers that stage their own device buffers next to the engine's calls
+ * (csrc/sys_compat.cu) select it first: b200_init binds the CALLING thread only. */
+int b200_bound_device(void);
 void b200_shutdown(void);
 const char *b200_last_error(void);
 
