@@ -346,3 +346,217 @@ int cpu_ref_hash_to_g1_direct(const uint8_t *domain8, const uint8_t *msg, size_t
     }
     return 1;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * COMPOSITE hasher in C (test infrastructure): Bowe-Hopwood CRH over ed-on-bw6-761 with the reference's
+ * generators (crates/bls-crypto/src/hashers/composite.rs:15-95; setup: Blake2s seed -> ChaCha20 -> Fq::rand as raw
+ * Montgomery limbs -> get_point_from_x -> cofactor 8; 560 windows x 93 chunks), then the same XOF / try-and-increment
+ * as above, with and without CIP22 (try_and_increment_cip22.rs:60-134).  Checked against the reference's CRH KAT and
+ * hash-to-curve vectors in tests/test_oracle_cref.py.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { fq377_t x, y, z, t; } ed_pt;
+static fq377_t g_ed_d;
+static ed_pt *g_bh_gens;                          /* 560 window bases, extended coordinates with z = 1 */
+static int g_bh_inited;
+enum { BH_WINDOW = 93, BH_WINDOWS = 560 };
+
+static void ed_add(ed_pt *r, const ed_pt *p, const ed_pt *q) {      /* unified add-2008-hwcd, a = -1 */
+    fq377_t A, B, C, D, E, F, G, H, t0, t1;
+    fq377_mul(&A, &p->x, &q->x);
+    fq377_mul(&B, &p->y, &q->y);
+    fq377_mul(&C, &p->t, &q->t);
+    fq377_mul(&C, &C, &g_ed_d);
+    fq377_mul(&D, &p->z, &q->z);
+    fq377_add(&t0, &p->x, &p->y);
+    fq377_add(&t1, &q->x, &q->y);
+    fq377_mul(&E, &t0, &t1);
+    fq377_sub(&E, &E, &A);
+    fq377_sub(&E, &E, &B);
+    fq377_sub(&F, &D, &C);
+    fq377_add(&G, &D, &C);
+    fq377_add(&H, &B, &A);
+    fq377_mul(&r->x, &E, &F);
+    fq377_mul(&r->y, &G, &H);
+    fq377_mul(&r->z, &F, &G);
+    fq377_mul(&r->t, &E, &H);
+}
+static void ed_identity(ed_pt *p) {
+    memset(p, 0, sizeof *p);
+    p->y = fq377_R1;
+    p->z = fq377_R1;
+}
+typedef struct { uint32_t key[8], buf[16]; uint64_t counter; int pos; } chacha_t;
+static inline uint32_t cc_rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+static void chacha_block(chacha_t *c) {
+    uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u}, w[16];
+    memcpy(s + 4, c->key, 32);
+    s[12] = (uint32_t)c->counter;
+    s[13] = (uint32_t)(c->counter >> 32);
+    s[14] = s[15] = 0;
+    memcpy(w, s, sizeof w);
+#define CC_QR(a, b, c_, d) \
+    w[a] += w[b]; w[d] = cc_rotl(w[d] ^ w[a], 16); w[c_] += w[d]; w[b] = cc_rotl(w[b] ^ w[c_], 12); \
+    w[a] += w[b]; w[d] = cc_rotl(w[d] ^ w[a], 8); w[c_] += w[d]; w[b] = cc_rotl(w[b] ^ w[c_], 7);
+    for (int r = 0; r < 10; r++) {
+        CC_QR(0, 4, 8, 12) CC_QR(1, 5, 9, 13) CC_QR(2, 6, 10, 14) CC_QR(3, 7, 11, 15)
+        CC_QR(0, 5, 10, 15) CC_QR(1, 6, 11, 12) CC_QR(2, 7, 8, 13) CC_QR(3, 4, 9, 14)
+    }
+#undef CC_QR
+    for (int i = 0; i < 16; i++) c->buf[i] = w[i] + s[i];
+    c->counter++;
+    c->pos = 0;
+}
+static uint32_t chacha_u32(chacha_t *c) {
+    if (c->pos == 16) chacha_block(c);
+    return c->buf[c->pos++];
+}
+static void bh_init(void) {
+    if (g_bh_inited) return;
+    ts_init();
+    static ed_pt gens[BH_WINDOWS];
+    fq377_t dd, one = fq377_R1;
+    memset(&dd, 0, sizeof dd);
+    dd.l[0] = 79743;
+    fq377_to_mont(&g_ed_d, &dd);
+    uint8_t seed[32];
+    const uint8_t *seg[3] = {(const uint8_t *)"ULTRALIGHT PRNG SEED", NULL, NULL};
+    const size_t len[3] = {20, 0, 0};
+    const uint32_t p[4] = {0x01010020u, 0, 0, 0};
+    b2s_hash(seed, p, (const uint8_t *)"UL_prngs", seg, len);
+    chacha_t rng;
+    memcpy(rng.key, seed, 32);
+    rng.counter = 0;
+    rng.pos = 16;
+    int have = 0;
+    while (have < BH_WINDOWS) {
+        fq377_t x, x2, num, den, y2, y;
+        do {                                         /* Fq::rand: raw limbs ARE the Montgomery form */
+            for (int k = 0; k < 6; k++) {
+                const uint64_t lo = chacha_u32(&rng);
+                x.l[k] = lo | ((uint64_t)chacha_u32(&rng) << 32);
+            }
+            x.l[5] &= ~(uint64_t)0 >> 7;
+        } while (fq377_geq_mod(x.l));
+        const int greatest = chacha_u32(&rng) >> 31;
+        fq377_sqr(&x2, &x);
+        fq377_add(&num, &x2, &one);
+        fq377_neg(&num, &num);                       /* a x^2 - 1, a = -1 */
+        fq377_mul(&den, &g_ed_d, &x2);
+        fq377_sub(&den, &den, &one);
+        if (fq377_is_zero(&den)) continue;
+        fq377_inv(&den, &den);
+        fq377_mul(&y2, &num, &den);
+        if (!fq377_sqrt(&y, &y2)) continue;
+        if (fq377_over_half(&y) != greatest) fq377_neg(&y, &y);
+        ed_pt pt;
+        pt.x = x;
+        pt.y = y;
+        pt.z = one;
+        fq377_mul(&pt.t, &x, &y);
+        for (int k = 0; k < 3; k++) ed_add(&pt, &pt, &pt);          /* cofactor 8 */
+        gens[have++] = pt;
+    }
+    g_bh_gens = gens;
+    g_bh_inited = 1;
+}
+static int bh_bit(size_t i, int has_c, uint8_t counter, const uint8_t *a, size_t la, const uint8_t *b, size_t lb) {
+    if (has_c) {
+        if (i < 8) return (counter >> i) & 1;
+        i -= 8;
+    }
+    size_t byte = i >> 3;
+    if (byte < la) return (a[byte] >> (i & 7)) & 1;
+    byte -= la;
+    return byte < lb ? (b[byte] >> (i & 7)) & 1 : 0;
+}
+/* x coordinate (48 canonical LE bytes) of the CRH of counter? | a | b; returns 1 when the input exceeds the capacity */
+static int bh_crh(uint8_t out48[48], int has_c, uint8_t counter, const uint8_t *a, size_t la, const uint8_t *b, size_t lb) {
+    bh_init();
+    const size_t bits = 8 * ((has_c ? 1 : 0) + la + lb), chunks = (bits + 2) / 3;
+    if (bits > (size_t)BH_WINDOW * BH_WINDOWS * 3) return 1;
+    ed_pt acc, g, g2, enc;
+    ed_identity(&acc);
+    for (size_t c = 0; c < chunks; c++) {
+        if (c % BH_WINDOW == 0) g = g_bh_gens[c / BH_WINDOW];
+        const int b0 = bh_bit(3 * c, has_c, counter, a, la, b, lb), b1 = bh_bit(3 * c + 1, has_c, counter, a, la, b, lb),
+                  b2 = bh_bit(3 * c + 2, has_c, counter, a, la, b, lb);
+        ed_add(&g2, &g, &g);
+        enc = g;
+        if (b0) ed_add(&enc, &enc, &g);
+        if (b1) ed_add(&enc, &enc, &g2);
+        if (b2) { fq377_neg(&enc.x, &enc.x); fq377_neg(&enc.t, &enc.t); }
+        ed_add(&acc, &acc, &enc);
+        ed_add(&g, &g2, &g2);                        /* 4 g, 8 g, 16 g */
+        ed_add(&g, &g, &g);
+        ed_add(&g, &g, &g);
+    }
+    fq377_t zi, x;
+    fq377_inv(&zi, &acc.z);
+    fq377_mul(&x, &acc.x, &zi);
+    fq377_from_mont(&x, &x);
+    memcpy(out48, x.l, 48);
+    return 0;
+}
+int cpu_ref_bh_crh(const uint8_t *msg, size_t msg_len, uint8_t *out48) { return bh_crh(out48, 0, 0, msg, msg_len, NULL, 0); }
+
+/* candidate bytes -> cofactor-cleared point; 0 = success */
+static int g1_from_candidate(const uint8_t cand_in[48], int compat, void *out_jac) {
+    static const uint64_t COFACTOR[4] = {0, 0x170b5d4430000000ull, 0, 0};
+    uint8_t cand[48];
+    memcpy(cand, cand_in, 48);
+    const int positive = compat ? (cand[47] >> 1) & 1 : (cand[47] >> 7) & 1;
+    const int infinity = (cand[47] >> 6) & 1;
+    cand[47] &= 0x01;
+    fq377_t x, y, rhs;
+    memcpy(x.l, cand, 48);
+    if (fq377_geq_mod(x.l)) return 1;
+    if (fq377_is_zero(&x) && infinity) return 1;
+    fq377_to_mont(&x, &x);
+    fq377_sqr(&rhs, &x);
+    fq377_mul(&rhs, &rhs, &x);
+    fq377_add(&rhs, &rhs, &fq377_R1);
+    if (!fq377_sqrt(&y, &rhs)) return 1;
+    if (fq377_over_half(&y) != positive) fq377_neg(&y, &y);
+    g1_377_aff a;
+    memset(&a, 0, sizeof a);
+    a.x = x;
+    a.y = y;
+    g1_377_jac r;
+    g1_377_scalar_mul(&r, &a, COFACTOR);
+    if (g1_377_jac_is_zero(&r)) return 1;
+    memcpy(out_jac, &r, sizeof r);
+    return 0;
+}
+
+int cpu_ref_hash_to_g1_composite(const uint8_t *domain8, const uint8_t *msg, size_t msg_len, const uint8_t *extra, size_t extra_len,
+                                 int compat, int cip22, void *out_jac, uint32_t *out_attempt) {
+    ts_init();
+    const uint32_t HB = 64;
+    uint8_t inner[48];
+    if (cip22 && bh_crh(inner, 0, 0, msg, msg_len, NULL, 0)) return 2;
+    for (uint32_t c = 0; c < 255; c++) {
+        const uint8_t counter = (uint8_t)c;
+        uint8_t crh[48], x0[32], x1[32], cand[48];
+        const uint8_t *xs[3];
+        size_t xl[3];
+        if (cip22) {
+            xs[0] = &counter; xl[0] = 1;
+            xs[1] = extra;    xl[1] = extra_len;
+            xs[2] = inner;    xl[2] = 48;
+        } else {
+            if (bh_crh(crh, 1, counter, extra, extra_len, msg, msg_len)) return 2;
+            xs[0] = crh; xl[0] = 48;
+            xs[1] = crh; xl[1] = 0;
+            xs[2] = crh; xl[2] = 0;
+        }
+        const uint32_t p0[4] = {32u, 32u, 0u, HB | (32u << 24)}, p1[4] = {32u, 32u, 1u, HB | (32u << 24)};
+        b2s_hash(x0, p0, domain8, xs, xl);
+        b2s_hash(x1, p1, domain8, xs, xl);
+        memcpy(cand, x0, 32);
+        memcpy(cand + 32, x1, 16);
+        if (g1_from_candidate(cand, compat, out_jac)) continue;
+        if (out_attempt) *out_attempt = c;
+        return 0;
+    }
+    return 1;
+}

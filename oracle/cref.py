@@ -205,3 +205,22 @@ def hash_to_g1_direct(domain: bytes, message: bytes, extra: bytes, compat: bool 
     if rc != 0:
         raise ValueError("hash to curve failed")
     return out.tobytes(), att.value
+
+
+def bh_crh(message: bytes) -> bytes:
+    """CompositeHasher::crh by the C port -> 48 bytes (x coordinate of the Bowe-Hopwood point)."""
+    out = np.zeros(48, dtype=np.uint8)
+    if lib().cpu_ref_bh_crh(message, ctypes.c_size_t(len(message)), _ptr(out)) != 0:
+        raise ValueError("message too long for the CRH")
+    return out.tobytes()
+
+
+def hash_to_g1_composite(domain: bytes, message: bytes, extra: bytes, compat: bool = True, cip22: bool = False):
+    """COMPOSITE_HASH_TO_G1 / ..._CIP22 by the C port -> (144-byte G1Projective image, attempt)."""
+    out = np.zeros(144, dtype=np.uint8)
+    att = ctypes.c_uint32(0)
+    rc = lib().cpu_ref_hash_to_g1_composite(domain.ljust(8, b"\0"), message, ctypes.c_size_t(len(message)), extra,
+                                            ctypes.c_size_t(len(extra)), int(compat), int(cip22), _ptr(out), ctypes.byref(att))
+    if rc != 0:
+        raise ValueError("hash to curve failed" if rc == 1 else "message too long for the CRH")
+    return out.tobytes(), att.value

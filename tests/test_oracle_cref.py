@@ -97,3 +97,33 @@ def test_c_direct_hash_to_g1_matches_python_oracle():
     image, _ = C.hash_to_g1_direct(b"abc", b"short domain", b"")
     pt, _ = HC.try_and_increment(O.G1, HC.DIRECT, b"abc", b"short domain", b"")
     assert L.jacobian_compressed(image) == O.serialize_compressed(O.G1, pt)
+
+
+def test_c_composite_hasher_reproduces_the_reference_vectors():
+    """The C port of the composite hasher (Bowe-Hopwood CRH with the ChaCha20-derived generators) against the
+    reference's own CRH KATs (hashers/composite.rs:104-131) and its 30 G1 hash-to-curve vectors
+    (hash_to_curve/mod.rs:413-487) -- a second, independent pin next to oracle/hash_to_curve.py."""
+    import json
+    import os
+    from oracle import hash_to_curve as HC
+    V = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    k = V["hasher_kats_composite"]["hex"]
+    rng = HC.XorShiftRng(HC.REFERENCE_SEED)
+    assert C.bh_crh(b"").hex() == k["test_crh_empty"][0]
+    assert C.bh_crh(bytes(rng.gen_u8() for _ in range(32))).hex() == k["test_crh_random"][0]
+    with pytest.raises(ValueError):
+        C.bh_crh(bytes(19531))
+    L = C.LAYOUTS["bls12_377_g1"]
+    for key, compat, cip22 in (("hash_to_g1_compat_pre_donut", True, False), ("hash_to_g1_compat_cip22", True, True),
+                               ("hash_to_g1_non_compat", False, False)):
+        rng = HC.XorShiftRng(HC.REFERENCE_SEED)
+        for want in V[key]["hex"]:
+            d, m, e = HC.generate_test_data(rng)
+            image, _ = C.hash_to_g1_composite(d, m, e, compat, cip22)
+            assert L.jacobian_compressed(image).hex() == want
+    # and against the Python oracle on a multi-window message, attempts included
+    msg, extra = bytes(range(256)) * 3, b"extra"
+    for cip22 in (False, True):
+        image, att = C.hash_to_g1_composite(b"ULforxof", msg, extra, True, cip22)
+        pt, want_att = HC.try_and_increment(O.G1, HC.COMPOSITE, b"ULforxof", msg, extra, compat=True, cip22=cip22)
+        assert L.jacobian_compressed(image) == O.serialize_compressed(O.G1, pt) and att == want_att
