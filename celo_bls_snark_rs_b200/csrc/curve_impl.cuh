@@ -245,12 +245,11 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     MsmWs &W = E.ws[0];
     int rc;
     if ((rc = msm_reserve<C>(W, p, n))) return rc;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     if ((rc = msm_stage_sort<C>(E, W, p, d_scalars, n, st))) return rc;
     if ((rc = msm_stage_accumulate<C>(E, W, p, d_bases, n, st))) return rc;
     if ((rc = msm_stage_tail<C>(W, p, d_out, st))) return rc;
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 
@@ -274,7 +273,7 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
     size_t live = 0;                                               // workspace sets alternate over the non-empty jobs
     for (size_t i = 0; i < count; i++)
         if (jobs[i].n && (rc = msm_reserve<C>(E.ws[live++ & 1], plans[i], jobs[i].n))) return rc;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     cudaStream_t s_sort = E.pipe_stream[0], s_acc = E.pipe_stream[1], s_tail = E.pipe_stream[2];
     CUDA_TRY(cudaEventRecord(E.ev_fork, st));
     for (cudaStream_t s : {s_sort, s_acc, s_tail}) CUDA_TRY(cudaStreamWaitEvent(s, E.ev_fork, 0));
@@ -302,8 +301,7 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
     }
     CUDA_TRY(cudaEventRecord(E.ev_join, s_tail));                  // the tail stream is last in every chain
     CUDA_TRY(cudaStreamWaitEvent(st, E.ev_join, 0));
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 
@@ -312,7 +310,7 @@ template <class C>
 int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scalars, size_t n, void *d_out,
                cudaStream_t st) {
     using F = typename C::F;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     // packed records are already the engine's layout (same Montgomery radix as arkworks)
     if (stride == sizeof(AffineMem<F>)) return msm_native<C>(E, d_bases, d_scalars, n, d_out, st);
     int rc = E.native_bases.reserve(n * sizeof(AffineMem<F>));

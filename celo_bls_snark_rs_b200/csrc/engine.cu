@@ -5,6 +5,8 @@
 
 namespace b200 {
 
+void engine_teardown(Engine &E);
+
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 
@@ -19,8 +21,15 @@ int fail(int code, const char *fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-static Engine *g_engine = nullptr;
+// The engine is shared by every host thread of the process (cgo callers arrive on arbitrary threads): entry points copy
+// the shared_ptr under g_engine_mu, then serialise on Engine::mu; b200_shutdown unpublishes it first, waits for the
+// call in flight by taking Engine::mu, tears the CUDA objects down and marks the object dead for late holders.
+static std::shared_ptr<Engine> g_engine;
 static std::mutex g_engine_mu;
+static std::shared_ptr<Engine> engine_ref() {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    return g_engine;
+}
 
 struct CurveInfo {
     size_t coord_bytes;   // one coordinate
@@ -62,14 +71,16 @@ int b200_init(int device) {
     if (g_engine && g_engine->device == device) return B200_OK;
     if (g_engine) return fail(B200_ERR_STATE, "engine already bound to device %d; call b200_shutdown first", g_engine->device);
     CUDA_TRY(cudaSetDevice(device));
-    Engine *E = new Engine();
+    // a failure below leaves through CUDA_TRY: the deleter releases whatever was created so far
+    std::shared_ptr<Engine> E(new Engine(), [](Engine *e) {
+        engine_teardown(*e);
+        delete e;
+    });
     E->device = device;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        delete E;
+    if (prop.major < 10)
         return fail(B200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-    }
     E->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&E->done, cudaEventDisableTiming));
@@ -94,28 +105,46 @@ int b200_init(int device) {
     return B200_OK;
 }
 
-int b200_ensure_init(void) { return g_engine ? B200_OK : b200_init(-1); }
+int b200_ensure_init(void) { return engine_ref() ? B200_OK : b200_init(-1); }
 
-int b200_bound_device(void) { return g_engine ? g_engine->device : -1; }
+int b200_bound_device(void) {
+    std::shared_ptr<Engine> e = engine_ref();
+    return e ? e->device : -1;
+}
 
 void b200_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_engine_mu);
-    if (!g_engine) return;
-    Engine *E = g_engine;
+    std::shared_ptr<Engine> e;
+    {
+        std::lock_guard<std::mutex> lk(g_engine_mu);
+        e.swap(g_engine);
+    }
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(e->mu);             // waits for the call in flight
+    engine_teardown(*e);
+}
+
+}  // extern "C"
+
+namespace b200 {
+// idempotent: runs from b200_shutdown and again (as a no-op) from the shared_ptr deleter
+void engine_teardown(Engine &En) {
+    Engine *E = &En;
+    if (E->dead) return;
+    E->dead = true;
     cudaSetDevice(E->device);
-    cudaStreamSynchronize(E->stream);
+    if (E->stream) cudaStreamSynchronize(E->stream);
     for (MsmWs &w : E->ws)
         for (b200::Buffer *b : {&w.counts, &w.offsets, &w.cursor, &w.tile_sums, &w.bins, &w.order, &w.sorted, &w.buckets, &w.partials,
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (b200::Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_sum, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
         b->release();
     for (NttDomain &d : E->ntt)
         for (b200::Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
     for (auto &ev : E->prof_ev)
         if (ev) cudaEventDestroy(ev);
-    cudaEventDestroy(E->done);
+    if (E->done) cudaEventDestroy(E->done);
     for (cudaEvent_t ev : {E->ev_fork, E->ev_join, E->ev_sorted[0], E->ev_sorted[1], E->ev_acc[0], E->ev_acc[1], E->ev_tail[0],
                            E->ev_tail[1]})
         if (ev) cudaEventDestroy(ev);
@@ -124,17 +153,20 @@ void b200_shutdown(void) {
     for (cudaEvent_t ev : E->ev_chunk)
         if (ev) cudaEventDestroy(ev);
     if (E->copy_stream) cudaStreamDestroy(E->copy_stream);
-    cudaStreamDestroy(E->stream);
-    delete E;
-    g_engine = nullptr;
+    if (E->stream) cudaStreamDestroy(E->stream);
 }
+}  // namespace b200
+
+extern "C" {
 
 #define REQUIRE_ENGINE()                                                              \
-    Engine *Ep = g_engine;                                                            \
+    std::shared_ptr<Engine> Ep = engine_ref();                                        \
     if (!Ep) return fail(B200_ERR_STATE, "b200_init has not been called");            \
     Engine &E = *Ep;                                                                  \
     std::lock_guard<std::mutex> lk(E.mu);                                             \
-    CUDA_TRY(cudaSetDevice(E.device))
+    if (E.dead) return fail(B200_ERR_STATE, "engine was shut down");                  \
+    CUDA_TRY(cudaSetDevice(E.device));                                                \
+    ENGINE_ORDER(E.stream)
 
 int b200_msm_device(int curve, const void *d_bases_packed, const void *d_scalars, size_t n, void *d_out_jacobian,
                     void *stream) {
@@ -153,7 +185,7 @@ int b200_msm_prepared_device(int curve, const void *d_bases_prepared, const void
     if (!d_out_jacobian || (n && (!d_bases_prepared || !d_scalars))) return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     return DISPATCH_CURVE(curve, msm_native, E, d_bases_prepared, d_scalars, n, d_out_jacobian, st);
 }
 
@@ -176,12 +208,16 @@ int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, 
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
     const void *dsrc = src;
     if (!src_on_device && n) {
+        ENGINE_ORDER(st);                             // the staging buffer may still feed a prior call
         int rc = E.h2d_bases.reserve(n * stride);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, src, n * stride, cudaMemcpyHostToDevice, st));
         dsrc = E.h2d_bases.p;
     }
-    return DISPATCH_CURVE(curve, pack_bases, dsrc, stride, n, d_dst_packed, st);
+    int rc = DISPATCH_CURVE(curve, pack_bases, dsrc, stride, n, d_dst_packed, st);
+    if (rc) return rc;
+    if (!src_on_device && n) ENGINE_MARK(st);
+    return B200_OK;
 }
 
 // Large inputs are cut into chunks: chunk c + 1 crosses PCIe (copy stream) while chunk c is being
@@ -256,6 +292,24 @@ int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void
     return DISPATCH_CURVE(curve, sum_jacobian, d_points, count, d_out, st);
 }
 
+// host-pointer form: `count` contiguous arkworks GroupProjective images in host memory -> their sum (host memory).
+// Everything is queued on the engine's stream (copies included), so the kernel can never see a stale staging buffer.
+int b200_sum_jacobian(int curve, const void *points, size_t count, void *out) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out || (count && !points)) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = E.stream;
+    int rc = E.v_sum.reserve((count + 1) * ci.jac_bytes);
+    if (rc) return rc;
+    char *d = E.v_sum.as<char>();
+    if (count) CUDA_TRY(cudaMemcpyAsync(d, points, count * ci.jac_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = DISPATCH_CURVE(curve, sum_jacobian, d, count, d + count * ci.jac_bytes, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, d + count * ci.jac_bytes, ci.jac_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
 int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void *d_scalars, size_t n,
                                void *d_out_packed, void *stream) {
     CurveInfo ci;
@@ -263,11 +317,10 @@ int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void 
     if (n && (!d_base_packed || !d_scalars || !d_out_packed)) return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     int rc = DISPATCH_CURVE(curve, fixed_base_mul, E, d_base_packed, d_scalars, n, d_out_packed, st);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 
@@ -285,11 +338,10 @@ int b200_miller_product_bls12_377_device(const void *d_g1_packed, const void *d_
     if (!d_out_fq12 || (n && (!d_g1_packed || !d_g2_packed))) return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     int rc = miller_product(E, d_g1_packed, d_g2_packed, n, d_out_fq12, st);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 
@@ -298,11 +350,10 @@ int b200_final_exp_bls12_377_device(const void *d_fq12_vals, size_t count, void 
     if (!d_fq12_vals || count == 0) return fail(B200_ERR_ARG, "null pointer / empty input");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     int rc = final_exp(E, d_fq12_vals, count, d_out_fq12, d_is_one, st);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 
@@ -348,11 +399,10 @@ int b200_miller_values_bw6_761_device(const void *d_g1_packed, const void *d_g2_
     if (n && (!d_g1_packed || !d_g2_packed || !d_out_vals)) return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     int rc = bw6_miller_values(E, d_g1_packed, d_g2_packed, n, d_out_vals, st);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 
@@ -360,11 +410,10 @@ int b200_final_exp_bw6_761_device(const void *d_vals, size_t count, void *d_out_
     if (!d_vals || count == 0) return fail(B200_ERR_ARG, "null pointer / empty input");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     int rc = bw6_final_exp(E, d_vals, count, d_out_fq6, d_is_one, st);
     if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 
@@ -395,8 +444,8 @@ int b200_verify_epochs(const uint8_t *vk, size_t vk_len, const uint8_t *proof, s
                        const void *last_epoch, int *out_ok) {
     if (!out_ok || !first_epoch || !last_epoch) return fail(B200_ERR_ARG, "null pointer");
     *out_ok = 0;
-    if (!g_engine) {                                  // the reference's init() is optional: bind on first use
-        int rc = b200_init(-1);
+    {                                                 // the reference's init() is optional: bind on first use
+        int rc = b200_ensure_init();
         if (rc) return rc;
     }
     REQUIRE_ENGINE();
@@ -412,8 +461,8 @@ int b200_epoch_public_inputs(const void *first_epoch, const void *last_epoch, ui
     if (!out_ok || !out_count || !first_epoch || !last_epoch) return fail(B200_ERR_ARG, "null pointer");
     *out_ok = 0;
     *out_count = 0;
-    if (!g_engine) {
-        int rc = b200_init(-1);
+    {
+        int rc = b200_ensure_init();
         if (rc) return rc;
     }
     REQUIRE_ENGINE();
@@ -475,7 +524,11 @@ int b200_ntt_device(int field, void *d_data, unsigned log_n, int inverse, int co
     if (log_n > 26) return fail(B200_ERR_ARG, "log_n = %u exceeds the 2^26 per-call limit", log_n);
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    return ntt_transform(E, field, d_data, (int)log_n, inverse, coset, st);
+    ENGINE_ORDER(st);                                 // the cached domain tables may have been built on another stream
+    int rc = ntt_transform(E, field, d_data, (int)log_n, inverse, coset, st);
+    if (rc) return rc;
+    ENGINE_MARK(st);
+    return B200_OK;
 }
 
 int b200_witness_map_device(int field, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_h, void *stream) {
@@ -484,7 +537,11 @@ int b200_witness_map_device(int field, void *d_a, void *d_b, void *d_c, unsigned
     if (log_n > 26) return fail(B200_ERR_ARG, "log_n = %u exceeds the 2^26 per-call limit", log_n);
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    return witness_map(E, field, d_a, d_b, d_c, (int)log_n, d_h, st);
+    ENGINE_ORDER(st);
+    int rc = witness_map(E, field, d_a, d_b, d_c, (int)log_n, d_h, st);
+    if (rc) return rc;
+    ENGINE_MARK(st);
+    return B200_OK;
 }
 
 int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
@@ -498,7 +555,7 @@ int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void 
     if (log_n == 0 || log_n > 26) return fail(B200_ERR_ARG, "log_n = %u out of range [1, 26]", log_n);
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
-    if (E.has_pending && st != E.stream) CUDA_TRY(cudaStreamWaitEvent(st, E.done, 0));
+    ENGINE_ORDER(st);
     return groth16_prove(E, family, pk, d_assignment, num_assign, num_aux, d_a, d_b, d_c, log_n, d_proof, st);
 }
 
@@ -540,7 +597,7 @@ int b200_profile_read(double *accumulate_ms, int *launches, uint64_t *pairs) {
 }
 
 int b200_sync(void *stream) {
-    Engine *Ep = g_engine;
+    std::shared_ptr<Engine> Ep = engine_ref();         // no Engine::mu: a sync must not queue behind other callers
     if (!Ep) return fail(B200_ERR_STATE, "b200_init has not been called");
     CUDA_TRY(cudaSetDevice(Ep->device));
     CUDA_TRY(cudaStreamSynchronize(stream ? (cudaStream_t)stream : Ep->stream));

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -30,6 +31,19 @@ void count_launch();
         count_launch();                                                                                  \
         cudaError_t e_ = cudaGetLastError();                                                             \
         if (e_ != cudaSuccess) return fail(B200_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e_));  \
+    } while (0)
+
+// Stream ordering of the engine-owned, grow-only workspaces: whatever stream the previous asynchronous entry point
+// ran on recorded Engine::done; the next user of the workspaces waits for it first -- also when it runs on the
+// engine's own stream (a wait for an event recorded on the same stream costs nothing).
+#define ENGINE_ORDER(st)                                                                                 \
+    do {                                                                                                 \
+        if (E.has_pending) CUDA_TRY(cudaStreamWaitEvent((st), E.done, 0));                               \
+    } while (0)
+#define ENGINE_MARK(st)                                                                                  \
+    do {                                                                                                 \
+        CUDA_TRY(cudaEventRecord(E.done, (st)));                                                         \
+        E.has_pending = true;                                                                            \
     } while (0)
 
 struct Buffer {
@@ -71,6 +85,7 @@ struct Engine {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;      // completion of the last MSM (orders workspace reuse across streams)
     bool has_pending = false;
+    bool dead = false;               // torn down by b200_shutdown while another thread still held a reference
     std::mutex mu;
     MsmWs ws[2];
     // software pipeline of b200_msm_batch_device: sort / accumulate / tail streams and their hand-over events
@@ -89,7 +104,7 @@ struct Engine {
     // Groth16 prover composite (inst_groth16.cu): quotient coefficients h, partial MSM results
     Buffer g16_h, g16_tmp;
     // batch-verification composites (inst_verify.cu)
-    Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff;
+    Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff, v_sum;
     // hash-to-G1 (inst_hash.cu): affine multiples of the Bowe-Hopwood generators (built at first use), per-call staging
     Buffer bh_table, hash_ws, sqrt_tables;
     bool bh_ready = false, sqrt_ready = false;

@@ -86,8 +86,7 @@ static int groth16_prove_t(Engine &E, int field, const b200_groth16_pk *pk, cons
     k_sum_jacobian<F1><<<1, SUM_THREADS, 0, st>>>(reinterpret_cast<const JacobianMem<F1> *>(tmp + J1), 2,
                                         reinterpret_cast<JacobianMem<F1> *>(proof + J1 + J2));
     LAUNCH_CHECK();
-    CUDA_TRY(cudaEventRecord(E.done, st));
-    E.has_pending = true;
+    ENGINE_MARK(st);
     return B200_OK;
 }
 

@@ -54,32 +54,13 @@ bool hasher_of(bool composite, bool cip22, int *hasher, int *flags) {
     return true;
 }
 
-// sum of Jacobian images on the device (PublicKey::aggregate / Signature::aggregate).  The staging buffer is a
-// process-lifetime, grow-only allocation: cudaMalloc / cudaFree per call cost more than the sum itself.
-std::mutex g_scratch_mu;
-void *g_scratch = nullptr;
-size_t g_scratch_cap = 0;
-int g_scratch_device = -1;
+// sum of Jacobian images on the device (PublicKey::aggregate / Signature::aggregate): gathered into one host block,
+// then b200_sum_jacobian stages, sums and reads back on the engine's own stream under the engine's lock
 bool sum_images(int curve, const std::vector<const void *> &images, size_t bytes, void *out) {
-    const size_t n = images.size(), need = (n + 1) * bytes;
+    const size_t n = images.size();
     std::vector<uint8_t> host(n * bytes + 16);
     for (size_t i = 0; i < n; i++) memcpy(&host[i * bytes], images[i], bytes);
-    std::lock_guard<std::mutex> lk(g_scratch_mu);
-    // the engine may be bound to a device that is not this thread's current one (b200_init binds its caller only)
-    const int device = b200_bound_device();
-    if (device < 0 || cudaSetDevice(device) != cudaSuccess) return false;
-    if (need > g_scratch_cap || device != g_scratch_device) {
-        if (g_scratch) cudaFree(g_scratch);
-        g_scratch_device = device;
-        g_scratch = nullptr;
-        g_scratch_cap = 0;
-        if (cudaMalloc(&g_scratch, need + need / 2) != cudaSuccess) return false;
-        g_scratch_cap = need + need / 2;
-    }
-    char *d = (char *)g_scratch;
-    return cudaMemcpy(d, host.data(), n * bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
-           b200_sum_jacobian_device(curve, d, n, d + n * bytes, nullptr) == B200_OK && b200_sync(nullptr) == B200_OK &&
-           cudaMemcpy(out, d + n * bytes, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+    return b200_sum_jacobian(curve, host.data(), n, out) == B200_OK;
 }
 
 // ark_std::log2: ceil(log2(x)), 0 for x <= 1

@@ -110,6 +110,9 @@ int b200_msm_batch_device(int curve, const b200_msm_job *jobs, size_t count, voi
 /* out = sum of `count` Jacobian points (device pointers).  Used to combine per-GPU
  * partial MSM results after the all-gather. */
 int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void *d_out_jacobian, void *stream);
+/* Host-pointer form: `count` contiguous GroupProjective images -> their sum; replaces the folds of
+ * PublicKey::aggregate / Signature::aggregate (crates/bls-crypto/src/bls/public.rs:34, signature.rs:52). */
+int b200_sum_jacobian(int curve, const void *points, size_t count, void *out_jacobian);
 
 /* d_out_packed[i] = scalars[i] * base, as packed affine records (device pointers;
  * base is one packed affine record).  Synthesises benchmark / test bases on the GPU. */
