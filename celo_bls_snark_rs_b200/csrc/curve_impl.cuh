@@ -1,6 +1,7 @@
 // Definitions of the per-curve host entry points (kernel launches).  Included by inst_*.cu only.
 #pragma once
 #include "engine.cuh"
+#include "coop.cuh"
 
 namespace b200 {
 
@@ -226,7 +227,15 @@ static int msm_stage_tail(MsmWs &W, const MsmPlan &p, void *d_out, cudaStream_t 
     k_window_sum<F, WS_THREADS><<<p.windows + 1, WS_THREADS, ws_smem, st>>>(W.partials.as<XYZZMem<F>>(), p,
                                                                         W.window_sums.as<XYZZMem<F>>());
     LAUNCH_CHECK();
-    k_window_combine<F><<<1, 32, 0, st>>>(W.window_sums.as<XYZZMem<F>>(), p, reinterpret_cast<JacobianMem<F> *>(d_out));
+    // Horner over the windows: four warps share every point operation (coop.cuh); B200_COMBINE_QUAD=1 selects the
+    // one-quad kernel it replaced (cross-check)
+    static const bool quad_combine = getenv("B200_COMBINE_QUAD") && atoi(getenv("B200_COMBINE_QUAD"));
+    if (quad_combine)
+        k_window_combine<F><<<1, 32, 0, st>>>(W.window_sums.as<XYZZMem<F>>(), p, reinterpret_cast<JacobianMem<F> *>(d_out));
+    else
+        k_window_combine_coop<F><<<1, COOP_THREADS, 0, st>>>(W.window_sums.as<XYZZMem<F>>(), 0, p.windows, p.c, 0,
+                                                             W.window_sums.as<XYZZMem<F>>() + p.windows, nullptr,
+                                                             reinterpret_cast<JacobianMem<F> *>(d_out), nullptr);
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -371,6 +380,12 @@ int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStre
     using F = typename C::F;
     if (n == 0) return B200_OK;
     using M = typename F::Mem;
+    if (op >= 8) {                                                 // the warp-cooperative routines of coop.cuh, one warp per element
+        k_coop_field_op<F><<<ceil_div(n * 32, COOP_THREADS), COOP_THREADS, 0, st>>>(
+            op - 8, reinterpret_cast<const M *>(a), reinterpret_cast<const M *>(b), (uint32_t)n, reinterpret_cast<M *>(out));
+        LAUNCH_CHECK();
+        return B200_OK;
+    }
     k_field_op<F><<<ceil_div(n, 64), 64, 0, st>>>(op, reinterpret_cast<const M *>(a), reinterpret_cast<const M *>(b),
                                                   (uint32_t)n, reinterpret_cast<M *>(out));
     LAUNCH_CHECK();

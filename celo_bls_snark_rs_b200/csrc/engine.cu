@@ -562,7 +562,7 @@ int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void 
 int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream) {
     CurveInfo ci;
     if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
-    if (op < 0 || op > 6) return fail(B200_ERR_ARG, "unknown field op %d", op);
+    if (op < 0 || op > 14 || op == 7 || op == 12) return fail(B200_ERR_ARG, "unknown field op %d", op);   // 8..14: cooperative forms (no inverse)
     if (n && (!d_a || !d_b || !d_out)) return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;

@@ -240,7 +240,9 @@ def batch_to_affine_device(curve: int, d_jac: int, n: int, d_out: int, stream: i
     _check(load().b200_batch_to_affine_device(curve, d_jac, n, d_out, stream or None))
 
 
-FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5, "dbl": 6}
+FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5, "dbl": 6,
+             # the warp-cooperative routines of csrc/coop.cuh (one warp per element)
+             "coop_add": 8, "coop_sub": 9, "coop_mul": 10, "coop_sqr": 11, "coop_neg": 13, "coop_dbl": 14}
 
 
 def field_op_device(curve: int, op: str, d_a: int, d_b: int, n: int, d_out: int, stream: int = 0):

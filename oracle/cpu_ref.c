@@ -25,6 +25,10 @@
 #define FP_NL 12
 #include "fp_tmpl.h"
 
+#define FP fr253                                   /* BLS12-377 scalar field (NTT domain of the inner proof) */
+#define FP_NL 4
+#include "fp_tmpl.h"
+
 static const uint64_t MOD377[6] = {
     0x8508c00000000001ULL, 0x170b5d4430000000ULL, 0x1ef3622fba094800ULL,
     0x1a22d9f300f5138fULL, 0xc63b05c06ca1493bULL, 0x01ae3a4617c510eaULL };
@@ -32,6 +36,9 @@ static const uint64_t MOD761[12] = {
     0xf49d00000000008bULL, 0xe6913e6870000082ULL, 0x160cf8aeeaf0a437ULL, 0x98a116c25667a8f8ULL,
     0x71dcd3dc73ebff2eULL, 0x8689c8ed12f9fd90ULL, 0x03cebaff25b42304ULL, 0x707ba638e584e919ULL,
     0x528275ef8087be41ULL, 0xb926186a81d14688ULL, 0xd187c94004faff3eULL, 0x0122e824fb83ce0aULL };
+
+static const uint64_t MODR253[4] = {
+    0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL, 0x12ab655e9a2ca556ULL };
 
 static inline fq377_t fq377_one(void) { return fq377_R1; }
 static inline fq761_t fq761_one(void) { return fq761_R1; }
@@ -62,7 +69,17 @@ static inline void fq2_377_mul(fq2_377_t *r, const fq2_377_t *a, const fq2_377_t
     fq377_mul5(&v1, &v1);
     fq377_sub(&r->c0, &v0, &v1);
 }
-static inline void fq2_377_sqr(fq2_377_t *r, const fq2_377_t *a) { fq2_377_mul(r, a, a); }
+static inline void fq2_377_sqr(fq2_377_t *r, const fq2_377_t *a) {
+    /* complex squaring, 2 products: c1 = 2 a0 a1, c0 = (a0 + a1)(a0 - 5 a1) + 4 a0 a1 */
+    fq377_t m, s, t;
+    fq377_mul(&m, &a->c0, &a->c1);
+    fq377_add(&s, &a->c0, &a->c1);
+    fq377_mul5(&t, &a->c1); fq377_sub(&t, &a->c0, &t);
+    fq377_mul(&s, &s, &t);
+    fq377_dbl(&r->c1, &m);
+    fq377_dbl(&t, &r->c1);
+    fq377_add(&r->c0, &s, &t);
+}
 static void fq2_377_inv(fq2_377_t *r, const fq2_377_t *a) {
     fq377_t n, t;
     fq377_sqr(&n, &a->c0);
@@ -99,6 +116,7 @@ static void ensure_init(void) {
     if (g_inited) return;
     fq377_init(MOD377);
     fq761_init(MOD761);
+    fr253_init(MODR253);
     g_inited = 1;
 }
 void cpu_ref_init(void) { ensure_init(); }
@@ -559,4 +577,37 @@ int cpu_ref_hash_to_g1_composite(const uint8_t *domain8, const uint8_t *msg, siz
         return 0;
     }
     return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * BLS12-377 product of pairings and the Groth16 prover's radix-2 transforms (see the two headers)
+ * ------------------------------------------------------------------------------------------------ */
+#include "pairing_tmpl.h"
+
+#define NT ntt253
+#define NTF fr253
+#define NT_NL 4
+#define NT_GEN 22
+#define NT_GEN_NEG 0
+#define NT_S 47
+#include "ntt_tmpl.h"
+
+#define NT ntt377
+#define NTF fq377
+#define NT_NL 6
+#define NT_GEN 5
+#define NT_GEN_NEG 1
+#define NT_S 46
+#include "ntt_tmpl.h"
+
+/* field: 0 = BLS12-377 Fr (4 limbs), 1 = BW6-761 Fr = BLS12-377 Fq (6 limbs); data: n x limbs Montgomery residues */
+int cpu_ref_ntt(int field, uint64_t *data, unsigned log_n, int inverse, int coset, int threads) {
+    if (field == 0) return ntt253_ntt((fr253_t *)data, log_n, inverse, coset, threads);
+    if (field == 1) return ntt377_ntt((fq377_t *)data, log_n, inverse, coset, threads);
+    return -1;
+}
+int cpu_ref_witness_map(int field, uint64_t *a, uint64_t *b, uint64_t *c, unsigned log_n, uint64_t *h, int threads) {
+    if (field == 0) return ntt253_witness_map((fr253_t *)a, (fr253_t *)b, (fr253_t *)c, log_n, (fr253_t *)h, threads);
+    if (field == 1) return ntt377_witness_map((fq377_t *)a, (fq377_t *)b, (fq377_t *)c, log_n, (fq377_t *)h, threads);
+    return -1;
 }

@@ -224,3 +224,41 @@ def hash_to_g1_composite(domain: bytes, message: bytes, extra: bytes, compat: bo
     if rc != 0:
         raise ValueError("hash to curve failed" if rc == 1 else "message too long for the CRH")
     return out.tobytes(), att.value
+
+
+# ---- BLS12-377 product of pairings and the prover's radix-2 transforms (pairing_tmpl.h, ntt_tmpl.h) ----------
+def multi_pairing(g1: np.ndarray, g2: np.ndarray, n: Optional[int] = None, threads: int = 1, phase: int = 0,
+                  value: Optional[bytes] = None):
+    """cpu_ref_multi_pairing over arkworks-layout records (uint8 [n, 104 | 96] and [n, 200 | 192]).
+    phase 0: product of pairings; 1: Miller value only; 2: final exponentiation of `value`.
+    threads = 1 is arkworks' own serial Miller loop.  Returns (is_one, 576-byte Fq12 image)."""
+    g1 = np.ascontiguousarray(g1)
+    g2 = np.ascontiguousarray(g2)
+    if n is None:
+        n = min(len(g1), len(g2))
+    out = np.zeros(576, dtype=np.uint8)
+    if value is not None:
+        out[:] = np.frombuffer(value, dtype=np.uint8)
+    flag = ctypes.c_int(0)
+    s1 = g1.strides[0] if n else 104
+    s2 = g2.strides[0] if n else 200
+    rc = lib().cpu_ref_multi_pairing(_ptr(g1) if n else None, ctypes.c_size_t(s1), _ptr(g2) if n else None, ctypes.c_size_t(s2),
+                                     ctypes.c_size_t(n), _ptr(out), ctypes.byref(flag), int(threads), int(phase))
+    assert rc == 0
+    return bool(flag.value), out.tobytes()
+
+
+def ntt(field_id: int, data: np.ndarray, log_n: int, inverse: bool, coset: bool, threads: int = 1) -> np.ndarray:
+    """In-place fft / ifft / coset_fft / coset_ifft on a uint64 [n, limbs] array of Montgomery residues (a copy is returned)."""
+    a = np.ascontiguousarray(data, dtype=np.uint64).copy()
+    rc = lib().cpu_ref_ntt(int(field_id), _ptr(a), ctypes.c_uint(log_n), int(inverse), int(coset), int(threads))
+    assert rc == 0
+    return a
+
+
+def witness_map(field_id: int, a: np.ndarray, b: np.ndarray, c: np.ndarray, log_n: int, threads: int = 1) -> np.ndarray:
+    a, b, c = (np.ascontiguousarray(x, dtype=np.uint64).copy() for x in (a, b, c))
+    h = np.zeros_like(a)
+    rc = lib().cpu_ref_witness_map(int(field_id), _ptr(a), _ptr(b), _ptr(c), ctypes.c_uint(log_n), _ptr(h), int(threads))
+    assert rc == 0
+    return h

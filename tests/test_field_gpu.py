@@ -44,12 +44,15 @@ def test_field_ops_match_python(name):
     d_a, d_b = enc(a), enc(b)
     d_o = torch.empty_like(d_a)
     cb = L.coord_bytes
-    for op in ("add", "sub", "mul", "sqr", "neg", "dbl", "inv"):
+    # coop_*: the same operations through the warp-cooperative routines (one limb per lane, csrc/coop.cuh)
+    for op in ("add", "sub", "mul", "sqr", "neg", "dbl", "inv", "coop_add", "coop_sub", "coop_mul", "coop_sqr", "coop_neg",
+               "coop_dbl"):
+        d_o.zero_()
         E.field_op_device(L.id, op, d_a.data_ptr(), d_b.data_ptr(), n, d_o.data_ptr())
         E.sync()
         raw = d_o.cpu().numpy().tobytes()
         got = [L.fe_from_mont_bytes(raw[i * cb:(i + 1) * cb]) for i in range(n)]
-        want = [_ref(L, op, x, y) for x, y in zip(a, b)]
+        want = [_ref(L, op.replace("coop_", ""), x, y) for x, y in zip(a, b)]
         assert got == want, (name, op, [i for i in range(n) if got[i] != want[i]][:5])
         # outputs must be canonical residues (fully reduced), i.e. the raw Montgomery words < p
         words = [int.from_bytes(raw[i * L.curve.coord_bytes:(i + 1) * L.curve.coord_bytes], "little")

@@ -127,3 +127,65 @@ def test_c_composite_hasher_reproduces_the_reference_vectors():
         image, att = C.hash_to_g1_composite(b"ULforxof", msg, extra, True, cip22)
         pt, want_att = HC.try_and_increment(O.G1, HC.COMPOSITE, b"ULforxof", msg, extra, compat=True, cip22=cip22)
         assert L.jacobian_compressed(image) == O.serialize_compressed(O.G1, pt) and att == want_att
+
+
+# ---- C product of pairings (oracle/pairing_tmpl.h) vs the Python restatement -------------------------------
+def _pairing_inputs(n, seed):
+    rng = O.SplitMix64(seed)
+    L1, L2 = C.LAYOUTS["bls12_377_g1"], C.LAYOUTS["bls12_377_g2"]
+    p1 = L1.affine_from_records(C.fixed_base_batch(L1, O.G1_GEN, [rng.below(O.R) for _ in range(n)]))
+    p2 = L2.affine_from_records(C.fixed_base_batch(L2, O.G2_GEN, [rng.below(O.R) for _ in range(n)]))
+    return L1, L2, p1, p2
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 5])
+def test_c_multi_pairing_bytes_match_python(n):
+    L1, L2, p1, p2 = _pairing_inputs(n, 40 + n)
+    if n >= 5:
+        p1[3] = None                         # pairs with an infinite member are skipped
+        p2[4] = None
+    want = O.product_of_pairings(list(zip(p1, p2)))
+    for threads, stride in ((1, None), (3, "packed")):
+        g1 = L1.affine_records(p1, L1.packed_stride if stride else None)
+        g2 = L2.affine_records(p2, L2.packed_stride if stride else None)
+        is_one, gt = C.multi_pairing(g1, g2, n, threads=threads)
+        assert gt == C.fq12_to_ark_bytes(want), (n, threads)
+        assert is_one == (want == O.FQ12_ONE)
+    # the two halves separately: Miller value, then its final exponentiation
+    _, mv = C.multi_pairing(L1.affine_records(p1), L2.affine_records(p2), n, phase=1)
+    assert mv == C.fq12_to_ark_bytes(O.miller_loop(list(zip(p1, p2))))
+    _, gt2 = C.multi_pairing(L1.affine_records(p1[:0]), L2.affine_records(p2[:0]), 0, phase=2, value=mv)
+    assert gt2 == C.fq12_to_ark_bytes(want)
+
+
+def test_c_multi_pairing_bilinear_check():
+    """e(a G1, b G2) e(-ab G1, G2) == 1: the shape of the 2-pair check of public.rs:102"""
+    rng = O.SplitMix64(77)
+    a, b = rng.below(O.R), rng.below(O.R)
+    L1, L2 = C.LAYOUTS["bls12_377_g1"], C.LAYOUTS["bls12_377_g2"]
+    p1 = [O.G1.pmul(O.G1_GEN, a), O.G1.pneg(O.G1.pmul(O.G1_GEN, a * b % O.R))]
+    p2 = [O.G2.pmul(O.G2_GEN, b), O.G2_GEN]
+    ok, _ = C.multi_pairing(L1.affine_records(p1), L2.affine_records(p2))
+    assert ok
+    p1[1] = O.G1.pmul(O.G1_GEN, 5)
+    ok, _ = C.multi_pairing(L1.affine_records(p1), L2.affine_records(p2))
+    assert not ok
+
+
+# ---- C radix-2 transforms (oracle/ntt_tmpl.h) vs oracle/ntt.py ------------------------------------------------
+@pytest.mark.parametrize("fname", ["fr_bls12_377", "fr_bw6_761"])
+@pytest.mark.parametrize("log_n", [0, 1, 3, 6])
+def test_c_ntt_matches_python(fname, log_n):
+    from oracle import ntt as N
+    f = N.FIELDS[fname]
+    rng = O.SplitMix64(9 + log_n)
+    n = 1 << log_n
+    vals = [rng.below(f.p) for _ in range(n)]
+    arr = f.to_mont_array(vals)
+    for inverse, coset, ref in ((0, 0, N.fft), (1, 0, N.ifft), (0, 1, N.coset_fft), (1, 1, N.coset_ifft)):
+        got = f.from_mont_array(C.ntt(f.id, arr, log_n, bool(inverse), bool(coset), threads=3))
+        assert got == ref(f, vals), (fname, log_n, inverse, coset)
+    if log_n >= 1:
+        b, c = [rng.below(f.p) for _ in range(n)], [rng.below(f.p) for _ in range(n)]
+        got = f.from_mont_array(C.witness_map(f.id, arr, f.to_mont_array(b), f.to_mont_array(c), log_n, threads=2))
+        assert got == N.witness_map(f, vals, b, c)
