@@ -355,6 +355,24 @@ int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, v
 }
 
 template <class C>
+int point_runs(Engine &E, const void *base, const void *scalars, size_t runs, size_t run, void *out, cudaStream_t st) {
+    using F = typename C::F;
+    const size_t n = runs * run;
+    if (n == 0) return B200_OK;
+    int rc = E.ws[0].buckets.reserve(n * sizeof(XYZZMem<F>));
+    if (rc) return rc;
+    constexpr int TH = 64;
+    k_point_runs<F, C::SCALAR_WORDS, TH><<<ceil_div(runs, TH), TH, 0, st>>>(
+        reinterpret_cast<const AffineMem<F> *>(base), reinterpret_cast<const uint32_t *>(scalars), (uint32_t)runs, (uint32_t)run,
+        E.ws[0].buckets.as<XYZZMem<F>>());
+    LAUNCH_CHECK();
+    k_xyzz_to_affine<F, TH><<<ceil_div(n, TH), TH, 0, st>>>(E.ws[0].buckets.as<XYZZMem<F>>(), (uint32_t)n,
+                                                            reinterpret_cast<AffineMem<F> *>(out));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+template <class C>
 int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st) {
     using F = typename C::F;
     if (n == 0) return B200_OK;
@@ -399,6 +417,7 @@ int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStre
     template int msm_batch<C>(Engine &, const b200_msm_job *, size_t, cudaStream_t, const cudaEvent_t *);         \
     template int sum_jacobian<C>(const void *, size_t, void *, cudaStream_t);                                     \
     template int fixed_base_mul<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);           \
+    template int point_runs<C>(Engine &, const void *, const void *, size_t, size_t, void *, cudaStream_t);       \
     template int batch_to_affine<C>(const void *, size_t, void *, cudaStream_t);                                  \
     template int plan_query<C>(size_t, int *, int *, uint32_t *);                                                 \
     template int field_op<C>(int, const void *, const void *, size_t, void *, cudaStream_t);

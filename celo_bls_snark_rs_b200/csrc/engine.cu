@@ -138,7 +138,7 @@ void engine_teardown(Engine &En) {
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (b200::Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_sum, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_sum, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->g16_part, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
         b->release();
     for (NttDomain &d : E->ntt)
         for (b200::Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
@@ -319,6 +319,21 @@ int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void 
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
     ENGINE_ORDER(st);
     int rc = DISPATCH_CURVE(curve, fixed_base_mul, E, d_base_packed, d_scalars, n, d_out_packed, st);
+    if (rc) return rc;
+    ENGINE_MARK(st);
+    return B200_OK;
+}
+
+int b200_point_runs_device(int curve, const void *d_base_packed, const void *d_start_scalars, size_t runs, size_t run_len,
+                           void *d_out_packed, void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (runs && run_len && (!d_base_packed || !d_start_scalars || !d_out_packed)) return fail(B200_ERR_ARG, "null pointer");
+    if (runs * run_len > ((size_t)1 << 28)) return fail(B200_ERR_ARG, "too many points");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    ENGINE_ORDER(st);
+    int rc = DISPATCH_CURVE(curve, point_runs, E, d_base_packed, d_start_scalars, runs, run_len, d_out_packed, st);
     if (rc) return rc;
     ENGINE_MARK(st);
     return B200_OK;
@@ -557,6 +572,33 @@ int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void 
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
     ENGINE_ORDER(st);
     return groth16_prove(E, family, pk, d_assignment, num_assign, num_aux, d_a, d_b, d_c, log_n, d_proof, st);
+}
+
+int b200_groth16_prove_partial_device(int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
+                                      size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, unsigned shard,
+                                      unsigned shards, void *d_partials, void *stream) {
+    if (family != B200_GROTH16_BLS12_377 && family != B200_GROTH16_BW6_761) return fail(B200_ERR_ARG, "unknown Groth16 family %d", family);
+    if (!pk || !pk->a_query || !pk->b_g2_query || !pk->h_query || !d_a || !d_b || !d_c || !d_partials ||
+        (num_assign && !d_assignment) || (num_aux && !pk->l_query))
+        return fail(B200_ERR_ARG, "null pointer");
+    if (num_aux > num_assign) return fail(B200_ERR_ARG, "num_aux exceeds num_assign");
+    if (log_n == 0 || log_n > 26) return fail(B200_ERR_ARG, "log_n = %u out of range [1, 26]", log_n);
+    if (shards == 0 || shard >= shards) return fail(B200_ERR_ARG, "shard %u of %u", shard, shards);
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    ENGINE_ORDER(st);
+    return groth16_partial(E, family, pk, d_assignment, num_assign, num_aux, d_a, d_b, d_c, log_n, shard, shards, d_partials, st);
+}
+
+int b200_groth16_assemble_device(int family, const b200_groth16_pk *pk, const void *d_partials, unsigned shards, void *d_proof,
+                                 void *stream) {
+    if (family != B200_GROTH16_BLS12_377 && family != B200_GROTH16_BW6_761) return fail(B200_ERR_ARG, "unknown Groth16 family %d", family);
+    if (!pk || !pk->a_query || !pk->b_g2_query || !pk->alpha_g1 || !pk->beta_g2 || !d_partials || !d_proof || shards == 0)
+        return fail(B200_ERR_ARG, "null pointer / no shards");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    ENGINE_ORDER(st);
+    return groth16_assemble(E, family, pk, d_partials, shards, d_proof, st);
 }
 
 int b200_field_op_device(int curve, int op, const void *d_a, const void *d_b, size_t n, void *d_out, void *stream) {

@@ -102,7 +102,7 @@ struct Engine {
     // NTT domains: [0] BLS12-377 Fr, [1] BW6-761 Fr (= BLS12-377 Fq)
     NttDomain ntt[2];
     // Groth16 prover composite (inst_groth16.cu): quotient coefficients h, partial MSM results
-    Buffer g16_h, g16_tmp;
+    Buffer g16_h, g16_tmp, g16_part;
     // batch-verification composites (inst_verify.cu)
     Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff, v_sum;
     // hash-to-G1 (inst_hash.cu): affine multiples of the Bowe-Hopwood generators (built at first use), per-call staging
@@ -127,6 +127,7 @@ template <class C> int msm_batch(Engine &E, const b200_msm_job *jobs, size_t cou
 template <class C> int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStream_t st);
 template <class C> int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st);
 template <class C> int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st);
+template <class C> int point_runs(Engine &E, const void *base, const void *scalars, size_t runs, size_t run, void *out, cudaStream_t st);
 template <class C> int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st);
 template <class C> int plan_query(size_t n, int *c, int *w, uint32_t *nb);
 template <class C> int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStream_t st);
@@ -140,6 +141,10 @@ int witness_map(Engine &E, int field, void *a, void *b, void *c, int log_n, void
 // Groth16 prover arithmetic (inst_groth16.cu)
 int groth16_prove(Engine &E, int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
                   size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_proof, cudaStream_t st);
+int groth16_partial(Engine &E, int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign, size_t num_aux,
+                    void *d_a, void *d_b, void *d_c, unsigned log_n, unsigned shard, unsigned shards, void *d_partials, cudaStream_t st);
+int groth16_assemble(Engine &E, int family, const b200_groth16_pk *pk, const void *d_partials, unsigned shards, void *d_proof,
+                     cudaStream_t st);
 // BW6-761 pairing / Groth16 verification (inst_bw6_pairing.cu)
 int bw6_miller_values(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_vals, cudaStream_t st);
 int bw6_final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_is_one, cudaStream_t st);

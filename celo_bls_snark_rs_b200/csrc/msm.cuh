@@ -727,6 +727,34 @@ __global__ void __launch_bounds__(THREADS) k_fixed_base_mul(const AffineMem<F> *
     out[i] = r.store();
 }
 
+// out[t * run + j] = (scalars[t] + j) * base for j < run: `run` consecutive multiples behind one double-and-add, so a
+// synthetic base array of 2^24 distinct points costs ~1 / run of k_fixed_base_mul (bench.py, configs 4 and 5)
+template <class F, int SW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_point_runs(const AffineMem<F> *__restrict__ base,
+                                                        const uint32_t *__restrict__ scalars, uint32_t runs, uint32_t run,
+                                                        XYZZMem<F> *__restrict__ out) {
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    if (t >= runs) return;
+    Affine<F> g = Affine<F>::from_ark(ldg_mem(base));
+    XYZZ<F> r = XYZZ<F>::inf();
+    for (int w = SW - 1; w >= 0; w--) {
+        uint32_t word = __ldg(scalars + (size_t)t * SW + w);
+        for (int b = 31; b >= 0; b--) {
+            r.dbl();
+            launder(r);
+            if ((word >> b) & 1u) {
+                r.madd(g.x, g.y);
+                launder(r);
+            }
+        }
+    }
+    for (uint32_t j = 0; j < run; j++) {
+        out[(size_t)t * run + j] = r.store();
+        r.madd(g.x, g.y);
+        launder(r);
+    }
+}
+
 }  // namespace b200
 
 namespace b200 {

@@ -28,11 +28,11 @@ PACKED_STRIDE = {k: 2 * v for k, v in COORD_BYTES.items()}
 EXPORTS = [
     "b200_init", "b200_shutdown", "b200_last_error", "b200_msm", "b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2",
     "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device", "b200_msm_prepared_device",
-    "b200_sum_jacobian_device", "b200_sum_jacobian", "b200_fixed_base_mul_device", "b200_batch_to_affine_device", "b200_sync",
+    "b200_sum_jacobian_device", "b200_sum_jacobian", "b200_fixed_base_mul_device", "b200_point_runs_device", "b200_batch_to_affine_device", "b200_sync",
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
     "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
-    "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_msm_batch_device",
+    "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_groth16_prove_partial_device", "b200_groth16_assemble_device", "b200_msm_batch_device",
     "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
     "b200_groth16_verify_bw6_761", "b200_deserialize_points", "b200_verify_epochs", "b200_epoch_public_inputs",
     "b200_blake2s_personal", "b200_hash_to_g1", "b200_serialize_points", "b200_ensure_init", "b200_bound_device",
@@ -118,6 +118,7 @@ def load() -> ctypes.CDLL:
     lib.b200_sum_jacobian_device.argtypes = [i32, vp, sz, vp, vp]
     lib.b200_sum_jacobian.argtypes = [i32, vp, sz, vp]
     lib.b200_fixed_base_mul_device.argtypes = [i32, vp, vp, sz, vp, vp]
+    lib.b200_point_runs_device.argtypes = [i32, vp, vp, sz, sz, vp, vp]
     lib.b200_batch_to_affine_device.argtypes = [i32, vp, sz, vp, vp]
     lib.b200_field_op_device.argtypes = [i32, i32, vp, vp, sz, vp, vp]
     lib.b200_multi_pairing_bls12_377.argtypes = [vp, sz, vp, sz, sz, vp, ctypes.POINTER(i32)]
@@ -141,6 +142,9 @@ def load() -> ctypes.CDLL:
     lib.b200_ntt_device.argtypes = [i32, vp, ctypes.c_uint, i32, i32, vp]
     lib.b200_witness_map_device.argtypes = [i32, vp, vp, vp, ctypes.c_uint, vp, vp]
     lib.b200_groth16_prove_device.argtypes = [i32, ctypes.POINTER(Groth16Pk), vp, sz, sz, vp, vp, vp, ctypes.c_uint, vp, vp]
+    lib.b200_groth16_prove_partial_device.argtypes = [i32, ctypes.POINTER(Groth16Pk), vp, sz, sz, vp, vp, vp, ctypes.c_uint,
+                                                      ctypes.c_uint, ctypes.c_uint, vp, vp]
+    lib.b200_groth16_assemble_device.argtypes = [i32, ctypes.POINTER(Groth16Pk), vp, ctypes.c_uint, vp, vp]
     lib.b200_msm_batch_device.argtypes = [i32, ctypes.POINTER(MsmJob), sz, vp]
     lib.b200_hash_to_g1.argtypes = [i32, i32, ctypes.c_char_p, sz, ctypes.POINTER(HashInput), sz, vp, vp]
     lib.b200_serialize_points.argtypes = [i32, vp, sz, vp]
@@ -234,6 +238,11 @@ def sum_jacobian_device(curve: int, d_points: int, count: int, d_out: int, strea
 
 def fixed_base_mul_device(curve: int, d_base: int, d_scalars: int, n: int, d_out: int, stream: int = 0):
     _check(load().b200_fixed_base_mul_device(curve, d_base, d_scalars, n, d_out, stream or None))
+
+
+def point_runs_device(curve: int, d_base: int, d_start_scalars: int, runs: int, run_len: int, d_out: int, stream: int = 0):
+    """d_out[t * run_len + j] = (start[t] + j) * base as packed affine records (b200_point_runs_device)."""
+    _check(load().b200_point_runs_device(curve, d_base, d_start_scalars, runs, run_len, d_out, stream or None))
 
 
 def batch_to_affine_device(curve: int, d_jac: int, n: int, d_out: int, stream: int = 0):
@@ -447,6 +456,23 @@ def groth16_prove_device(family: int, pk: "Groth16Pk", d_assignment: int, num_as
     """Groth16 prover arithmetic after synthesis (witness map + 4 MSMs + assembly); d_proof = A | B | C Jacobian."""
     _check(load().b200_groth16_prove_device(family, ctypes.byref(pk), d_assignment or None, num_assign, num_aux, d_a, d_b, d_c,
                                             log_n, d_proof, stream or None))
+
+
+def groth16_partial_bytes(family: int) -> int:
+    """size of one shard's record a_acc | l_acc | h_acc | b_acc"""
+    return 3 * 144 + 288 if family == GROTH16_BLS12_377 else 4 * 288
+
+
+def groth16_prove_partial_device(family: int, pk: "Groth16Pk", d_assignment: int, num_assign: int, num_aux: int, d_a: int,
+                                 d_b: int, d_c: int, log_n: int, shard: int, shards: int, d_partials: int, stream: int = 0):
+    """One GPU's share of a proof: witness map + its slice of each MSM -> d_partials (groth16_partial_bytes)."""
+    _check(load().b200_groth16_prove_partial_device(family, ctypes.byref(pk), d_assignment or None, num_assign, num_aux, d_a,
+                                                    d_b, d_c, log_n, shard, shards, d_partials, stream or None))
+
+
+def groth16_assemble_device(family: int, pk: "Groth16Pk", d_partials: int, shards: int, d_proof: int, stream: int = 0):
+    """`shards` gathered partial records (rank-major) -> A | B | C."""
+    _check(load().b200_groth16_assemble_device(family, ctypes.byref(pk), d_partials, shards, d_proof, stream or None))
 
 
 def profile_enable(on: bool = True):

@@ -17,6 +17,14 @@ import torch.distributed as dist
 from . import engine as E
 
 
+def _current_stream(device) -> int:
+    """torch's current stream on `device`: NCCL collectives are issued there, so the engine calls around them must be
+    too (stream 0 would select the engine's private non-blocking stream, unordered with NCCL)."""
+    if torch.device(device).type != "cuda":
+        return 0
+    return torch.cuda.current_stream(device).cuda_stream or 1      # 1 = cudaStreamLegacy: torch's default stream, by handle
+
+
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous chunk [lo, hi) of rank `rank`; the first n % world ranks get one extra pair."""
     if world <= 0 or not (0 <= rank < world):
@@ -49,6 +57,7 @@ class ShardedMsm:
     def run(self, d_bases: torch.Tensor, d_scalars: torch.Tensor, n_local: int, stream: int = 0) -> torch.Tensor:
         """Local MSM over this rank's chunk, exchange, combine.  Asynchronous on `stream`
         (which must be torch's current stream so NCCL orders after the MSM)."""
+        stream = stream or _current_stream(self.device)
         E.msm_device(self.curve, d_bases.data_ptr(), d_scalars.data_ptr(), n_local, self.partial.data_ptr(), stream)
         if self.world == 1:
             return self.partial
@@ -61,6 +70,7 @@ class ShardedMsm:
         through the engine's pipelined batch entry (sort / accumulate / tail of consecutive MSMs
         overlap), then every MSM gets its own all-gather + sum, as in run().  Returns uint8
         [len(jobs), jac_bytes] results (the partials themselves when world == 1)."""
+        stream = stream or _current_stream(self.device)
         jb = E.JAC_BYTES[self.curve]
         k = len(jobs)
         if getattr(self, "_batch_k", 0) < k:
@@ -96,6 +106,7 @@ class ShardedPairing:
     def run(self, d_g1: torch.Tensor, d_g2: torch.Tensor, n_local: int, stream: int = 0):
         """d_g1 / d_g2: this rank's packed affine records (96 / 192 bytes each).  Returns (gt, is_one)
         device tensors, asynchronous on `stream` (torch's current stream, so NCCL orders after it)."""
+        stream = stream or _current_stream(self.device)
         E.miller_product_device(d_g1.data_ptr() if n_local else 0, d_g2.data_ptr() if n_local else 0, n_local,
                                 self.partial.data_ptr(), stream)
         vals = self.partial
@@ -146,3 +157,32 @@ class ShardedHashToG1:
             torch.zeros(0, dtype=torch.uint8, device=self.device)
         flat = gather_ragged(local, n, 144, self.group).cpu().numpy().tobytes()
         return [flat[144 * i:144 * (i + 1)] for i in range(n)]
+
+
+class ShardedGroth16:
+    """Groth16 prover arithmetic split over the ranks (BASELINE config 5: "8 x B200"; crates/epoch-snark/src/api/prover.rs:78,112).
+    Every rank holds the whole proving key and witness (as a prover node does), runs the witness map and its contiguous
+    share of the four MSMs (b200_groth16_prove_partial_device), the ONE exchange is an all-gather of the 4-point partial
+    records, and every rank assembles A | B | C from them (b200_groth16_assemble_device)."""
+
+    def __init__(self, family: int, device: torch.device, group=None):
+        self.family, self.device, self.group = family, device, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        pb = E.groth16_partial_bytes(family)
+        self.partial = torch.zeros(pb, dtype=torch.uint8, device=device)
+        self.gathered = torch.zeros(self.world * pb, dtype=torch.uint8, device=device)
+        self.proof = torch.zeros(2 * (144 if family == E.GROTH16_BLS12_377 else 288) + 288, dtype=torch.uint8, device=device)
+
+    def run(self, pk, d_assign: torch.Tensor, num_assign: int, num_aux: int, d_a: torch.Tensor, d_b: torch.Tensor,
+            d_c: torch.Tensor, log_n: int, stream: int = 0) -> torch.Tensor:
+        """Asynchronous on `stream` (torch's current stream, so NCCL orders after the local share)."""
+        stream = stream or torch.cuda.current_stream().cuda_stream
+        E.groth16_prove_partial_device(self.family, pk, d_assign.data_ptr(), num_assign, num_aux, d_a.data_ptr(), d_b.data_ptr(),
+                                       d_c.data_ptr(), log_n, self.rank, self.world, self.partial.data_ptr(), stream)
+        vals = self.partial
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.partial, group=self.group)
+            vals = self.gathered
+        E.groth16_assemble_device(self.family, pk, vals.data_ptr(), self.world, self.proof.data_ptr(), stream)
+        return self.proof

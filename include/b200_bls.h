@@ -119,6 +119,11 @@ int b200_sum_jacobian(int curve, const void *points, size_t count, void *out_jac
 int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void *d_scalars, size_t n,
                                void *d_out_packed, void *stream);
 
+/* d_out_packed[t * run_len + j] = (start_scalars[t] + j) * base: runs of consecutive multiples (one double-and-add per
+ * run).  Synthetic base arrays of 2^22 .. 2^24 distinct points for the benchmarks at ~1 / run_len of the cost above. */
+int b200_point_runs_device(int curve, const void *d_base_packed, const void *d_start_scalars, size_t runs, size_t run_len,
+                           void *d_out_packed, void *stream);
+
 /* Jacobian -> affine with Montgomery batch inversion; replaces
  * ProjectiveCurve::batch_normalization_into_affine (signature.rs:82, public.rs:58).
  * d_out_packed receives packed affine records, infinity as (0, 0). */
@@ -230,6 +235,15 @@ typedef struct {
 int b200_groth16_prove_device(int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
                               size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, void *d_proof,
                               void *stream);
+/* The same proof split over `shards` GPUs (BASELINE config 5: "8 x B200"): every GPU runs the witness map and its
+ * contiguous share of each of the four MSMs -> d_partials = a_acc | l_acc | h_acc | b_acc (3 G1 + 1 G2
+ * GroupProjective images: 3 * 144 + 288 or 4 * 288 bytes); the single exchange is an all-gather of those records;
+ * b200_groth16_assemble_device folds `shards` records (rank-major) into A | B | C.  shards = 1 is the call above. */
+int b200_groth16_prove_partial_device(int family, const b200_groth16_pk *pk, const void *d_assignment, size_t num_assign,
+                                      size_t num_aux, void *d_a, void *d_b, void *d_c, unsigned log_n, unsigned shard,
+                                      unsigned shards, void *d_partials, void *stream);
+int b200_groth16_assemble_device(int family, const b200_groth16_pk *pk, const void *d_partials, unsigned shards, void *d_proof,
+                                 void *stream);
 
 /* ---- BW6-761 product of pairings and Groth16 verification -------------------------------------------
  * Replaces BW6_761::product_of_pairings as reached from ark-groth16 0.1.0 verify_proof at

@@ -115,7 +115,7 @@ LAYOUTS = {name: CurveLayout(c) for name, c in O.CURVES.items()}
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_SO) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
-            for f in ("cpu_ref.c", "fp_tmpl.h", "ec_tmpl.h")):
+            for f in ("cpu_ref.c", "fp_tmpl.h", "ec_tmpl.h", "pairing_tmpl.h", "ntt_tmpl.h")):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return _SO
 
