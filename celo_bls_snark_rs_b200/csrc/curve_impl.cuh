@@ -107,24 +107,24 @@ static int msm_reserve(MsmWs &W, const MsmPlan &p, size_t n) {
     int rc;
     if ((rc = W.counts.reserve(total * 4)) || (rc = W.offsets.reserve((total + 1) * 4)) ||
         (rc = W.cursor.reserve(total * 4)) || (rc = W.tile_sums.reserve((size_t)tiles * 4)) ||
-        (rc = W.bins.reserve(2 * SIZE_BINS * 4)) || (rc = W.order.reserve(total * 4)) ||
+        (rc = W.bins.reserve(4 * SIZE_BINS * 4)) || (rc = W.order.reserve(total * 4)) ||
         (rc = W.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = W.buckets.reserve(total * sizeof(XYZZMem<F>))) ||
         (rc = W.partials.reserve(((size_t)p.windows * p.segs + ONES_PARTS) * sizeof(XYZZMem<F>))) ||
-        (rc = W.window_sums.reserve((size_t)(p.windows + 1) * sizeof(XYZZMem<F>))) ||
+        (rc = W.window_sums.reserve((size_t)(p.windows + 2) * sizeof(XYZZMem<F>))) ||
         (rc = W.ones.reserve((n + 1) * 4)) || (rc = W.huge_slices.reserve(max_huge * HUGE_SLICES * sizeof(XYZZMem<F>))))
         return rc;
     return B200_OK;
 }
 
 template <class C>
-static int msm_stage_sort(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_scalars, size_t n, cudaStream_t st) {
+static int msm_stage_sort(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_scalars, size_t n, cudaStream_t st, int split = 0) {
     size_t total = (size_t)p.windows * p.nb;
     uint32_t tiles = (uint32_t)ceil_div(total, SCAN_TILE);
     const uint32_t *sc = reinterpret_cast<const uint32_t *>(d_scalars);
     uint32_t *counts = W.counts.as<uint32_t>(), *offsets = W.offsets.as<uint32_t>(), *cursor = W.cursor.as<uint32_t>();
     uint32_t *bins = W.bins.as<uint32_t>();
     CUDA_TRY(cudaMemsetAsync(counts, 0, total * 4, st));
-    CUDA_TRY(cudaMemsetAsync(bins, 0, 2 * SIZE_BINS * 4, st));
+    CUDA_TRY(cudaMemsetAsync(bins, 0, 4 * SIZE_BINS * 4, st));
     CUDA_TRY(cudaMemsetAsync(W.ones.p, 0, 4, st));
     int nblk = ceil_div(n, 256);
     k_digit_hist<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, counts);
@@ -137,34 +137,52 @@ static int msm_stage_sort(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_s
     LAUNCH_CHECK();
     k_digit_scatter<C::SCALAR_WORDS><<<nblk, 256, 0, st>>>(sc, p, cursor, W.sorted.as<uint32_t>(), W.ones.as<uint32_t>());
     LAUNCH_CHECK();
-    k_size_hist<<<std::min(ceil_div(total, 256), E.sm_count * 4), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins);
-    LAUNCH_CHECK();
-    k_size_scan<<<1, SIZE_BINS, 0, st>>>(bins, bins + SIZE_BINS);
-    LAUNCH_CHECK();
-    k_size_scatter<<<ceil_div(total, 256), 256, 0, st>>>(counts, (uint32_t)total, p.big, bins + SIZE_BINS,
-                                                         W.order.as<uint32_t>());
-    LAUNCH_CHECK();
+    // population order, separately for the buckets of windows [split, windows) -- group A, first in `order` -- and of
+    // windows [0, split) -- group B (split = 0: one group)
+    const size_t total_b = (size_t)split * p.nb, total_a = total - total_b;
+    for (int g = 0; g < 2; g++) {
+        const size_t cnt = g ? total_b : total_a, first = g ? 0 : total_b;     // bucket range of the group
+        if (cnt == 0) continue;
+        uint32_t *gb = bins + (size_t)g * 2 * SIZE_BINS;
+        k_size_hist<<<std::min(ceil_div(cnt, 256), E.sm_count * 4), 256, 0, st>>>(counts + first, (uint32_t)cnt, p.big, gb);
+        LAUNCH_CHECK();
+        k_size_scan<<<1, SIZE_BINS, 0, st>>>(gb, gb + SIZE_BINS);
+        LAUNCH_CHECK();
+        k_size_scatter<<<ceil_div(cnt, 256), 256, 0, st>>>(counts + first, (uint32_t)cnt, p.big, gb + SIZE_BINS,
+                                                           W.order.as<uint32_t>() + (g ? total_a : 0), (uint32_t)first);
+        LAUNCH_CHECK();
+    }
     return B200_OK;
 }
 
+// W: the sort buffers of this input (chunk); B: the workspace holding the buckets and the unit-scalar partials (B is W
+// for a whole-input MSM; the host-pointer MSM sorts chunk by chunk and resumes ONE bucket set: resume = not the first chunk)
+// split / group: the sort stage ordered the buckets of windows [split, windows) (group 0) and [0, split) (group 1)
+// separately; group = -1 takes everything in one launch (split must be 0), 0 / 1 one group (unit scalars ride with group 0)
 template <class C>
-static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_bases, size_t n, cudaStream_t st) {
+static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_bases, size_t n, cudaStream_t st,
+                                MsmWs *Bp = nullptr, int resume = 0, int split = 0, int group = -1) {
     using F = typename C::F;
     using T = CurveTraits<C>;
-    size_t total = (size_t)p.windows * p.nb;
+    MsmWs &B = Bp ? *Bp : W;
+    const size_t all = (size_t)p.windows * p.nb, total_b = (size_t)split * p.nb, total_a = all - total_b;
+    const size_t total = group < 0 ? all : (group ? total_b : total_a);
+    const size_t pts = group < 0 ? n * (size_t)p.windows : n * (size_t)(group ? split : p.windows - split);   // sorted entries of the group
+    const uint32_t *order = W.order.as<uint32_t>() + (group == 1 ? total_a : 0);
     const AffineMem<F> *bases = reinterpret_cast<const AffineMem<F> *>(d_bases);
-    uint32_t *offsets = W.offsets.as<uint32_t>(), *bins = W.bins.as<uint32_t>();
-    bool prof = E.profile && E.prof_used < Engine::PROF_SLOTS;
+    uint32_t *offsets = W.offsets.as<uint32_t>(), *bins = W.bins.as<uint32_t>() + (group == 1 ? 2 * SIZE_BINS : 0);
+    if (total == 0) return B200_OK;
+    bool prof = group < 0 && E.profile && E.prof_used < Engine::PROF_SLOTS;    // window groups: timed by msm_split_run
     if (prof) CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used], st));
     size_t ra, rb;
     bool affine = false;
-    if constexpr (T::AFFINE) affine = msm_use_affine<C>(p, n, &ra, &rb);
+    if constexpr (T::AFFINE) affine = !resume && msm_use_affine<C>(p, n, &ra, &rb);
     if constexpr (T::AFFINE) {
         if (affine) {
             static const int variant = getenv("B200_AFFINE_VARIANT") ? atoi(getenv("B200_AFFINE_VARIANT")) : 0;
             AffineMem<F> *sa = W.aff_a.as<AffineMem<F>>(), *sb = W.aff_b.as<AffineMem<F>>();
-            const uint32_t *so = W.sorted.as<uint32_t>(), *ord = W.order.as<uint32_t>();
-            XYZZMem<F> *bk = W.buckets.as<XYZZMem<F>>();
+            const uint32_t *so = W.sorted.as<uint32_t>(), *ord = order;
+            XYZZMem<F> *bk = B.buckets.as<XYZZMem<F>>();
 #define B200_AFF_LAUNCH(TH, MB, BB, CC, BI)                                                                          \
     k_bucket_accumulate_affine<F, TH, MB, BB, CC, BI><<<ceil_div(total, TH), TH, 0, st>>>(bases, so, offsets, ord,      \
                                                                                           (uint32_t)total, p.big, sa, sb, bk)
@@ -182,13 +200,13 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
     if (!affine && shared_mul && T::AFFINE)
         k_bucket_accumulate_shared<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
             <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
-                bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), (uint32_t)total, p.big,
-                W.buckets.as<XYZZMem<F>>());
+                bases, W.sorted.as<uint32_t>(), offsets, order, (uint32_t)total, p.big, resume,
+                B.buckets.as<XYZZMem<F>>());
     else if (!affine)
         k_bucket_accumulate<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
             <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
-                bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), (uint32_t)total, p.big,
-                W.buckets.as<XYZZMem<F>>());
+                bases, W.sorted.as<uint32_t>(), offsets, order, (uint32_t)total, p.big, resume,
+                B.buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     if (prof) {
         CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));
@@ -197,19 +215,40 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
     }
     // over-populated buckets (skewed scalars) and unit scalars: bounded extra launches
     constexpr int BT = T::RED_THREADS;                             // smem: BT XYZZ images (<= 24.5 KB)
-    uint32_t max_big = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / p.big + 1);
-    uint32_t max_huge = (uint32_t)std::min<size_t>(total, n * (size_t)p.windows / HUGE_BUCKET + 1);
+    uint32_t max_big = (uint32_t)std::min<size_t>(total, pts / p.big + 1);
+    uint32_t max_huge = (uint32_t)std::min<size_t>(total, pts / HUGE_BUCKET + 1);
     k_big_buckets<F, BT><<<std::min<uint32_t>(max_big, (uint32_t)E.sm_count * 16), BT, BT * sizeof(XYZZMem<F>), st>>>(
-        bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), bins, p.big, W.buckets.as<XYZZMem<F>>());
+        bases, W.sorted.as<uint32_t>(), offsets, order, bins, p.big, resume, B.buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     k_huge_buckets<F, BT><<<dim3(max_huge, HUGE_SLICES), BT, BT * sizeof(XYZZMem<F>), st>>>(
-        bases, W.sorted.as<uint32_t>(), offsets, W.order.as<uint32_t>(), bins, p.big, W.huge_slices.as<XYZZMem<F>>());
+        bases, W.sorted.as<uint32_t>(), offsets, order, bins, p.big, W.huge_slices.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     k_huge_finish<F, BT><<<ceil_div((size_t)max_huge * 4, BT), BT, 0, st>>>(
-        W.huge_slices.as<XYZZMem<F>>(), offsets, W.order.as<uint32_t>(), bins, p.big, max_huge, W.buckets.as<XYZZMem<F>>());
+        W.huge_slices.as<XYZZMem<F>>(), offsets, order, bins, p.big, max_huge, resume, B.buckets.as<XYZZMem<F>>());
     LAUNCH_CHECK();
-    k_ones_accumulate<F, BT><<<ONES_PARTS / BT, BT, 0, st>>>(bases, W.ones.as<uint32_t>(),
-                                                             W.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs);
+    if (group <= 0) {
+        k_ones_accumulate<F, BT><<<ONES_PARTS / BT, BT, 0, st>>>(bases, W.ones.as<uint32_t>(), resume,
+                                                                 B.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs);
+        LAUNCH_CHECK();
+    }
+    return B200_OK;
+}
+
+// bucket reduce + window sums of windows [w_lo, w_hi) (with_ones: also the unit-scalar partials -> window_sums[windows])
+template <class C>
+static int msm_stage_reduce(MsmWs &W, const MsmPlan &p, int w_lo, int w_hi, bool with_ones, cudaStream_t st) {
+    using F = typename C::F;
+    using T = CurveTraits<C>;
+    uint32_t red_threads = (uint32_t)(w_hi - w_lo) * p.segs * 4;   // one quad per segment
+    if (red_threads) {
+        k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
+            W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi, W.partials.as<XYZZMem<F>>());
+        LAUNCH_CHECK();
+    }
+    constexpr int WS_THREADS = 256;                                // 64 quads per window
+    size_t ws_smem = (WS_THREADS / 4) * sizeof(XYZZMem<F>);
+    k_window_sum<F, WS_THREADS><<<(w_hi - w_lo) + (with_ones ? 1 : 0), WS_THREADS, ws_smem, st>>>(
+        W.partials.as<XYZZMem<F>>(), p, w_lo, w_hi, W.window_sums.as<XYZZMem<F>>());
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -217,16 +256,8 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
 template <class C>
 static int msm_stage_tail(MsmWs &W, const MsmPlan &p, void *d_out, cudaStream_t st) {
     using F = typename C::F;
-    using T = CurveTraits<C>;
-    uint32_t red_threads = (uint32_t)p.windows * p.segs * 4;      // one quad per segment
-    k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
-        W.buckets.as<XYZZMem<F>>(), p, W.partials.as<XYZZMem<F>>());
-    LAUNCH_CHECK();
-    constexpr int WS_THREADS = 256;                                // 64 quads per window
-    size_t ws_smem = (WS_THREADS / 4) * sizeof(XYZZMem<F>);
-    k_window_sum<F, WS_THREADS><<<p.windows + 1, WS_THREADS, ws_smem, st>>>(W.partials.as<XYZZMem<F>>(), p,
-                                                                        W.window_sums.as<XYZZMem<F>>());
-    LAUNCH_CHECK();
+    int rc = msm_stage_reduce<C>(W, p, 0, p.windows, true, st);
+    if (rc) return rc;
     // Horner over the windows: four warps share every point operation (coop.cuh); B200_COMBINE_QUAD=1 selects the
     // one-quad kernel it replaced (cross-check)
     static const bool quad_combine = getenv("B200_COMBINE_QUAD") && atoi(getenv("B200_COMBINE_QUAD"));
@@ -236,6 +267,64 @@ static int msm_stage_tail(MsmWs &W, const MsmPlan &p, void *d_out, cudaStream_t 
         k_window_combine_coop<F><<<1, COOP_THREADS, 0, st>>>(W.window_sums.as<XYZZMem<F>>(), 0, p.windows, p.c, 0,
                                                              W.window_sums.as<XYZZMem<F>>() + p.windows, nullptr,
                                                              reinterpret_cast<JacobianMem<F> *>(d_out), nullptr);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// ---- window groups: the tail of the high windows hides under the accumulation of the low ones ---------------
+// The tail (bucket reduce, window sums, Horner) is latency-bound and leaves the multiplier pipe idle; a single MSM
+// used to pay it in full after the accumulation (1.6 of 8.3 ms at n = 2^20, 14 of 47 ms for BW6-761).  The windows
+// are therefore cut in two groups: group A = windows [split, W) is bucketed first, its tail -- including the
+// split * c doublings that carry its Horner value down to weight 2^0 -- runs on the high-priority tail stream while
+// group B = windows [0, split) is still being bucketed; only B's short tail (split windows, (split - 1) * c doublings)
+// and one addition remain exposed.  Both groups' accumulate kernels are in flight together (A launched first), so B's
+// blocks fill the SMs as A's drain.
+template <class C>
+static int msm_split_of(const MsmPlan &p, size_t n) {
+    static const int forced = getenv("B200_MSM_SPLIT") ? atoi(getenv("B200_MSM_SPLIT")) : -1;
+    if (forced >= 0) return std::min(forced, p.windows - 1);
+    if (n < ((size_t)1 << 15) || p.windows < 6) return 0;         // small inputs: launch latency dominates, keep one group
+    return std::max(2, p.windows / 4);
+}
+
+// sort buffers in W (already sorted with the same `split`), buckets in B; everything ordered after `st`'s prior work and
+// joined back into it.  resume: the buckets hold the sums of earlier chunks.
+template <class C>
+static int msm_split_run(Engine &E, MsmWs &W, MsmWs &B, const MsmPlan &p, int split, const void *d_bases, size_t n, int resume,
+                         void *d_out, cudaStream_t st) {
+    using F = typename C::F;
+    int rc;
+    if (split == 0) {
+        if ((rc = msm_stage_accumulate<C>(E, W, p, d_bases, n, st, &B, resume))) return rc;
+        return msm_stage_tail<C>(B, p, d_out, st);
+    }
+    cudaStream_t s_a = E.split_stream, s_t = E.pipe_stream[2];
+    const bool prof = E.profile && E.prof_used < Engine::PROF_SLOTS;
+    if (prof) CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used], st));
+    CUDA_TRY(cudaEventRecord(E.ev_split[0], st));
+    CUDA_TRY(cudaStreamWaitEvent(s_a, E.ev_split[0], 0));
+    if ((rc = msm_stage_accumulate<C>(E, W, p, d_bases, n, s_a, &B, resume, split, 0))) return rc;     // group A first
+    CUDA_TRY(cudaEventRecord(E.ev_split[1], s_a));
+    if ((rc = msm_stage_accumulate<C>(E, W, p, d_bases, n, st, &B, resume, split, 1))) return rc;      // group B beside it
+    if (prof) {
+        CUDA_TRY(cudaStreamWaitEvent(st, E.ev_split[1], 0));       // the timed span covers both groups' kernels
+        CUDA_TRY(cudaEventRecord(E.prof_ev[2 * E.prof_used + 1], st));
+        E.prof_used++;
+        E.prof_units += n;
+    }
+    // tail of group A on the tail stream: value carried down by split * c doublings, unit scalars added -> XYZZ in window_sums[windows + 1]
+    XYZZMem<F> *ws = B.window_sums.as<XYZZMem<F>>();
+    CUDA_TRY(cudaStreamWaitEvent(s_t, E.ev_split[1], 0));
+    if ((rc = msm_stage_reduce<C>(B, p, split, p.windows, true, s_t))) return rc;
+    k_window_combine_coop<F><<<1, COOP_THREADS, 0, s_t>>>(ws, split, p.windows, p.c, split * p.c, ws + p.windows, nullptr, nullptr,
+                                                          ws + p.windows + 1);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaEventRecord(E.ev_split[2], s_t));
+    // tail of group B, then the sum of the two
+    if ((rc = msm_stage_reduce<C>(B, p, 0, split, false, st))) return rc;
+    CUDA_TRY(cudaStreamWaitEvent(st, E.ev_split[2], 0));
+    k_window_combine_coop<F><<<1, COOP_THREADS, 0, st>>>(ws, 0, split, p.c, 0, ws + p.windows + 1, nullptr,
+                                                         reinterpret_cast<JacobianMem<F> *>(d_out), nullptr);
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -255,9 +344,9 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
     int rc;
     if ((rc = msm_reserve<C>(W, p, n))) return rc;
     ENGINE_ORDER(st);
-    if ((rc = msm_stage_sort<C>(E, W, p, d_scalars, n, st))) return rc;
-    if ((rc = msm_stage_accumulate<C>(E, W, p, d_bases, n, st))) return rc;
-    if ((rc = msm_stage_tail<C>(W, p, d_out, st))) return rc;
+    const int split = msm_split_of<C>(p, n);
+    if ((rc = msm_stage_sort<C>(E, W, p, d_scalars, n, st, split))) return rc;
+    if ((rc = msm_split_run<C>(E, W, W, p, split, d_bases, n, 0, d_out, st))) return rc;
     ENGINE_MARK(st);
     return B200_OK;
 }
@@ -309,6 +398,77 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
         k++;
     }
     CUDA_TRY(cudaEventRecord(E.ev_join, s_tail));                  // the tail stream is last in every chain
+    CUDA_TRY(cudaStreamWaitEvent(st, E.ev_join, 0));
+    ENGINE_MARK(st);
+    return B200_OK;
+}
+
+// ---- one MSM fed chunk by chunk (the host-pointer path) -------------------------------------------------
+// The input crosses PCIe in chunks; chunk k is sorted by window digit and bucketed as soon as it has landed,
+// into ONE bucket set that the following chunks resume, and the tail runs once at the end: copies hide behind
+// the bucket accumulation of earlier chunks without paying one tail per chunk.  Window width follows the whole
+// input.  Sort buffers alternate between the two workspace sets (the sort of chunk k + 1 runs beside the
+// accumulation of chunk k); buckets and unit-scalar partials live in set 0.
+//   begin(total)  ->  add(d_bases, d_scalars, cnt, ready) per chunk  ->  finish(d_out) joins everything into `st`
+template <class C>
+int msm_chunks_begin(Engine &E, size_t n_total, size_t chunk_max, cudaStream_t st) {
+    if (n_total > (size_t)1 << 26) return fail(B200_ERR_ARG, "n = %zu exceeds the 2^26 per-call limit", n_total);
+    E.chunk_plan = make_plan<C>(n_total);
+    E.chunk_index = 0;
+    E.chunk_done = false;
+    MsmPlan p = E.chunk_plan;
+    int rc;
+    // bucket-side buffers sized by the plan (set 0), sort-side buffers by the largest chunk (both sets)
+    if ((rc = msm_reserve<C>(E.ws[0], p, chunk_max)) || (rc = msm_reserve<C>(E.ws[1], p, chunk_max))) return rc;
+    cudaStream_t s_sort = E.pipe_stream[0], s_acc = E.pipe_stream[1];
+    CUDA_TRY(cudaEventRecord(E.ev_fork, st));
+    for (cudaStream_t s : {s_sort, s_acc}) CUDA_TRY(cudaStreamWaitEvent(s, E.ev_fork, 0));
+    return B200_OK;
+}
+
+// last: the final chunk -- its accumulation runs in two window groups and the tail of the high group hides under the
+// low group's accumulation (msm_split_run); msm_chunks_finish then only joins
+template <class C>
+int msm_chunks_add(Engine &E, const void *d_bases_packed, const void *d_scalars, size_t cnt, cudaEvent_t ready, int last,
+                   void *d_out) {
+    if (cnt == 0 && !last) return B200_OK;
+    const size_t k = E.chunk_index++;
+    const int w = (int)(k & 1);
+    MsmPlan p = E.chunk_plan;
+    p.n = (uint32_t)cnt;
+    p.big = (uint32_t)std::min<size_t>(SIZE_BINS - 1, std::max<size_t>(64, 8 * (cnt / p.nb) + 64));
+    cudaStream_t s_sort = E.pipe_stream[0], s_acc = E.pipe_stream[1];
+    int rc;
+    if (ready) CUDA_TRY(cudaStreamWaitEvent(s_sort, ready, 0));
+    if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(s_sort, E.ev_acc[w], 0));          // sort buffers of chunk k - 2 consumed
+    const int split = last ? msm_split_of<C>(p, E.chunk_plan.n) : 0;
+    if ((rc = msm_stage_sort<C>(E, E.ws[w], p, d_scalars, cnt, s_sort, split))) return rc;
+    CUDA_TRY(cudaEventRecord(E.ev_sorted[w], s_sort));
+    CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_sorted[w], 0));
+    if (last) {
+        if ((rc = msm_split_run<C>(E, E.ws[w], E.ws[0], p, split, d_bases_packed, cnt, k > 0, d_out, s_acc))) return rc;
+        E.chunk_done = true;
+    } else if ((rc = msm_stage_accumulate<C>(E, E.ws[w], p, d_bases_packed, cnt, s_acc, &E.ws[0], k > 0))) {
+        return rc;
+    }
+    CUDA_TRY(cudaEventRecord(E.ev_acc[w], s_acc));
+    return B200_OK;
+}
+
+template <class C>
+int msm_chunks_finish(Engine &E, void *d_out, cudaStream_t st) {
+    using F = typename C::F;
+    cudaStream_t s_acc = E.pipe_stream[1];
+    if (E.chunk_done) {
+        // the last chunk ran its own tail
+    } else if (E.chunk_index == 0) {
+        k_sum_jacobian<F><<<1, SUM_THREADS, 0, s_acc>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(d_out));
+        LAUNCH_CHECK();
+    } else {
+        int rc = msm_stage_tail<C>(E.ws[0], E.chunk_plan, d_out, s_acc);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(E.ev_join, s_acc));
     CUDA_TRY(cudaStreamWaitEvent(st, E.ev_join, 0));
     ENGINE_MARK(st);
     return B200_OK;
@@ -417,6 +577,9 @@ int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStre
     template int msm_batch<C>(Engine &, const b200_msm_job *, size_t, cudaStream_t, const cudaEvent_t *);         \
     template int sum_jacobian<C>(const void *, size_t, void *, cudaStream_t);                                     \
     template int fixed_base_mul<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);           \
+    template int msm_chunks_begin<C>(Engine &, size_t, size_t, cudaStream_t);                                     \
+    template int msm_chunks_add<C>(Engine &, const void *, const void *, size_t, cudaEvent_t, int, void *);       \
+    template int msm_chunks_finish<C>(Engine &, void *, cudaStream_t);                                            \
     template int point_runs<C>(Engine &, const void *, const void *, size_t, size_t, void *, cudaStream_t);       \
     template int batch_to_affine<C>(const void *, size_t, void *, cudaStream_t);                                  \
     template int plan_query<C>(size_t, int *, int *, uint32_t *);                                                 \

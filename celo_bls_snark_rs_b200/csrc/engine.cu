@@ -1,6 +1,8 @@
 // The extern "C" surface declared in include/b200_bls.h.
 // No CPU compute path exists in this library: every entry point either launches the CUDA
 // kernels of msm.cuh or returns an error.
+#include <thread>
+
 #include "engine.cuh"
 
 namespace b200 {
@@ -25,7 +27,12 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 // the shared_ptr under g_engine_mu, then serialise on Engine::mu; b200_shutdown unpublishes it first, waits for the
 // call in flight by taking Engine::mu, tears the CUDA objects down and marks the object dead for late holders.
 static std::shared_ptr<Engine> g_engine;
+static std::vector<std::shared_ptr<Engine>> g_group;      // b200_init_devices: one engine per GPU, g_group[0] == g_engine
 static std::mutex g_engine_mu;
+static std::vector<std::shared_ptr<Engine>> engine_group() {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    return g_group;
+}
 static std::shared_ptr<Engine> engine_ref() {
     std::lock_guard<std::mutex> lk(g_engine_mu);
     return g_engine;
@@ -60,16 +67,8 @@ extern "C" {
 const char *b200_last_error(void) { return g_err.c_str(); }
 uint64_t b200_launch_count(void) { return g_launches.load(); }
 
-int b200_init(int device) {
-    std::lock_guard<std::mutex> lk(g_engine_mu);
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return fail(B200_ERR_CUDA, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
-    if (device >= count) return fail(B200_ERR_ARG, "device %d out of range (%d devices)", device, count);
-    if (g_engine && g_engine->device == device) return B200_OK;
-    if (g_engine) return fail(B200_ERR_STATE, "engine already bound to device %d; call b200_shutdown first", g_engine->device);
+// creates the engine of one device (streams, events); the caller publishes it
+static int create_engine(int device, std::shared_ptr<Engine> &out) {
     CUDA_TRY(cudaSetDevice(device));
     // a failure below leaves through CUDA_TRY: the deleter releases whatever was created so far
     std::shared_ptr<Engine> E(new Engine(), [](Engine *e) {
@@ -100,9 +99,82 @@ int b200_init(int device) {
             CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         CUDA_TRY(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
         for (cudaEvent_t &ev : E->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (cudaEvent_t &ev : E->ev_slot) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (cudaEvent_t &ev : E->ev_split) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamCreateWithFlags(&E->split_stream, cudaStreamNonBlocking));
     }
-    g_engine = E;
+    out = E;
     return B200_OK;
+}
+
+int b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B200_ERR_CUDA, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) return fail(B200_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    if (g_engine && g_engine->device == device) return B200_OK;
+    if (g_engine) return fail(B200_ERR_STATE, "engine already bound to device %d; call b200_shutdown first", g_engine->device);
+    std::shared_ptr<Engine> E;
+    int rc = create_engine(device, E);
+    if (rc) return rc;
+    g_engine = E;
+    g_group.assign(1, E);
+    return B200_OK;
+}
+
+// One process, several GPUs: one engine per listed device.  devices[0] becomes the primary engine -- every single-device
+// entry point keeps using it -- and the *_sharded entry points spread one call over all of them.
+int b200_init_devices(const int *devices, int count) {
+    if (!devices || count <= 0) return fail(B200_ERR_ARG, "no devices");
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    int have = 0;
+    cudaError_t e = cudaGetDeviceCount(&have);
+    if (e != cudaSuccess || have == 0)
+        return fail(B200_ERR_CUDA, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    for (int i = 0; i < count; i++) {
+        if (devices[i] < 0 || devices[i] >= have) return fail(B200_ERR_ARG, "device %d out of range (%d devices)", devices[i], have);
+        // a device listed twice gets two engines (tests drive the sharded path on a one-GPU box this way)
+        static const bool allow_dup = getenv("B200_ALLOW_DUP_DEVICES") != nullptr;
+        for (int j = 0; j < i && !allow_dup; j++)
+            if (devices[j] == devices[i]) return fail(B200_ERR_ARG, "device %d listed twice", devices[i]);
+    }
+    if (g_engine && g_engine->device != devices[0])
+        return fail(B200_ERR_STATE, "engine already bound to device %d; call b200_shutdown first", g_engine->device);
+    std::vector<std::shared_ptr<Engine>> group;
+    for (int i = 0; i < count; i++) {
+        std::shared_ptr<Engine> E;
+        for (const std::shared_ptr<Engine> &old : g_group) {
+            bool taken = false;
+            for (const std::shared_ptr<Engine> &g : group) taken = taken || g == old;
+            if (old->device == devices[i] && !taken && !E) E = old;
+        }
+        if (!E) {
+            int rc = create_engine(devices[i], E);
+            if (rc) return rc;
+        }
+        group.push_back(E);
+    }
+    // partial results travel to the primary device by peer copy: direct over NVLink when peer access can be enabled
+    for (int i = 1; i < count; i++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can) {
+            cudaSetDevice(devices[i]);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(devices[0], 0);
+            if (pe != cudaSuccess) cudaGetLastError();       // already enabled, or not possible: the copy is staged instead
+        }
+    }
+    cudaSetDevice(devices[0]);
+    g_group = group;
+    g_engine = group[0];
+    return B200_OK;
+}
+
+int b200_device_count(void) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    return (int)g_group.size();
 }
 
 int b200_ensure_init(void) { return engine_ref() ? B200_OK : b200_init(-1); }
@@ -113,14 +185,17 @@ int b200_bound_device(void) {
 }
 
 void b200_shutdown(void) {
-    std::shared_ptr<Engine> e;
+    std::vector<std::shared_ptr<Engine>> all;
     {
         std::lock_guard<std::mutex> lk(g_engine_mu);
-        e.swap(g_engine);
+        all.swap(g_group);
+        if (g_engine && all.empty()) all.push_back(g_engine);
+        g_engine.reset();
     }
-    if (!e) return;
-    std::lock_guard<std::mutex> lk(e->mu);             // waits for the call in flight
-    engine_teardown(*e);
+    for (std::shared_ptr<Engine> &e : all) {
+        std::lock_guard<std::mutex> lk(e->mu);         // waits for the call in flight
+        engine_teardown(*e);
+    }
 }
 
 }  // extern "C"
@@ -138,7 +213,7 @@ void engine_teardown(Engine &En) {
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (b200::Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->v_sum, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->g16_part, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->gather, &E->v_sum, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->g16_part, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
         b->release();
     for (NttDomain &d : E->ntt)
         for (b200::Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
@@ -152,6 +227,15 @@ void engine_teardown(Engine &En) {
         if (s) cudaStreamDestroy(s);
     for (cudaEvent_t ev : E->ev_chunk)
         if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : E->ev_slot)
+        if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : E->ev_split)
+        if (ev) cudaEventDestroy(ev);
+    if (E->split_stream) cudaStreamDestroy(E->split_stream);
+    for (void *&p : E->pinned) {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+    }
     if (E->copy_stream) cudaStreamDestroy(E->copy_stream);
     if (E->stream) cudaStreamDestroy(E->stream);
 }
@@ -220,20 +304,34 @@ int b200_pack_bases_device(int curve, const void *src, size_t stride, size_t n, 
     return B200_OK;
 }
 
-// Large inputs are cut into chunks: chunk c + 1 crosses PCIe (copy stream) while chunk c is being
-// multiplied -- each chunk is one job of the pipelined batch, gated by its `ready` event -- and the
-// chunk results are summed on the device.  Small inputs take the single-MSM path.
-constexpr size_t HOST_CHUNK_MIN = (size_t)1 << 18;
+// ---- host-pointer MSM ------------------------------------------------------------------------------------
+// Large inputs are cut into chunks (about 2^18 pairs): chunk k + 1 crosses PCIe on the copy stream while chunk k
+// is sorted and bucketed; all chunks feed ONE bucket set and one tail (msm_chunks_* in curve_impl.cuh).
+// Page-locked callers (cudaHostAlloc / cudaHostRegister) are copied from directly.  Ordinary (pageable) memory --
+// what a Rust Vec is -- goes through two pinned staging slots filled by a few host threads, so the PCIe copy
+// runs at its pinned rate and overlaps the host-side memcpy of the next chunk.
+constexpr size_t HOST_CHUNK_MIN = (size_t)1 << 17;       // below this: one plain copy + one MSM
+constexpr size_t HOST_CHUNK_PAIRS = (size_t)1 << 18;
+constexpr int STAGE_THREADS = 6;
 
-int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian) {
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// result (one GroupProjective image) is left in E.result[0]; asynchronous on E.stream, except that pageable inputs
+// have been fully read when the call returns.  Caller holds E.mu and has selected E.device.
+static int msm_host(Engine &E, int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n) {
     CurveInfo ci;
-    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
-    if (!out_jacobian || (n && (!bases || !scalars))) return fail(B200_ERR_ARG, "null pointer");
-    REQUIRE_ENGINE();
+    curve_info(curve, ci);
     cudaStream_t st = E.stream;
     int rc;
     const size_t packed = 2 * ci.coord_bytes;
-    if ((rc = E.result.reserve((Engine::MAX_CHUNKS + 1) * ci.jac_bytes))) return rc;
+    if ((rc = E.result.reserve(4 * ci.jac_bytes))) return rc;
     char *res = E.result.as<char>();
     if (n) {
         if (stride % 4 || stride < packed) return fail(B200_ERR_ARG, "bad base stride %zu", stride);
@@ -241,40 +339,184 @@ int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalar
         if (stride != packed && (rc = E.native_bases.reserve(n * packed))) return rc;
     }
     static const bool no_chunks = getenv("B200_HOST_NOCHUNK") != nullptr;
-    const int chunks = (n < HOST_CHUNK_MIN || no_chunks) ? 1 : (n < ((size_t)1 << 22) ? 2 : Engine::MAX_CHUNKS);
-    if (chunks == 1) {
+    if (n < HOST_CHUNK_MIN || no_chunks) {
         const void *d_bases = nullptr;
         if (n) {
             CUDA_TRY(cudaMemcpyAsync(E.scalars.p, scalars, n * ci.scalar_bytes, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(E.h2d_bases.p, bases, n * stride, cudaMemcpyHostToDevice, st));
             d_bases = E.h2d_bases.p;
         }
-        rc = DISPATCH_CURVE(curve, msm_device, E, d_bases, stride, E.scalars.p, n, res, st);
-        if (rc) return rc;
-    } else {
-        b200_msm_job jobs[Engine::MAX_CHUNKS];
-        cudaStream_t cs = E.copy_stream;
-        if (E.has_pending) CUDA_TRY(cudaStreamWaitEvent(cs, E.done, 0));      // staging buffers may still feed a prior MSM
-        const char *hb = reinterpret_cast<const char *>(bases), *hs = reinterpret_cast<const char *>(scalars);
-        char *db = E.h2d_bases.as<char>(), *ds = E.scalars.as<char>(), *dn = E.native_bases.as<char>();
-        for (int c = 0; c < chunks; c++) {
-            const size_t lo = n * c / chunks, cnt = n * (c + 1) / chunks - lo;
-            CUDA_TRY(cudaMemcpyAsync(ds + lo * ci.scalar_bytes, hs + lo * ci.scalar_bytes, cnt * ci.scalar_bytes,
-                                     cudaMemcpyHostToDevice, cs));
-            CUDA_TRY(cudaMemcpyAsync(db + lo * stride, hb + lo * stride, cnt * stride, cudaMemcpyHostToDevice, cs));
-            const void *chunk_bases = db + lo * stride;
-            if (stride != packed) {
-                if ((rc = DISPATCH_CURVE(curve, pack_bases, db + lo * stride, stride, cnt, dn + lo * packed, cs))) return rc;
-                chunk_bases = dn + lo * packed;
-            }
-            CUDA_TRY(cudaEventRecord(E.ev_chunk[c], cs));
-            jobs[c] = {chunk_bases, ds + lo * ci.scalar_bytes, cnt, res + (size_t)(c + 1) * ci.jac_bytes};
-        }
-        if ((rc = DISPATCH_CURVE(curve, msm_batch, E, jobs, (size_t)chunks, st, E.ev_chunk))) return rc;
-        if ((rc = DISPATCH_CURVE(curve, sum_jacobian, res + ci.jac_bytes, (size_t)chunks, res, st))) return rc;
+        return DISPATCH_CURVE(curve, msm_device, E, d_bases, stride, E.scalars.p, n, res, st);
     }
-    CUDA_TRY(cudaMemcpyAsync(out_jacobian, res, ci.jac_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    const int chunks = (int)std::min<size_t>(Engine::MAX_CHUNKS, std::max<size_t>(2, n / HOST_CHUNK_PAIRS));
+    const size_t chunk_max = (n + chunks - 1) / chunks + 1;
+    const size_t rec = stride + ci.scalar_bytes;
+    const bool pinned = host_is_pinned(bases) && host_is_pinned(scalars);
+    if (!pinned && E.pinned_cap < chunk_max * rec) {          // staging slots: grow-only
+        for (void *&p : E.pinned) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+        }
+        E.pinned_cap = 0;
+        for (void *&p : E.pinned) CUDA_TRY(cudaHostAlloc(&p, chunk_max * rec + chunk_max * rec / 8, cudaHostAllocDefault));
+        E.pinned_cap = chunk_max * rec + chunk_max * rec / 8;
+    }
+    cudaStream_t cs = E.copy_stream;
+    CUDA_TRY(cudaEventRecord(E.ev_fork, st));                 // the copy stream starts after everything queued on st
+    CUDA_TRY(cudaStreamWaitEvent(cs, E.ev_fork, 0));
+    if ((rc = DISPATCH_CURVE(curve, msm_chunks_begin, E, n, chunk_max, st))) return rc;
+    const char *hb = reinterpret_cast<const char *>(bases), *hs = reinterpret_cast<const char *>(scalars);
+    char *db = E.h2d_bases.as<char>(), *ds = E.scalars.as<char>(), *dn = E.native_bases.as<char>();
+
+    // pageable input: STAGE_THREADS host threads copy chunk k into slot k % 2 as soon as the slot's previous H2D is done
+    std::atomic<int> staged[Engine::MAX_CHUNKS];
+    std::atomic<int> free_upto{2};                            // chunks below this index may be written into their slot
+    std::vector<std::thread> workers;
+    if (!pinned) {
+        for (int c = 0; c < chunks; c++) staged[c].store(0);
+        for (int t = 0; t < STAGE_THREADS; t++)
+            workers.emplace_back([&, t]() {
+                for (int c = 0; c < chunks; c++) {
+                    while (free_upto.load(std::memory_order_acquire) <= c) std::this_thread::yield();
+                    const size_t lo = n * c / chunks, cnt = n * (c + 1) / chunks - lo;
+                    char *slot = reinterpret_cast<char *>(E.pinned[c & 1]);
+                    const size_t bbytes = cnt * stride, sbytes = cnt * ci.scalar_bytes, total = bbytes + sbytes;
+                    const size_t a = total * t / STAGE_THREADS, b = total * (t + 1) / STAGE_THREADS;   // this thread's byte range
+                    if (a < bbytes) memcpy(slot + a, hb + lo * stride + a, std::min(b, bbytes) - a);
+                    if (b > bbytes) {
+                        const size_t sa = std::max(a, bbytes) - bbytes;
+                        memcpy(slot + bbytes + sa, hs + lo * ci.scalar_bytes + sa, b - bbytes - sa);
+                    }
+                    staged[c].fetch_add(1, std::memory_order_release);
+                }
+            });
+    }
+    auto join = [&]() {
+        free_upto.store(1 << 30, std::memory_order_release);
+        for (std::thread &w : workers) w.join();
+        workers.clear();
+    };
+    rc = B200_OK;
+    for (int c = 0; c < chunks && rc == B200_OK; c++) {
+        const size_t lo = n * c / chunks, cnt = n * (c + 1) / chunks - lo;
+        const char *src_b = hb + lo * stride, *src_s = hs + lo * ci.scalar_bytes;
+        if (!pinned) {
+            while (staged[c].load(std::memory_order_acquire) < STAGE_THREADS) std::this_thread::yield();
+            src_b = reinterpret_cast<const char *>(E.pinned[c & 1]);
+            src_s = src_b + cnt * stride;
+        }
+        cudaError_t e = cudaMemcpyAsync(ds + lo * ci.scalar_bytes, src_s, cnt * ci.scalar_bytes, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(db + lo * stride, src_b, cnt * stride, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess && !pinned) e = cudaEventRecord(E.ev_slot[c & 1], cs);
+        if (e != cudaSuccess) {
+            rc = fail(B200_ERR_CUDA, "host-to-device copy: %s", cudaGetErrorString(e));
+            break;
+        }
+        const void *chunk_bases = db + lo * stride;
+        if (stride != packed) {
+            if ((rc = DISPATCH_CURVE(curve, pack_bases, db + lo * stride, stride, cnt, dn + lo * packed, cs))) break;
+            chunk_bases = dn + lo * packed;
+        }
+        if ((e = cudaEventRecord(E.ev_chunk[c], cs)) != cudaSuccess) {
+            rc = fail(B200_ERR_CUDA, "event record: %s", cudaGetErrorString(e));
+            break;
+        }
+        if ((rc = DISPATCH_CURVE(curve, msm_chunks_add, E, chunk_bases, ds + lo * ci.scalar_bytes, cnt, E.ev_chunk[c], c == chunks - 1, res)))
+            break;
+        if (!pinned && c + 2 < chunks) {                      // slot c % 2 is reusable once its copy has left the host
+            if ((e = cudaEventSynchronize(E.ev_slot[c & 1])) != cudaSuccess) {
+                rc = fail(B200_ERR_CUDA, "event sync: %s", cudaGetErrorString(e));
+                break;
+            }
+            free_upto.store(c + 3, std::memory_order_release);
+        }
+    }
+    join();
+    if (rc) return rc;
+    if (!pinned) CUDA_TRY(cudaStreamSynchronize(cs));          // the caller's buffers and the slots are free again
+    return DISPATCH_CURVE(curve, msm_chunks_finish, E, res, st);
+}
+
+int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out_jacobian || (n && (!bases || !scalars))) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    int rc = msm_host(E, curve, bases, stride, scalars, n);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_jacobian, E.result.p, ci.jac_bytes, cudaMemcpyDeviceToHost, E.stream));
+    CUDA_TRY(cudaStreamSynchronize(E.stream));
+    return B200_OK;
+}
+
+// ---- one process, several GPUs ------------------------------------------------------------------------------
+// The input is cut into one contiguous slice per engine; a host thread per GPU runs that slice through the host-pointer
+// MSM above, every GPU peer-copies its partial point (144 / 288 bytes) to the primary GPU, which adds them up.
+}  // extern "C"
+
+template <class Fn>
+static int run_on_group(const std::vector<std::shared_ptr<Engine>> &group, Fn fn) {
+    std::vector<int> rcs(group.size(), B200_OK);
+    std::vector<std::string> errs(group.size());
+    std::vector<std::thread> th;
+    for (size_t d = 0; d < group.size(); d++)
+        th.emplace_back([&, d]() {
+            Engine &E = *group[d];
+            std::lock_guard<std::mutex> lk(E.mu);
+            if (E.dead) {
+                rcs[d] = fail(B200_ERR_STATE, "engine was shut down");
+            } else if (cudaSetDevice(E.device) != cudaSuccess) {
+                rcs[d] = fail(B200_ERR_CUDA, "cudaSetDevice(%d)", E.device);
+            } else {
+                rcs[d] = fn(E, d);
+            }
+            if (rcs[d]) errs[d] = g_err;                       // the error text is thread-local
+        });
+    for (std::thread &t : th) t.join();
+    for (size_t d = 0; d < group.size(); d++)
+        if (rcs[d]) return fail(rcs[d], "GPU %d: %s", group[d]->device, errs[d].c_str());
+    return B200_OK;
+}
+
+extern "C" {
+
+static int sharded_gather(Engine &E, Engine &E0, size_t d, size_t bytes, const void *d_src) {
+    // E0.gather was sized before the worker threads started
+    CUDA_TRY(cudaMemcpyPeerAsync(E0.gather.as<char>() + d * bytes, E0.device, d_src, E.device, bytes, E.stream));
+    CUDA_TRY(cudaStreamSynchronize(E.stream));
+    return B200_OK;
+}
+
+int b200_msm_sharded(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!out_jacobian || (n && (!bases || !scalars))) return fail(B200_ERR_ARG, "null pointer");
+    std::vector<std::shared_ptr<Engine>> group = engine_group();
+    if (group.empty()) return fail(B200_ERR_STATE, "b200_init / b200_init_devices has not been called");
+    if (group.size() == 1 || n < group.size() * 1024) return b200_msm(curve, bases, stride, scalars, n, out_jacobian);
+    const size_t G = group.size();
+    Engine &E0 = *group[0];
+    {
+        std::lock_guard<std::mutex> lk(E0.mu);
+        CUDA_TRY(cudaSetDevice(E0.device));
+        int rc = E0.gather.reserve((G + 1) * ci.jac_bytes);
+        if (rc) return rc;
+    }
+    const char *hb = reinterpret_cast<const char *>(bases);
+    int rc = run_on_group(group, [&](Engine &E, size_t d) -> int {
+        const size_t lo = n * d / G, cnt = n * (d + 1) / G - lo;
+        ENGINE_ORDER(E.stream);
+        int r = msm_host(E, curve, hb + lo * stride, stride, scalars + lo * (ci.scalar_bytes / 8), cnt);
+        if (r) return r;
+        return sharded_gather(E, E0, d, ci.jac_bytes, E.result.p);
+    });
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(E0.mu);
+    CUDA_TRY(cudaSetDevice(E0.device));
+    char *g = E0.gather.as<char>();
+    if ((rc = DISPATCH_CURVE(curve, sum_jacobian, g, G, g + G * ci.jac_bytes, E0.stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_jacobian, g + G * ci.jac_bytes, ci.jac_bytes, cudaMemcpyDeviceToHost, E0.stream));
+    CUDA_TRY(cudaStreamSynchronize(E0.stream));
     return B200_OK;
 }
 
@@ -372,11 +614,8 @@ int b200_final_exp_bls12_377_device(const void *d_fq12_vals, size_t count, void 
     return B200_OK;
 }
 
-int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
-                                 void *out_fq12, int *out_is_one) {
-    if (n && (!g1 || !g2)) return fail(B200_ERR_ARG, "null pointer");
-    if (!out_fq12 && !out_is_one) return fail(B200_ERR_ARG, "no output requested");
-    REQUIRE_ENGINE();
+// Miller product of n host pairs -> E.result[0 .. 576); asynchronous on E.stream (caller holds E.mu)
+static int pairing_host_miller(Engine &E, const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n) {
     cudaStream_t st = E.stream;
     int rc;
     if ((rc = E.result.reserve(576 + 16))) return rc;
@@ -390,15 +629,63 @@ int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2,
         if ((rc = pack_bases<G1_377>(E.h2d_bases.p, stride1, n, E.native_bases.p, st))) return rc;
         if ((rc = pack_bases<G2_377>(E.h2d_g2.p, stride2, n, E.g2_packed.p, st))) return rc;
     }
+    return miller_product(E, E.native_bases.p, E.g2_packed.p, n, E.result.p, st);
+}
+
+// final exponentiation of `count` Miller values at d_vals (engine's device) -> host outputs
+static int pairing_host_finish(Engine &E, const void *d_vals, size_t count, void *out_fq12, int *out_is_one) {
+    cudaStream_t st = E.stream;
+    int rc;
+    if ((rc = E.result.reserve(576 + 16))) return rc;
     char *res = E.result.as<char>();
-    if ((rc = miller_product(E, E.native_bases.p, E.g2_packed.p, n, res, st))) return rc;
-    if ((rc = final_exp(E, res, 1, res, reinterpret_cast<int *>(res + 576), st))) return rc;
+    if ((rc = final_exp(E, d_vals, count, res, reinterpret_cast<int *>(res + 576), st))) return rc;
     if (out_fq12) CUDA_TRY(cudaMemcpyAsync(out_fq12, res, 576, cudaMemcpyDeviceToHost, st));
     int flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, res + 576, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (out_is_one) *out_is_one = flag;
     return B200_OK;
+}
+
+int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
+                                 void *out_fq12, int *out_is_one) {
+    if (n && (!g1 || !g2)) return fail(B200_ERR_ARG, "null pointer");
+    if (!out_fq12 && !out_is_one) return fail(B200_ERR_ARG, "no output requested");
+    REQUIRE_ENGINE();
+    int rc = pairing_host_miller(E, g1, stride1, g2, stride2, n);
+    if (rc) return rc;
+    return pairing_host_finish(E, E.result.p, 1, out_fq12, out_is_one);
+}
+
+// the pairs split over the GPUs of b200_init_devices: one Miller value (576 bytes) per GPU travels to the primary GPU,
+// which multiplies them and runs the one final exponentiation -- the same GT element as the single-GPU call
+int b200_multi_pairing_bls12_377_sharded(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
+                                         void *out_fq12, int *out_is_one) {
+    if (n && (!g1 || !g2)) return fail(B200_ERR_ARG, "null pointer");
+    if (!out_fq12 && !out_is_one) return fail(B200_ERR_ARG, "no output requested");
+    std::vector<std::shared_ptr<Engine>> group = engine_group();
+    if (group.empty()) return fail(B200_ERR_STATE, "b200_init / b200_init_devices has not been called");
+    if (group.size() == 1 || n < group.size() * 64) return b200_multi_pairing_bls12_377(g1, stride1, g2, stride2, n, out_fq12, out_is_one);
+    const size_t G = group.size();
+    Engine &E0 = *group[0];
+    {
+        std::lock_guard<std::mutex> lk(E0.mu);
+        CUDA_TRY(cudaSetDevice(E0.device));
+        int rc = E0.gather.reserve(G * 576);
+        if (rc) return rc;
+    }
+    const char *h1 = reinterpret_cast<const char *>(g1), *h2 = reinterpret_cast<const char *>(g2);
+    int rc = run_on_group(group, [&](Engine &E, size_t d) -> int {
+        const size_t lo = n * d / G, cnt = n * (d + 1) / G - lo;
+        ENGINE_ORDER(E.stream);
+        int r = pairing_host_miller(E, h1 + lo * stride1, stride1, h2 + lo * stride2, stride2, cnt);
+        if (r) return r;
+        return sharded_gather(E, E0, d, 576, E.result.p);
+    });
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(E0.mu);
+    CUDA_TRY(cudaSetDevice(E0.device));
+    return pairing_host_finish(E0, E0.gather.p, G, out_fq12, out_is_one);
 }
 
 int b200_multi_pairing_bw6_761(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,

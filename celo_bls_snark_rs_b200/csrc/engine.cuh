@@ -93,12 +93,25 @@ struct Engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sorted[2] = {}, ev_acc[2] = {}, ev_tail[2] = {};
     // host-pointer MSM: chunked H2D copies on their own stream, one `ready` event per chunk
     cudaStream_t copy_stream = nullptr;
-    static constexpr int MAX_CHUNKS = 4;
+    static constexpr int MAX_CHUNKS = 16;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {};
+    // chunk-fed MSM in flight (msm_chunks_*): the plan of the whole input and the next chunk's index
+    MsmPlan chunk_plan{};
+    size_t chunk_index = 0;
+    bool chunk_done = false;         // the last chunk has run the tail itself (window groups)
+    // window groups of one MSM (msm_split_run): group A's accumulate stream and the hand-over events
+    cudaStream_t split_stream = nullptr;
+    cudaEvent_t ev_split[3] = {};
+    // pageable callers: two pinned staging slots (host threads fill slot k + 1 while slot k crosses PCIe)
+    void *pinned[2] = {nullptr, nullptr};
+    size_t pinned_cap = 0;
+    cudaEvent_t ev_slot[2] = {};
     // staging for the host-pointer API
     Buffer h2d_bases, native_bases, scalars, result;
     // multi-pairing: Miller values, packed G2 staging
     Buffer miller, g2_packed, h2d_g2;
+    // *_sharded entry points: per-GPU partial results gathered on the primary GPU
+    Buffer gather;
     // NTT domains: [0] BLS12-377 Fr, [1] BW6-761 Fr (= BLS12-377 Fq)
     NttDomain ntt[2];
     // Groth16 prover composite (inst_groth16.cu): quotient coefficients h, partial MSM results
@@ -124,6 +137,10 @@ inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 template <class C> int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
 template <class C> int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
 template <class C> int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st, const cudaEvent_t *ready = nullptr);
+template <class C> int msm_chunks_begin(Engine &E, size_t n_total, size_t chunk_max, cudaStream_t st);
+template <class C> int msm_chunks_add(Engine &E, const void *d_bases_packed, const void *d_scalars, size_t cnt, cudaEvent_t ready, int last,
+                                      void *d_out);
+template <class C> int msm_chunks_finish(Engine &E, void *d_out, cudaStream_t st);
 template <class C> int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStream_t st);
 template <class C> int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st);
 template <class C> int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st);

@@ -214,7 +214,8 @@ static __global__ void __launch_bounds__(SIZE_BINS) k_size_scan(const uint32_t *
 }
 
 static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__restrict__ counts, uint32_t total, uint32_t big,
-                                                      uint32_t *__restrict__ bin_cursor, uint32_t *__restrict__ order) {
+                                                      uint32_t *__restrict__ bin_cursor, uint32_t *__restrict__ order,
+                                                      uint32_t id_base) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     uint32_t bin = min(counts[i], big);
@@ -224,7 +225,7 @@ static __global__ void __launch_bounds__(256) k_size_scatter(const uint32_t *__r
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(&bin_cursor[bin], (uint32_t)__popc(peers));
     base = __shfl_sync(peers, base, leader);
-    order[base + __popc(peers & ((1u << lane) - 1u))] = i;
+    order[base + __popc(peers & ((1u << lane) - 1u))] = id_base + i;     // counts points at the group's first bucket
 }
 
 // Buckets holding at least MsmPlan::big points (the top population bin of k_size_*; a few times the
@@ -241,13 +242,15 @@ template <class F, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_bucket_accumulate(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                     const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
-                    uint32_t big, XYZZMem<F> *__restrict__ buckets) {
+                    uint32_t big, int resume, XYZZMem<F> *__restrict__ buckets) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     if (t >= total_buckets) return;
     uint32_t id = order[t];
     uint32_t k = offsets[id], end = offsets[id + 1];
     if (end - k >= big) return;                      // left to k_big_buckets (one block per bucket)
-    XYZZ<F> acc = XYZZ<F>::inf();
+    // resume: the buckets already hold the sums of earlier input chunks (host-pointer MSM, one chunk per H2D copy)
+    if (resume && k == end) return;
+    XYZZ<F> acc = resume ? XYZZ<F>::load(buckets[id]) : XYZZ<F>::inf();
     if (k < end) {
         uint32_t e = __ldg(sorted + k);
         AffineMem<F> img = ldg_mem(bases + (e & 0x7fffffffu));
@@ -447,13 +450,14 @@ template <class F, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 k_bucket_accumulate_shared(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                            const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
-                           uint32_t big, XYZZMem<F> *__restrict__ buckets) {
+                           uint32_t big, int resume, XYZZMem<F> *__restrict__ buckets) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     if (t >= total_buckets) return;
     uint32_t id = order[t];
     uint32_t k = offsets[id], end = offsets[id + 1];
     if (end - k >= big) return;
-    XYZZ<F> acc = XYZZ<F>::inf();
+    if (resume && k == end) return;
+    XYZZ<F> acc = resume ? XYZZ<F>::load(buckets[id]) : XYZZ<F>::inf();
     if (k < end) {
         uint32_t e = __ldg(sorted + k);
         AffineMem<F> img = ldg_mem(bases + (e & 0x7fffffffu));
@@ -499,8 +503,8 @@ __global__ void __launch_bounds__(THREADS) k_big_buckets(const AffineMem<F> *__r
                                                          const uint32_t *__restrict__ sorted,
                                                          const uint32_t *__restrict__ offsets,
                                                          const uint32_t *__restrict__ order,
-                                                         const uint32_t *__restrict__ bin_counts, uint32_t big,
-                                                         XYZZMem<F> *__restrict__ buckets) {
+                                                         const uint32_t *__restrict__ bin_counts, uint32_t big, int resume,
+                                                         XYZZMem<F> *buckets) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nbig = bin_counts[big];
     for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
@@ -514,7 +518,10 @@ __global__ void __launch_bounds__(THREADS) k_big_buckets(const AffineMem<F> *__r
             if (!pt.is_inf()) acc.madd(pt.x, pt.y.cneg(e >> 31));
         }
         acc = block_sum<F, THREADS>(acc, reinterpret_cast<XYZZMem<F> *>(smem_raw));
-        if (threadIdx.x == 0) buckets[id] = acc.store();
+        if (threadIdx.x == 0) {
+            if (resume) acc.add(XYZZ<F>::load(buckets[id]));
+            buckets[id] = acc.store();
+        }
         __syncthreads();
     }
 }
@@ -549,12 +556,12 @@ __global__ void __launch_bounds__(THREADS) k_huge_buckets(const AffineMem<F> *__
 constexpr uint32_t ONES_PARTS = 8192;
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_ones_accumulate(const AffineMem<F> *__restrict__ bases,
-                                                             const uint32_t *__restrict__ ones,
-                                                             XYZZMem<F> *__restrict__ parts) {
+                                                             const uint32_t *__restrict__ ones, int resume,
+                                                             XYZZMem<F> *parts) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     if (t >= ONES_PARTS) return;
     uint32_t count = ones[0];
-    XYZZ<F> acc = XYZZ<F>::inf();
+    XYZZ<F> acc = resume ? XYZZ<F>::load(parts[t]) : XYZZ<F>::inf();
     for (uint32_t k = t; k < count; k += ONES_PARTS) {
         Affine<F> pt = Affine<F>::load(ldg_mem(bases + __ldg(ones + 1 + k)));
         if (!pt.is_inf()) acc.madd(pt.x, pt.y);
@@ -580,25 +587,26 @@ __global__ void __launch_bounds__(THREADS) k_huge_finish(const XYZZMem<F> *__res
                                                          const uint32_t *__restrict__ offsets,
                                                          const uint32_t *__restrict__ order,
                                                          const uint32_t *__restrict__ bin_counts, uint32_t big, uint32_t max_huge,
-                                                         XYZZMem<F> *__restrict__ buckets) {
+                                                         int resume, XYZZMem<F> *buckets) {
     const Quad Q;
     uint32_t b = (blockIdx.x * THREADS + threadIdx.x) >> 2;
     if (b >= max_huge || b >= bin_counts[big]) return;
     uint32_t id = order[b];
     if (offsets[id + 1] - offsets[id] < HUGE_BUCKET) return;
-    XYZZ<F> acc = XYZZ<F>::inf();
+    XYZZ<F> acc = resume ? XYZZ<F>::load(buckets[id]) : XYZZ<F>::inf();
     for (uint32_t y = 0; y < HUGE_SLICES; y++) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(slices + (size_t)b * HUGE_SLICES + y)));
     if (Q.q == 0) buckets[id] = acc.store();
 }
 
 // quad (w, seg): partial = sum_{j < L} (seg*L + j + 1) * B[w][seg*L + j]
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__restrict__ buckets, MsmPlan p,
+__global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__restrict__ buckets, MsmPlan p, int w_lo, int w_hi,
                                                            XYZZMem<F> *__restrict__ partials) {
     const Quad Q;
     uint32_t t = (blockIdx.x * THREADS + threadIdx.x) >> 2;
-    uint32_t total = (uint32_t)p.windows * p.segs;
+    uint32_t total = (uint32_t)(w_hi - w_lo) * p.segs;
     if (t >= total) return;                          // whole quads leave together (THREADS % 4 == 0)
+    t += (uint32_t)w_lo * p.segs;                    // windows [w_lo, w_hi) only (window groups, see msm_split_tail)
     uint32_t w = t / p.segs, seg = t % p.segs;
     const XYZZMem<F> *b = buckets + (size_t)w * p.nb + (size_t)seg * p.seg_len;
     XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
@@ -612,16 +620,17 @@ __global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__r
 
 // block w: window_sums[w] = sum of the window's partials (THREADS / 4 quads, tree in smem)
 template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__restrict__ partials, MsmPlan p,
+__global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__restrict__ partials, MsmPlan p, int w_lo, int w_hi,
                                                         XYZZMem<F> *__restrict__ window_sums) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     XYZZMem<F> *sm = reinterpret_cast<XYZZMem<F> *>(smem_raw);
     constexpr int QUADS = THREADS / 4;
     const Quad Q;
     const int quad = threadIdx.x >> 2;
-    // blocks 0 .. windows-1: the window's segment partials; block `windows`: the unit-scalar partials
-    const bool ones_block = blockIdx.x == (uint32_t)p.windows;
-    const XYZZMem<F> *src = partials + (size_t)(ones_block ? p.windows : blockIdx.x) * p.segs;
+    // blocks 0 .. (w_hi - w_lo) - 1: the segment partials of window w_lo + block; one block more: the unit-scalar partials
+    const bool ones_block = blockIdx.x == (uint32_t)(w_hi - w_lo);
+    const uint32_t window = ones_block ? (uint32_t)p.windows : (uint32_t)w_lo + blockIdx.x;
+    const XYZZMem<F> *src = partials + (size_t)window * p.segs;
     const uint32_t count = ones_block ? ONES_PARTS : p.segs;
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t i = quad; i < count; i += QUADS) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(src + i)));
@@ -634,7 +643,7 @@ __global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__rest
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) window_sums[blockIdx.x] = acc.store();
+    if (threadIdx.x == 0) window_sums[window] = acc.store();
 }
 
 // one quad: Horner over the windows, high to low; result leaves as an arkworks GroupProjective

@@ -26,7 +26,7 @@ ARK_STRIDE = {0: 104, 1: 200, 2: 200, 3: 200}
 PACKED_STRIDE = {k: 2 * v for k, v in COORD_BYTES.items()}
 
 EXPORTS = [
-    "b200_init", "b200_shutdown", "b200_last_error", "b200_msm", "b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2",
+    "b200_init", "b200_init_devices", "b200_device_count", "b200_msm_sharded", "b200_multi_pairing_bls12_377_sharded", "b200_shutdown", "b200_last_error", "b200_msm", "b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2",
     "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device", "b200_msm_prepared_device",
     "b200_sum_jacobian_device", "b200_sum_jacobian", "b200_fixed_base_mul_device", "b200_point_runs_device", "b200_batch_to_affine_device", "b200_sync",
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
@@ -110,6 +110,9 @@ def load() -> ctypes.CDLL:
     lib.b200_init.argtypes = [i32]
     lib.b200_last_error.restype = ctypes.c_char_p
     lib.b200_msm.argtypes = [i32, vp, sz, vp, sz, vp]
+    lib.b200_msm_sharded.argtypes = [i32, vp, sz, vp, sz, vp]
+    lib.b200_init_devices.argtypes = [ctypes.POINTER(i32), i32]
+    lib.b200_multi_pairing_bls12_377_sharded.argtypes = [vp, sz, vp, sz, sz, vp, ctypes.POINTER(i32)]
     for name in ("b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2", "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2"):
         getattr(lib, name).argtypes = [vp, vp, sz, vp]
     lib.b200_msm_device.argtypes = [i32, vp, vp, sz, vp, vp]
@@ -178,6 +181,16 @@ def init(device: int = -1):
     _check(load().b200_init(device))
 
 
+def init_devices(devices):
+    """One engine per listed GPU in THIS process (b200_init_devices); devices[0] is the primary engine."""
+    arr = (ctypes.c_int * len(devices))(*devices)
+    _check(load().b200_init_devices(arr, len(devices)))
+
+
+def device_count() -> int:
+    return load().b200_device_count()
+
+
 def shutdown():
     load().b200_shutdown()
 
@@ -207,6 +220,30 @@ def msm(curve: int, bases: np.ndarray, scalars: np.ndarray, n: Optional[int] = N
     out = np.zeros(JAC_BYTES[curve], dtype=np.uint8)
     _check(load().b200_msm(curve, _hptr(bases), stride, _hptr(scalars), n, _hptr(out)))
     return out.tobytes()
+
+
+def msm_sharded(curve: int, bases: np.ndarray, scalars: np.ndarray, n: Optional[int] = None) -> bytes:
+    """b200_msm_sharded: one host-pointer MSM spread over the GPUs of init_devices."""
+    bases = np.ascontiguousarray(bases)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+    if n is None:
+        n = min(len(bases), len(scalars))
+    stride = bases.strides[0] if n else ARK_STRIDE[curve]
+    out = np.zeros(JAC_BYTES[curve], dtype=np.uint8)
+    _check(load().b200_msm_sharded(curve, _hptr(bases) if n else None, stride, _hptr(scalars) if n else None, n, _hptr(out)))
+    return out.tobytes()
+
+
+def multi_pairing_sharded(g1: np.ndarray, g2: np.ndarray, n: Optional[int] = None, want_gt: bool = True):
+    """b200_multi_pairing_bls12_377_sharded: pairs split over the GPUs of init_devices.  Returns (is_one, gt | None)."""
+    g1, g2 = np.ascontiguousarray(g1), np.ascontiguousarray(g2)
+    if n is None:
+        n = min(len(g1), len(g2))
+    out = np.zeros(576, dtype=np.uint8)
+    flag = ctypes.c_int(0)
+    _check(load().b200_multi_pairing_bls12_377_sharded(_hptr(g1), g1.strides[0] if n else 104, _hptr(g2), g2.strides[0] if n else 200, n,
+                                                       _hptr(out) if want_gt else None, ctypes.byref(flag)))
+    return bool(flag.value), (out.tobytes() if want_gt else None)
 
 
 def msm_host_ptrs(curve: int, bases_ptr: int, stride: int, scalars_ptr: int, n: int, out: np.ndarray):

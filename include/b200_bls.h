@@ -58,6 +58,12 @@ int b200_ensure_init(void);
 /* The device the engine is bound to, or -1.  Callers that stage their own device buffers next to the engine's calls
  * (csrc/sys_compat.cu) select it first: b200_init binds the CALLING thread only. */
 int b200_bound_device(void);
+/* One process, several GPUs (a Rust caller of Signature::batch or ark-groth16's MSMs is one process): one engine per listed
+ * device; devices[0] is the primary engine every single-device entry point keeps using.  The *_sharded entry points below
+ * cut one call into a contiguous slice per GPU, one host thread per GPU, partial results (144 / 288 /
+ * 576 bytes) peer-copied to the primary GPU and combined there. */
+int b200_init_devices(const int *devices, int count);
+int b200_device_count(void);
 void b200_shutdown(void);
 const char *b200_last_error(void);
 
@@ -70,6 +76,8 @@ const char *b200_last_error(void);
  * Semantics follow arkworks: min(len) is the caller's job (pass one n), zero scalars
  * and infinite bases contribute nothing, bases may repeat. */
 int b200_msm(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian);
+/* the same call spread over the GPUs of b200_init_devices (one GPU: identical to b200_msm) */
+int b200_msm_sharded(int curve, const void *bases, size_t stride, const uint64_t *scalars, size_t n, void *out_jacobian);
 int b200_msm_bls12_377_g1(const void *bases_104B, const uint64_t *scalars, size_t n, void *out_144B);
 int b200_msm_bls12_377_g2(const void *bases_200B, const uint64_t *scalars, size_t n, void *out_288B);
 int b200_msm_bw6_761_g1(const void *bases_200B, const uint64_t *scalars, size_t n, void *out_288B);
@@ -140,6 +148,9 @@ int b200_batch_to_affine_device(int curve, const void *d_jacobian, size_t n, voi
  * comparison the reference makes at signature.rs:150 / public.rs:115. */
 int b200_multi_pairing_bls12_377(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
                                  void *out_fq12, int *out_is_one);
+/* the pairs split over the GPUs of b200_init_devices; same GT element (a product of Miller values is exact) */
+int b200_multi_pairing_bls12_377_sharded(const void *g1, size_t stride1, const void *g2, size_t stride2, size_t n,
+                                         void *out_fq12, int *out_is_one);
 /* Device-pointer halves, for pipelines and for sharding the pairs across GPUs:
  * product of the Miller values of n pairs (packed records) -> one Fq12 image; then the product
  * of `count` such images (e.g. one per GPU after an all-gather) -> final exponentiation.

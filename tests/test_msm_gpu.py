@@ -279,3 +279,89 @@ def test_config4_bw6_761_large_linearity_and_c_oracle(eng):
     pts = [L.jacobian_to_affine(raw[j * L.jac_bytes:(j + 1) * L.jac_bytes]) for j in range(4)]
     assert L.curve.padd(pts[0], pts[1]) == pts[2]
     assert pts[3] == L.jacobian_to_affine(C.msm(L, bases_m, s[:m]))
+
+
+@pytest.mark.parametrize("name", ["bls12_377_g1", "bls12_377_g2", "bw6_761_g1"])
+def test_batch_normalisation_4096_points_with_infinities(eng, name):
+    """Row a3 at a real size: batch_normalization_into_affine (signature.rs:82, public.rs:58) over 4096 Jacobian points
+    with non-trivial Z, infinities sprinkled in (also a whole batch-of-8 group of them), against the oracle."""
+    import torch
+    L = C.LAYOUTS[name]
+    dev = torch.device("cuda:0")
+    n = 4096
+    base = H.random_points(name, 64, 31, distinct=64)
+    jac, want = [], []
+    for i in range(n):
+        k = 0 if (i % 97 == 5 or 800 <= i < 808) else 3 + (i % 11)
+        j = C.scalar_mul(L, base[i % 64], k)
+        jac.append(j)
+        want.append(L.jacobian_to_affine(j))
+    d_jac = torch.from_numpy(np.frombuffer(b"".join(jac), dtype=np.uint8).copy()).to(dev)
+    d_aff = torch.empty((n, L.packed_stride), dtype=torch.uint8, device=dev)
+    eng.batch_to_affine_device(L.id, d_jac.data_ptr(), n, d_aff.data_ptr())
+    eng.sync()
+    got = L.affine_from_records(d_aff.cpu().numpy())
+    assert got == want and want[5] is None and want[803] is None
+
+
+def test_bw6_761_g2_msm_4096(eng):
+    """BW6-761 G2 (the b_g2_query MSM of the outer proof, prover.rs:78) at n = 2^12 with the edge cases, against the C port"""
+    name, n = "bw6_761_g2", 1 << 12
+    L = C.LAYOUTS[name]
+    pts, scalars = H.edge_case_inputs(name, n, 77)
+    bases, sc = L.affine_records(pts), L.scalars_array(scalars)
+    assert L.jacobian_compressed(eng.msm(L.id, bases, sc)) == L.jacobian_compressed(C.msm(L, bases, sc))
+
+
+def test_config4_bw6_761_g1_full_size_against_c_port(eng):
+    """BASELINE config 4 at its full size, n = 2^22: the device MSM and the host-pointer MSM against the C port of arkworks'
+    algorithm on the same inputs (the C port takes about half a minute on 16 cores)."""
+    import torch
+    name, n = "bw6_761_g1", 1 << 22
+    L = C.LAYOUTS[name]
+    dev = torch.device("cuda:0")
+    rng = O.SplitMix64(5)
+    g = H.generator(name, rng)
+    starts = np.zeros((n // 32, 6), dtype=np.uint64)
+    starts[:, 0] = np.random.default_rng(9).integers(1 << 40, 1 << 62, size=n // 32, dtype=np.uint64)
+    d_gen = torch.from_numpy(L.affine_records([g], L.packed_stride).copy()).to(dev)
+    d_st = torch.from_numpy(starts.view(np.int64)).to(dev)
+    d_bases = torch.empty((n, L.packed_stride), dtype=torch.uint8, device=dev)
+    eng.point_runs_device(L.id, d_gen.data_ptr(), d_st.data_ptr(), n // 32, 32, d_bases.data_ptr())
+    eng.sync()
+    bases = d_bases.cpu().numpy()
+    for i in (0, 1, 33, n - 1):                                    # the generator kernel itself, spot-checked
+        k = int(starts[i // 32, 0]) + i % 32
+        assert L.affine_from_records(bases[i:i + 1])[0] == L.jacobian_to_affine(C.scalar_mul(L, g, k))
+    sc = H.random_scalars_array(L, n, 10)
+    d_sc = torch.from_numpy(sc.view(np.int64)).to(dev)
+    d_out = torch.empty(L.jac_bytes, dtype=torch.uint8, device=dev)
+    eng.msm_device(L.id, d_bases.data_ptr(), d_sc.data_ptr(), n, d_out.data_ptr())
+    eng.sync()
+    want = L.jacobian_compressed(C.msm(L, bases, sc))
+    assert L.jacobian_compressed(d_out.cpu().numpy().tobytes()) == want
+    assert L.jacobian_compressed(eng.msm(L.id, bases, sc)) == want     # chunk-fed host path, pageable memory
+
+
+@pytest.mark.parametrize("name,log_n", [("bls12_377_g1", 19), ("bls12_377_g2", 18), ("bw6_761_g1", 18)])
+def test_host_pointer_msm_pinned_and_pageable_chunks(eng, name, log_n):
+    """The chunk-fed host path (one bucket set resumed chunk by chunk) from page-locked and from ordinary memory, with
+    unit / zero scalars and duplicates spread over the chunks, at a ragged size; against the device path and the C port."""
+    import torch
+    L = C.LAYOUTS[name]
+    n = (1 << log_n) + 12345
+    pts = H.random_points(name, 512, 3, distinct=512)
+    recs = L.affine_records(pts)
+    bases = np.tile(recs, (n // 512 + 1, 1))[:n].copy()
+    sc = H.random_scalars_array(L, n, 4)
+    sc[::7] = 0
+    sc[3::11] = 0
+    sc[3::11, 0] = 1                                               # unit scalars in every chunk
+    bases[5::1001, :] = 0
+    bases[5::1001, 2 * L.coord_bytes] = 1                          # infinity flags
+    want = L.jacobian_compressed(C.msm(L, bases, sc))
+    assert L.jacobian_compressed(eng.msm(L.id, bases, sc)) == want                  # pageable: staged through pinned slots
+    pb, ps = torch.from_numpy(bases).pin_memory(), torch.from_numpy(sc.view(np.int64)).pin_memory()
+    out = np.zeros(L.jac_bytes, dtype=np.uint8)
+    eng.msm_host_ptrs(L.id, pb.data_ptr(), bases.strides[0], ps.data_ptr(), n, out)
+    assert L.jacobian_compressed(out.tobytes()) == want                             # pinned: copied from directly

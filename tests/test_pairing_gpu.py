@@ -124,3 +124,9 @@ def test_config2_full_size_4096_signatures(eng):
     eng.sync()
     _, gt_bad = eng.multi_pairing(L1.affine_records(g1b), L2.affine_records(g2b))
     assert out.cpu().numpy().tobytes() == gt_bad != gt
+    # GT BYTES of the corrupted batch (a generic element of GT, not 1) against the C port of product_of_pairings
+    # (oracle/pairing_tmpl.h, pinned against the Python restatement): all 4097 pairs, not a GPU-vs-GPU comparison
+    cpu_ok, gt_cpu = C.multi_pairing(L1.affine_records(g1b), L2.affine_records(g2b), n + 1, threads=8)
+    assert cpu_ok is False and gt_cpu == gt_bad
+    cpu_ok, gt_cpu = C.multi_pairing(r1, r2, n + 1, threads=8)
+    assert cpu_ok is True and gt_cpu == gt
