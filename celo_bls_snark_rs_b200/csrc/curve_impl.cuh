@@ -281,10 +281,14 @@ static int msm_stage_tail(MsmWs &W, const MsmPlan &p, void *d_out, cudaStream_t 
 // blocks fill the SMs as A's drain.
 template <class C>
 static int msm_split_of(const MsmPlan &p, size_t n) {
-    static const int forced = getenv("B200_MSM_SPLIT") ? atoi(getenv("B200_MSM_SPLIT")) : -1;
-    if (forced >= 0) return std::min(forced, p.windows - 1);
-    if (n < ((size_t)1 << 15) || p.windows < 6) return 0;         // small inputs: launch latency dominates, keep one group
-    return std::max(2, p.windows / 4);
+    // MEASURED NEGATIVE on B200 (profiles/r2_experiments.md): BLS12-377 G1 n = 2^20 8.44 ms unsplit, 8.53 / 8.58 / 8.76 / 9.10 /
+    // 9.41 ms at split = 2 / 3 / 4 / 6 / 8; BW6-761 47.4 -> 47.5 .. 48.9 ms.  The exposed remainder is not the Horner chain any
+    // more (coop.cuh) but the bucket reduce, whose duration does not shrink with the number of windows (it is paced by the
+    // two warps per scheduler it puts on the machine), while the second accumulate launch and the displaced blocks cost more
+    // than the hidden part saves.  Off by default; B200_MSM_SPLIT = k forces windows [0, k) into the second group.
+    static const int forced = getenv("B200_MSM_SPLIT") ? atoi(getenv("B200_MSM_SPLIT")) : 0;
+    (void)n;
+    return forced > 0 ? std::min(forced, p.windows - 1) : 0;
 }
 
 // sort buffers in W (already sorted with the same `split`), buckets in B; everything ordered after `st`'s prior work and

@@ -213,7 +213,7 @@ void engine_teardown(Engine &En) {
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (b200::Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->gather, &E->v_sum, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->g16_part, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->gather, &E->v_sum, &E->v_pairs1, &E->v_pairs2, &E->v_offsets, &E->v_flags, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->g16_part, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
         b->release();
     for (NttDomain &d : E->ntt)
         for (b200::Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
@@ -552,6 +552,45 @@ int b200_sum_jacobian(int curve, const void *points, size_t count, void *out) {
     return B200_OK;
 }
 
+// out = scalar * base for ONE point, host pointers, GroupProjective images in and out (out is (x, y, 1) or zero()): the
+// scalar multiplications of PrivateKey::sign_raw / to_public (crates/bls-crypto/src/bls/secret.rs:65-72)
+int b200_scalar_mul(int curve, const void *base_jacobian, const uint64_t *scalar, void *out_jacobian) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (!base_jacobian || !scalar || !out_jacobian) return fail(B200_ERR_ARG, "null pointer");
+    REQUIRE_ENGINE();
+    cudaStream_t st = E.stream;
+    const size_t packed = 2 * ci.coord_bytes;
+    int rc = E.v_sum.reserve(ci.jac_bytes + 2 * packed + ci.scalar_bytes + 64);
+    if (rc) return rc;
+    char *d_j = E.v_sum.as<char>(), *d_a = d_j + ci.jac_bytes, *d_o = d_a + packed, *d_s = d_o + packed;
+    CUDA_TRY(cudaMemcpyAsync(d_j, base_jacobian, ci.jac_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_s, scalar, ci.scalar_bytes, cudaMemcpyHostToDevice, st));
+    if ((rc = DISPATCH_CURVE(curve, batch_to_affine, d_j, (size_t)1, d_a, st))) return rc;
+    if ((rc = DISPATCH_CURVE(curve, fixed_base_mul, E, d_a, d_s, (size_t)1, d_o, st))) return rc;
+    std::vector<unsigned char> aff(packed);
+    CUDA_TRY(cudaMemcpyAsync(aff.data(), d_o, packed, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    // Montgomery form of 1 in the coordinate field (c0 of an Fq2 coordinate; c1 = 0)
+    unsigned char one[96] = {0};
+    if (ci.coord_bytes == 96 && curve != B200_BLS12_377_G2)
+        for (int i = 0; i < 24; i++) reinterpret_cast<uint32_t *>(one)[i] = Fq761Params::one(i);
+    else
+        for (int i = 0; i < 12; i++) reinterpret_cast<uint32_t *>(one)[i] = Fq377Params::one(i);
+    unsigned char *o = reinterpret_cast<unsigned char *>(out_jacobian);
+    bool inf = true;
+    for (size_t i = 0; i < packed; i++) inf = inf && aff[i] == 0;
+    memset(o, 0, ci.jac_bytes);
+    if (inf) {                                        // GroupProjective::zero() = (1, 1, 0)
+        memcpy(o, one, ci.coord_bytes);
+        memcpy(o + ci.coord_bytes, one, ci.coord_bytes);
+    } else {
+        memcpy(o, aff.data(), packed);
+        memcpy(o + packed, one, ci.coord_bytes);
+    }
+    return B200_OK;
+}
+
 int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void *d_scalars, size_t n,
                                void *d_out_packed, void *stream) {
     CurveInfo ci;
@@ -805,6 +844,13 @@ int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, c
         return fail(B200_ERR_ARG, "null pointer");
     REQUIRE_ENGINE();
     return batch_verify_strict_hash(E, pubkeys, signatures, exponents, n, message_hash, out_verified);
+}
+
+int b200_batch_verify_strict_many(const b200_strict_batch *batches, size_t count, int *out_verified) {
+    if (count && (!batches || !out_verified)) return fail(B200_ERR_ARG, "null pointer");
+    if (count == 0) return B200_OK;
+    REQUIRE_ENGINE();
+    return batch_verify_strict_many(E, batches, count, out_verified);
 }
 
 int b200_serialize_points(int kind, const void *jacobian_images, size_t n, void *out_bytes) {

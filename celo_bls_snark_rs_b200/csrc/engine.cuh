@@ -117,7 +117,7 @@ struct Engine {
     // Groth16 prover composite (inst_groth16.cu): quotient coefficients h, partial MSM results
     Buffer g16_h, g16_tmp, g16_part;
     // batch-verification composites (inst_verify.cu)
-    Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff, v_sum;
+    Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff, v_sum, v_pairs1, v_pairs2, v_offsets, v_flags;
     // hash-to-G1 (inst_hash.cu): affine multiples of the Bowe-Hopwood generators (built at first use), per-call staging
     Buffer bh_table, hash_ws, sqrt_tables;
     bool bh_ready = false, sqrt_ready = false;
@@ -152,6 +152,7 @@ template <class C> int field_op(int op, const void *a, const void *b, size_t n, 
 // BLS12-377 multi-pairing (inst_pairing.cu)
 int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out, cudaStream_t st);
 int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_is_one, cudaStream_t st);
+int pairing_checks_2(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t count, int *d_flags, cudaStream_t st);
 // radix-2 NTT / Groth16 witness map (inst_ntt.cu)
 int ntt_transform(Engine &E, int field, void *data, int log_n, int inverse, int coset, cudaStream_t st);
 int witness_map(Engine &E, int field, void *a, void *b, void *c, int log_n, void *h, cudaStream_t st);
@@ -183,6 +184,7 @@ int hash_to_g1(Engine &E, int hasher, int flags, const uint8_t *domain, size_t d
                void *out, uint32_t *out_attempts);
 // batch-verification flows (inst_verify.cu)
 int batch_verify_hashes(Engine &E, const void *signature, const void *pubkeys, const void *hashes, size_t n, int *out_verified);
+int batch_verify_strict_many(Engine &E, const b200_strict_batch *batches, size_t count, int *out_verified);
 int batch_verify_strict_hash(Engine &E, const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,
                              const void *message_hash, int *out_verified);
 

@@ -65,6 +65,22 @@ int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, 
     return B200_OK;
 }
 
+// `count` independent two-pair checks (pairs 2b and 2b + 1 belong to check b): one warp runs both Miller loops of a check
+// on a shared Miller variable, one block per check finishes it -> d_flags[b] = 1 iff the product is one
+int pairing_checks_2(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t count, int *d_flags, cudaStream_t st) {
+    if (count == 0) return B200_OK;
+    int rc = E.miller.reserve(count * sizeof(Fq12::Mem));
+    if (rc) return rc;
+    Fq12::Mem *vals = E.miller.as<Fq12::Mem>();
+    k_w2_miller_loop<<<ceil_div(count, W_WARPS), 32 * W_WARPS, 0, st>>>(reinterpret_cast<const AffineMem<PFq> *>(d_g1_packed),
+                                                                          reinterpret_cast<const AffineMem<PFq2> *>(d_g2_packed),
+                                                                          (uint32_t)(2 * count), vals);
+    LAUNCH_CHECK();
+    k_b_final_exp<<<(unsigned)count, B_THREADS, 0, st>>>(vals, nullptr, d_flags);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
 // product of `count` Fq12 images (Miller values, e.g. one per GPU) -> final exponentiation
 int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_is_one, cudaStream_t st) {
     if (count == 0) return fail(B200_ERR_ARG, "final_exp needs at least one value");

@@ -736,6 +736,48 @@ __global__ void __launch_bounds__(THREADS) k_fixed_base_mul(const AffineMem<F> *
     out[i] = r.store();
 }
 
+template <class F> struct FieldInv;
+
+// ---- many small MSMs in one launch ------------------------------------------------------------------------------
+// batch_verify_strict hands over hundreds of batches of a few dozen signatures (the reference's own benchmark: 300 epochs
+// x 20 validators, crates/bls-crypto/benches/batch_bls.rs:62-95); each is two tiny MSMs (signature.rs:85, public.rs:61)
+// for which the bucket method's sort / reduce / Horner stages cost more than they save.  One block per MSM: thread i
+// multiplies point i by its scalar (double-and-add over the top `bits` bits, XYZZ), a shared-memory tree adds the block
+// up, thread 0 normalises.  out record of MSM b: out[b * out_stride + out_slot] (packed affine, (0, 0) = infinity).
+template <class F, int SW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_small_msm(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ scalars,
+                                                       const uint32_t *__restrict__ offsets, int bits,
+                                                       AffineMem<F> *__restrict__ out, uint32_t out_stride, uint32_t out_slot) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += THREADS) {
+        Affine<F> g = Affine<F>::from_ark(ldg_mem(bases + i));
+        if (g.is_inf()) continue;
+        XYZZ<F> r = XYZZ<F>::inf();
+        for (int b = bits - 1; b >= 0; b--) {
+            r.dbl();
+            launder(r);
+            if ((__ldg(scalars + (size_t)i * SW + (b >> 5)) >> (b & 31)) & 1u) {
+                r.madd(g.x, g.y);
+                launder(r);
+            }
+        }
+        acc.add(r);
+        launder(acc);
+    }
+    acc = block_sum<F, THREADS>(acc, reinterpret_cast<XYZZMem<F> *>(smem_raw));
+    if (threadIdx.x == 0) {
+        Affine<F> r = {F::zero(), F::zero()};
+        if (!acc.is_inf()) {
+            F iv = FieldInv<F>::inv(acc.zz * acc.zzz);
+            r.x = acc.x * (iv * acc.zzz);
+            r.y = acc.y * (iv * acc.zz);
+        }
+        out[(size_t)blockIdx.x * out_stride + out_slot] = r.to_ark();
+    }
+}
+
 // out[t * run + j] = (scalars[t] + j) * base for j < run: `run` consecutive multiples behind one double-and-add, so a
 // synthetic base array of 2^24 distinct points costs ~1 / run of k_fixed_base_mul (bench.py, configs 4 and 5)
 template <class F, int SW, int THREADS>

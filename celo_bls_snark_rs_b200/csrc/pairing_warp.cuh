@@ -597,6 +597,11 @@ __global__ void __launch_bounds__(B_THREADS) k_b_final_exp(const Fq12::Mem *__re
     __shared__ BlockScratch S;
     __shared__ Fq12::Mem inv_img;
     const int t = threadIdx.x;
+    // one block per value: a grid of `count` blocks finishes `count` independent products of pairings (the per-batch
+    // checks of batch_verify_strict); the single-value callers launch one block
+    in += blockIdx.x;
+    if (out) out += blockIdx.x;
+    if (is_one) is_one += blockIdx.x;
     enum { R = 0, Y0, Y1, Y2, Y3, Y4, Y5, X, T };
     FqImg(*V)[12] = S.V;
     FqImg *P = S.P;

@@ -293,42 +293,62 @@ bool batch_verify_strict(const BatchMessageFFI *in_batches_ptr, size_t in_batche
     const bool hasher_ok = hasher_of(should_use_composite, should_use_cip22, &hasher, &flags);
     if (b200_ensure_init() != B200_OK) return engine_failed(fn);
     const size_t nb = in_batches_len;
-    // one launch hashes the message of every batch (each Batch::verify hashes its own message once)
+    for (size_t b = 0; b < nb; b++) out_results[b] = false;
+    if (nb == 0) return true;
+    if (!hasher_ok) return failed(fn, "bad hash to curve configuration");      // every batch: Err -> false (signatures.rs:389-398)
+    // one launch hashes the message of every batch (each Batch::verify hashes its own message once); should a message fail
+    // to hash, the reference marks THAT batch false and goes on (signatures.rs:389-398): retry one by one to find it
     std::vector<b200_hash_input> inputs(nb);
     for (size_t b = 0; b < nb; b++) inputs[b] = {in_batches_ptr[b].data.ptr, in_batches_ptr[b].data.len, in_batches_ptr[b].extra.ptr, in_batches_ptr[b].extra.len};
     std::vector<uint8_t> hashes(nb * SIG_BYTES + 16);
-    if (hasher_ok && nb && b200_hash_to_g1(hasher, flags, SIG_DOMAIN, 8, inputs.data(), nb, hashes.data(), nullptr) != B200_OK)
-        return engine_failed(fn);
-    std::random_device entropy;                                               // the reference draws from rand::thread_rng()
-    bool all_valid = true;
-    for (size_t b = 0; b < nb; b++) {
-        const BatchMessageFFI &batch = in_batches_ptr[b];
-        bool result = false;
-        if (hasher_ok) {                                                      // (false, true): "bad hash to curve configuration" -> false
-            const size_t n = batch.public_keys_len < batch.signatures_len ? batch.public_keys_len : batch.signatures_len;   // zip()
-            std::vector<uint8_t> pks(n * PK_BYTES + 16), sigs(n * SIG_BYTES + 16);
-            std::vector<uint64_t> exps(4 * n + 4, 0);
-            // byte_count_from_target_batch_size (batch.rs:23-28): min((128 + ceil(log2 n) + 7) / 8, 253 / 8) random bytes,
-            // read little-endian (Fr::from_random_bytes)
-            const size_t exp_bytes = std::min<size_t>((128 + log2_ceil(n) + 7) / 8, 253 / 8);
-            for (size_t i = 0; i < n; i++) {
-                if (!batch.public_keys[i] || !batch.signatures[i]) return failed(fn, "null handle");
-                memcpy(&pks[i * PK_BYTES], batch.public_keys[i], PK_BYTES);
-                memcpy(&sigs[i * SIG_BYTES], batch.signatures[i], SIG_BYTES);
-                uint8_t *e = reinterpret_cast<uint8_t *>(&exps[4 * i]);
-                for (size_t k = 0; k < exp_bytes; k += 4) {
-                    const uint32_t r = entropy();
-                    memcpy(e + k, &r, std::min<size_t>(4, exp_bytes - k));
-                }
-            }
-            int ok = 0;
-            if (b200_batch_verify_strict_hash(pks.data(), sigs.data(), exps.data(), n, &hashes[b * SIG_BYTES], &ok) != B200_OK)
-                return engine_failed(fn);
-            result = ok != 0;
-        }
-        if (!result) all_valid = false;
-        out_results[b] = result;
+    std::vector<char> hashed(nb, 1);
+    if (b200_hash_to_g1(hasher, flags, SIG_DOMAIN, 8, inputs.data(), nb, hashes.data(), nullptr) != B200_OK) {
+        for (size_t b = 0; b < nb; b++)
+            hashed[b] = b200_hash_to_g1(hasher, flags, SIG_DOMAIN, 8, &inputs[b], 1, &hashes[b * SIG_BYTES], nullptr) == B200_OK;
     }
+    std::random_device entropy;                                               // the reference draws from rand::thread_rng()
+    // every batch's keys, signatures and fresh exponents gathered, then ALL batches verified in one pass on the device
+    std::vector<std::vector<uint8_t>> pks(nb), sigs(nb);
+    std::vector<std::vector<uint64_t>> exps(nb);
+    std::vector<b200_strict_batch> jobs;
+    std::vector<size_t> job_batch;
+    for (size_t b = 0; b < nb; b++) {
+        if (!hashed[b]) continue;
+        const BatchMessageFFI &batch = in_batches_ptr[b];
+        const size_t n = batch.public_keys_len < batch.signatures_len ? batch.public_keys_len : batch.signatures_len;   // zip()
+        pks[b].resize(n * PK_BYTES + 16);
+        sigs[b].resize(n * SIG_BYTES + 16);
+        exps[b].assign(4 * n + 4, 0);
+        // byte_count_from_target_batch_size (batch.rs:23-28): min((128 + ceil(log2 n) + 7) / 8, 253 / 8) random bytes,
+        // read little-endian (Fr::from_random_bytes)
+        const size_t exp_bytes = std::min<size_t>((128 + log2_ceil(n) + 7) / 8, 253 / 8);
+        for (size_t i = 0; i < n; i++) {
+            if (!batch.public_keys[i] || !batch.signatures[i]) return failed(fn, "null handle");
+            memcpy(&pks[b][i * PK_BYTES], batch.public_keys[i], PK_BYTES);
+            memcpy(&sigs[b][i * SIG_BYTES], batch.signatures[i], SIG_BYTES);
+            uint8_t *e = reinterpret_cast<uint8_t *>(&exps[b][4 * i]);
+            for (size_t k = 0; k < exp_bytes; k += 4) {
+                const uint32_t r = entropy();
+                memcpy(e + k, &r, std::min<size_t>(4, exp_bytes - k));
+            }
+        }
+        jobs.push_back({pks[b].data(), sigs[b].data(), exps[b].data(), n, &hashes[b * SIG_BYTES]});
+        job_batch.push_back(b);
+    }
+    std::vector<int> ok(jobs.size() + 1, 0);
+    if (jobs.size() > 2) {
+        if (b200_batch_verify_strict_many(jobs.data(), jobs.size(), ok.data()) != B200_OK) return engine_failed(fn);
+    } else {
+        // one or two batches: the bucket-method path has the shorter latency (the small-MSM kernel walks one
+        // double-and-add chain per point, which only pays when hundreds of batches run side by side)
+        for (size_t j = 0; j < jobs.size(); j++)
+            if (b200_batch_verify_strict_hash(jobs[j].pubkeys, jobs[j].signatures, jobs[j].exponents, jobs[j].n, jobs[j].message_hash,
+                                              &ok[j]) != B200_OK)
+                return engine_failed(fn);
+    }
+    bool all_valid = true;
+    for (size_t j = 0; j < jobs.size(); j++) out_results[job_batch[j]] = ok[j] != 0;
+    for (size_t b = 0; b < nb; b++) all_valid = all_valid && out_results[b];
     if (!all_valid) return failed(fn, "signature verification failed");       // BLSError::VerificationFailed
     return true;
 }

@@ -28,10 +28,10 @@ PACKED_STRIDE = {k: 2 * v for k, v in COORD_BYTES.items()}
 EXPORTS = [
     "b200_init", "b200_init_devices", "b200_device_count", "b200_msm_sharded", "b200_multi_pairing_bls12_377_sharded", "b200_shutdown", "b200_last_error", "b200_msm", "b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2",
     "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device", "b200_msm_prepared_device",
-    "b200_sum_jacobian_device", "b200_sum_jacobian", "b200_fixed_base_mul_device", "b200_point_runs_device", "b200_batch_to_affine_device", "b200_sync",
+    "b200_sum_jacobian_device", "b200_sum_jacobian", "b200_scalar_mul", "b200_fixed_base_mul_device", "b200_point_runs_device", "b200_batch_to_affine_device", "b200_sync",
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
-    "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash",
+    "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash", "b200_batch_verify_strict_many",
     "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_groth16_prove_partial_device", "b200_groth16_assemble_device", "b200_msm_batch_device",
     "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
     "b200_groth16_verify_bw6_761", "b200_deserialize_points", "b200_verify_epochs", "b200_epoch_public_inputs",
@@ -41,7 +41,10 @@ EXPORTS = [
 COMPAT_EXPORTS = ["verify", "deserialize_public_key", "deserialize_signature", "serialize_public_key", "serialize_signature",
                   "free_vec", "destroy_public_key", "destroy_signature", "aggregate_public_keys", "aggregate_signatures",
                   "verify_signature", "verify_pop", "batch_verify_signature", "batch_verify_strict", "compress_signature",
-                  "compress_pubkey"]
+                  "compress_pubkey", "init", "generate_private_key", "deserialize_private_key", "serialize_private_key",
+                  "destroy_private_key", "private_key_to_public_key", "sign_message", "sign_pop", "hash_direct",
+                  "hash_direct_with_attempt", "hash_composite", "hash_composite_cip22", "hash_crh", "deserialize_public_key_cached",
+                  "serialize_public_key_uncompressed", "serialize_signature_uncompressed", "aggregate_public_keys_subtract"]
 
 
 class Groth16Pk(ctypes.Structure):
@@ -152,6 +155,17 @@ def load() -> ctypes.CDLL:
     lib.b200_hash_to_g1.argtypes = [i32, i32, ctypes.c_char_p, sz, ctypes.POINTER(HashInput), sz, vp, vp]
     lib.b200_serialize_points.argtypes = [i32, vp, sz, vp]
     cb, pp, pb, ci = ctypes.c_bool, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_bool), ctypes.c_int
+    pci, pu8 = ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_uint8)
+    for name, args in (("generate_private_key", [pp]), ("deserialize_private_key", [vp, ci, pp]), ("serialize_private_key", [vp, pp, pci]),
+                       ("destroy_private_key", [vp]), ("private_key_to_public_key", [vp, pp]),
+                       ("sign_message", [vp, vp, ci, vp, ci, cb, cb, pp]), ("sign_pop", [vp, vp, ci, pp]),
+                       ("hash_direct", [vp, ci, pp, pci, cb]), ("hash_direct_with_attempt", [vp, ci, pp, pci, pci, cb]),
+                       ("hash_composite", [vp, ci, vp, ci, pp, pci]), ("hash_composite_cip22", [vp, ci, vp, ci, pp, pci, pu8]),
+                       ("hash_crh", [vp, ci, ci, pp, pci]), ("deserialize_public_key_cached", [vp, ci, pp]),
+                       ("serialize_public_key_uncompressed", [vp, pp, pci]), ("serialize_signature_uncompressed", [vp, pp, pci]),
+                       ("aggregate_public_keys_subtract", [vp, pp, ci, pp]), ("init", [])):
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, cb
     for name, args in (("deserialize_public_key", [vp, ci, pp]), ("deserialize_signature", [vp, ci, pp]),
                        ("serialize_public_key", [vp, pp, ctypes.POINTER(ci)]), ("serialize_signature", [vp, pp, ctypes.POINTER(ci)]),
                        ("compress_signature", [vp, ci, pp, ctypes.POINTER(ci)]), ("compress_pubkey", [vp, ci, pp, ctypes.POINTER(ci)]),

@@ -122,6 +122,11 @@ int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void
  * PublicKey::aggregate / Signature::aggregate (crates/bls-crypto/src/bls/public.rs:34, signature.rs:52). */
 int b200_sum_jacobian(int curve, const void *points, size_t count, void *out_jacobian);
 
+/* out = scalar * base for one point, host pointers, GroupProjective images in and out (the result is normalised:
+ * (x, y, 1), or zero() = (1, 1, 0)).  Replaces the scalar multiplications of PrivateKey::sign_raw / to_public
+ * (crates/bls-crypto/src/bls/secret.rs:65-72). */
+int b200_scalar_mul(int curve, const void *base_jacobian, const uint64_t *scalar, void *out_jacobian);
+
 /* d_out_packed[i] = scalars[i] * base, as packed affine records (device pointers;
  * base is one packed affine record).  Synthesises benchmark / test bases on the GPU. */
 int b200_fixed_base_mul_device(int curve, const void *d_base_packed, const void *d_scalars, size_t n,
@@ -177,6 +182,18 @@ int b200_batch_verify_hashes(const void *signature, const void *pubkeys, const v
                              int *out_verified);
 int b200_batch_verify_strict_hash(const void *pubkeys, const void *signatures, const uint64_t *exponents, size_t n,
                                   const void *message_hash, int *out_verified);
+/* Batch::verify for `count` batches in one pass -- what batch_verify_strict is called with
+ * (crates/bls-snark-sys/src/signatures.rs:343-404; the reference's benchmark: 300 batches of 20 signatures,
+ * crates/bls-crypto/benches/batch_bls.rs:62-95).  Every batch's two MSMs, 2-pair Miller loops and final exponentiation
+ * run side by side on the device; out_verified[b] = 1 iff Batch::verify of batch b would return Ok(()). */
+typedef struct {
+    const void *pubkeys;       /* n x 288 bytes, G2Projective images */
+    const void *signatures;    /* n x 144 bytes, G1Projective images */
+    const uint64_t *exponents; /* n x 4 limbs, canonical */
+    size_t n;
+    const void *message_hash;  /* 144 bytes, what HashToCurve::hash returned for the batch's message */
+} b200_strict_batch;
+int b200_batch_verify_strict_many(const b200_strict_batch *batches, size_t count, int *out_verified);
 
 /* ---- batched hash-to-G1 ------------------------------------------------------------------------------
  * Replaces HashToCurve::hash for BLS12-377 G1 -- the step before the multi-pairing in

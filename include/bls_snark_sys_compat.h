@@ -47,6 +47,7 @@ bool verify(const uint8_t *vk, uint32_t vk_len, const uint8_t *proof, uint32_t p
  * free_vec.  A handle made by the reference's library has the same layout and can be passed in as it is. */
 typedef struct PublicKey PublicKey;
 typedef struct Signature Signature;
+typedef struct PrivateKey PrivateKey;          /* Fr, 32 bytes (Montgomery residue) */
 
 /* utils.rs:75-82 */
 typedef struct {
@@ -81,6 +82,40 @@ bool serialize_signature(const Signature *in_signature, uint8_t **out_bytes, int
  * compressed encoding (48 / 96 bytes, free_vec).  Integer comparisons only; runs on the host. */
 bool compress_signature(const uint8_t *in_signature, int in_signature_len, uint8_t **out_signature, int *out_len);
 bool compress_pubkey(const uint8_t *in_pubkey, int in_pubkey_len, uint8_t **out_pubkey, int *out_len);
+/* ---- csrc/sys_compat_keys.cu: private keys, signing, hash helpers, uncompressed encodings ---------------------
+ * lib.rs:29-34 */
+bool init(void);
+/* signatures.rs:19-42; serialization.rs:13-33, 224-234.  generate_private_key draws Fr::rand from the OS entropy source
+ * (the reference: rand::thread_rng()); private_key_to_public_key is sk * g2 on the device. */
+bool generate_private_key(PrivateKey **out_private_key);
+bool deserialize_private_key(const uint8_t *in_private_key_bytes, int in_private_key_bytes_len, PrivateKey **out_private_key);
+bool serialize_private_key(const PrivateKey *in_private_key, uint8_t **out_bytes, int *out_len);
+bool destroy_private_key(PrivateKey *private_key);
+bool private_key_to_public_key(const PrivateKey *in_private_key, PublicKey **out_public_key);
+/* signatures.rs:44-91: hash-to-G1 on the device (same hasher selection as verify_signature), then hash * sk on the device */
+bool sign_message(const PrivateKey *in_private_key, const uint8_t *in_message, int in_message_len, const uint8_t *in_extra_data,
+                  int in_extra_data_len, bool should_use_composite, bool should_use_cip22, Signature **out_signature);
+bool sign_pop(const PrivateKey *in_private_key, const uint8_t *in_message, int in_message_len, Signature **out_signature);
+/* signatures.rs:93-242.  hash_direct*: G1Affine::write = canonical x | y | infinity byte (97 bytes).  hash_composite*:
+ * G1Projective::write = canonical X | Y | Z (144 bytes) of the NORMALISED representative (x, y, 1) -- the reference writes
+ * the representative its cofactor multiplication ended on; the point is the same.  hash_crh: the 48-byte composite CRH. */
+bool hash_direct(const uint8_t *in_message, int in_message_len, uint8_t **out_hash, int *out_len, bool use_pop);
+bool hash_direct_with_attempt(const uint8_t *in_message, int in_message_len, uint8_t **out_hash, int *out_len, int *out_attempt,
+                              bool use_pop);
+bool hash_composite(const uint8_t *in_message, int in_message_len, const uint8_t *in_extra_data, int in_extra_data_len, uint8_t **out_hash,
+                    int *out_len);
+bool hash_composite_cip22(const uint8_t *in_message, int in_message_len, const uint8_t *in_extra_data, int in_extra_data_len,
+                          uint8_t **out_hash, int *out_len, uint8_t *attempt_counter);
+bool hash_crh(const uint8_t *in_message, int in_message_len, int hash_bytes, uint8_t **out_hash, int *out_len);
+/* serialization.rs:44-61, 72-105: the cached decoder hands out the same key; serialize_uncompressed = canonical x | y
+ * (192 / 96 bytes), infinity flag in bit 6 of the last byte */
+bool deserialize_public_key_cached(const uint8_t *in_public_key_bytes, int in_public_key_bytes_len, PublicKey **out_public_key);
+bool serialize_public_key_uncompressed(const PublicKey *in_public_key, uint8_t **out_bytes, int *out_len);
+bool serialize_signature_uncompressed(const Signature *in_signature, uint8_t **out_bytes, int *out_len);
+/* signatures.rs:454-483: aggregated - sum(keys) */
+bool aggregate_public_keys_subtract(const PublicKey *in_aggregated_public_key, const PublicKey *const *in_public_keys, int in_public_keys_len,
+                                    PublicKey **out_public_key);
+
 /* serialization.rs:236-266 */
 bool free_vec(uint8_t *bytes, int len);
 bool destroy_public_key(PublicKey *public_key);

@@ -179,3 +179,90 @@ def test_batch_verify_strict(lib):
     # wrong hasher for these signatures: every batch fails; (false, true) marks every batch false as well
     assert not lib.batch_verify_strict(good, 2, False, False, results2) and list(results2) == [False, False]
     assert not lib.batch_verify_strict(good, 2, False, True, results2) and list(results2) == [False, False]
+
+
+# ---- private keys, signing, hash helpers, uncompressed encodings (csrc/sys_compat_keys.cu) ---------------------------
+def _out_bytes(lib, call):
+    ptr, n = ctypes.c_void_p(), ctypes.c_int()
+    assert call(ctypes.byref(ptr), ctypes.byref(n))
+    data = ctypes.string_at(ptr, n.value)
+    assert lib.free_vec(ptr, n.value)
+    return data
+
+
+def test_private_key_sign_and_verify_round_trip(lib):
+    """test_simple_sig / test_pop of crates/bls-crypto/src/bls/signature.rs:158-180 and secret.rs through the exported symbols:
+    keys and signatures made by the library verify, against the oracle's own values too."""
+    assert lib.init()
+    rng = O.SplitMix64(21)
+    sk_int = rng.below(O.R - 1) + 1
+    sk = _handle(lib, "deserialize_private_key", sk_int.to_bytes(32, "little"))
+    assert _out_bytes(lib, lambda p, n: lib.serialize_private_key(sk, p, n)) == sk_int.to_bytes(32, "little")
+    pk = ctypes.c_void_p()
+    assert lib.private_key_to_public_key(sk, ctypes.byref(pk))
+    assert _bytes_of(lib, "serialize_public_key", pk) == pk_bytes(sk_int)
+    msg, extra = b"hello celo", b"xtra"
+    for cfg in HASHERS:
+        sig = ctypes.c_void_p()
+        assert lib.sign_message(sk, msg, len(msg), extra, len(extra), cfg[0], cfg[1], ctypes.byref(sig))
+        assert _bytes_of(lib, "serialize_signature", sig) == sign_bytes(sk_int, msg, extra, cfg)
+        ok = ctypes.c_bool(False)
+        assert lib.verify_signature(pk, msg, len(msg), extra, len(extra), sig, cfg[0], cfg[1], ctypes.byref(ok)) and ok.value
+        assert lib.verify_signature(pk, b"other", 5, extra, len(extra), sig, cfg[0], cfg[1], ctypes.byref(ok)) and not ok.value
+        assert lib.destroy_signature(sig)
+    out = ctypes.c_void_p()
+    assert not lib.sign_message(sk, msg, len(msg), extra, len(extra), False, True, ctypes.byref(out))      # (false, true): HashToCurveError
+    pop = ctypes.c_void_p()
+    pkb = pk_bytes(sk_int)
+    assert lib.sign_pop(sk, pkb, len(pkb), ctypes.byref(pop))
+    ok = ctypes.c_bool(False)
+    assert lib.verify_pop(pk, pkb, len(pkb), pop, ctypes.byref(ok)) and ok.value
+    # a generated key is a valid scalar and signs verifiably
+    gen = ctypes.c_void_p()
+    assert lib.generate_private_key(ctypes.byref(gen))
+    g_int = int.from_bytes(_out_bytes(lib, lambda p, n: lib.serialize_private_key(gen, p, n)), "little")
+    assert 0 < g_int < O.R
+    gpk, gsig = ctypes.c_void_p(), ctypes.c_void_p()
+    assert lib.private_key_to_public_key(gen, ctypes.byref(gpk)) and lib.sign_message(gen, msg, len(msg), None, 0, True, True, ctypes.byref(gsig))
+    assert lib.verify_signature(gpk, msg, len(msg), None, 0, gsig, True, True, ctypes.byref(ok)) and ok.value
+    assert not lib.deserialize_private_key(O.R.to_bytes(32, "little"), 32, ctypes.byref(out))                  # not below the order
+    for h in (sk, gen):
+        assert lib.destroy_private_key(h)
+
+
+def test_hash_helpers_and_uncompressed_encodings(lib):
+    msg, extra = b"some message", b"\x01\x02"
+    fe = lambda v: v.to_bytes(48, "little")
+    # hash_direct: G1Affine::write = canonical x | y | infinity byte
+    for pop in (False, True):
+        pt, att = H.try_and_increment(O.G1, H.DIRECT, POP_DOMAIN if pop else SIG_DOMAIN, msg, b"", compat=True, cip22=False)
+        want = fe(pt[0]) + fe(pt[1]) + b"\x00"
+        assert _out_bytes(lib, lambda p, n: lib.hash_direct(msg, len(msg), p, n, pop)) == want
+        a = ctypes.c_int(-1)
+        assert _out_bytes(lib, lambda p, n: lib.hash_direct_with_attempt(msg, len(msg), p, n, ctypes.byref(a), pop)) == want and a.value == att
+    # hash_composite / _cip22: the point, as canonical (x, y, 1)
+    pt, _ = H.try_and_increment(O.G1, H.COMPOSITE, SIG_DOMAIN, msg, extra, compat=True, cip22=False)
+    assert _out_bytes(lib, lambda p, n: lib.hash_composite(msg, len(msg), extra, len(extra), p, n)) == fe(pt[0]) + fe(pt[1]) + fe(1)
+    pt, att = H.try_and_increment(O.G1, H.COMPOSITE, SIG_DOMAIN, msg, extra, compat=True, cip22=True)
+    c = ctypes.c_uint8(255)
+    got = _out_bytes(lib, lambda p, n: lib.hash_composite_cip22(msg, len(msg), extra, len(extra), p, n, ctypes.byref(c)))
+    assert got == fe(pt[0]) + fe(pt[1]) + fe(1) and c.value == att
+    assert _out_bytes(lib, lambda p, n: lib.hash_crh(msg, len(msg), 48, p, n)) == H.COMPOSITE[0](SIG_DOMAIN, msg, 48)
+    # uncompressed encodings and the key subtraction
+    rng = O.SplitMix64(33)
+    sks = [rng.below(O.R - 1) + 1 for _ in range(4)]
+    pks = [_handle(lib, "deserialize_public_key_cached", pk_bytes(s)) for s in sks]
+    sig = _handle(lib, "deserialize_signature", O.serialize_compressed(O.G1, O.G1.pmul(O.G1_GEN, sks[0])))
+    assert _out_bytes(lib, lambda p, n: lib.serialize_public_key_uncompressed(pks[0], p, n)) == \
+        O.serialize_uncompressed(O.G2, O.G2.pmul(O.G2_GEN, sks[0]))
+    assert _out_bytes(lib, lambda p, n: lib.serialize_signature_uncompressed(sig, p, n)) == \
+        O.serialize_uncompressed(O.G1, O.G1.pmul(O.G1_GEN, sks[0]))
+    arr = (ctypes.c_void_p * 4)(*[p.value for p in pks])
+    agg = ctypes.c_void_p()
+    assert lib.aggregate_public_keys(arr, 4, ctypes.byref(agg))
+    sub = (ctypes.c_void_p * 2)(pks[1].value, pks[3].value)
+    rest = ctypes.c_void_p()
+    assert lib.aggregate_public_keys_subtract(agg, sub, 2, ctypes.byref(rest))
+    assert _bytes_of(lib, "serialize_public_key", rest) == pk_bytes((sks[0] + sks[2]) % O.R)
+    inf = _handle(lib, "deserialize_signature", O.serialize_compressed(O.G1, None))
+    assert _out_bytes(lib, lambda p, n: lib.serialize_signature_uncompressed(inf, p, n)) == O.serialize_uncompressed(O.G1, None)
