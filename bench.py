@@ -403,9 +403,8 @@ def headline(ctx: Ctx):
         last["results"] = job.run_batch([(sets[i & 1][0], sets[i & 1][1], n) for i in range(k)], sp)
         last["k"] = k
 
-    sampler = ClockSampler(ctx.local)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(ctx.local)                   # every rank samples its own GPU (per_rank in the JSON line)
+    sampler.start()
     steps(args.warmup)
     ctx.barrier()
     # the same MSM one call at a time (no overlap between consecutive MSMs), for reference
@@ -418,8 +417,7 @@ def headline(ctx: Ctx):
     ctx.barrier()
     seq_ms = s0.elapsed_time(s1) / seq_steps
     E.profile_enable(True)
-    if rank == 0:
-        sampler.mark()
+    sampler.mark()
     launches0 = E.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.barrier()
@@ -431,9 +429,13 @@ def headline(ctx: Ctx):
     launches = E.launch_count() - launches0 + (args.steps if world > 1 else 0)     # + NCCL all-gather kernels
     acc_ms, acc_launches, acc_pairs = E.profile_read()
     E.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     if clocks and clocks.get("sm_mhz"):
         ctx.clock_hz = clocks["sm_mhz"] * 1e6
+    # per-rank view of the timed region: where a weak-scaling loss comes from (kernel time per GPU, clocks, power)
+    per_rank = ctx.gather_objects({"rank": rank, "ms_per_step": ms / args.steps, "kernel_ms": acc_ms / max(acc_launches, 1),
+                                   "sm_mhz": clocks.get("sm_mhz"), "power_w_max": clocks.get("power_w_max"),
+                                   "reasons": clocks.get("reasons")})
 
     # ---- parity of the LAST timed MSM: this rank's partial and the combined point against the C port ----
     k_last = args.steps - 1
@@ -522,6 +524,7 @@ def headline(ctx: Ctx):
             "gpu_launches": int(launches),
             "roofline": roof,
             "clocks": clocks,
+            "per_rank": per_rank,
         }
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_msm_baseline(ctx, CURVE, sets[0][0].cpu().numpy(), sets[0][2], budget_s=6.0)

@@ -13,6 +13,17 @@ template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
 // keeping enough buckets in flight to fill 148 SMs.
 template <class C>
+static MsmPlan make_plan(size_t n);
+
+// window plan for n pairs of which only n_eff scalars reach the buckets (the others are 0 or 1): the width follows n_eff
+template <class C>
+static MsmPlan make_plan_eff(size_t n, size_t n_eff) {
+    MsmPlan p = make_plan<C>(std::max<size_t>(std::min(n, n_eff), 256));
+    p.n = (uint32_t)n;
+    return p;
+}
+
+template <class C>
 static MsmPlan make_plan(size_t n) {
     MsmPlan best{};
     double best_cost = 1e300;
@@ -109,7 +120,7 @@ static int msm_reserve(MsmWs &W, const MsmPlan &p, size_t n) {
         (rc = W.cursor.reserve(total * 4)) || (rc = W.tile_sums.reserve((size_t)tiles * 4)) ||
         (rc = W.bins.reserve(4 * SIZE_BINS * 4)) || (rc = W.order.reserve(total * 4)) ||
         (rc = W.sorted.reserve(n * (size_t)p.windows * 4)) || (rc = W.buckets.reserve(total * sizeof(XYZZMem<F>))) ||
-        (rc = W.partials.reserve(((size_t)p.windows * p.segs + ONES_PARTS) * sizeof(XYZZMem<F>))) ||
+        (rc = W.partials.reserve(((size_t)p.windows * p.segs + ONES_PARTS + ONES_GROUPS) * sizeof(XYZZMem<F>))) ||
         (rc = W.window_sums.reserve((size_t)(p.windows + 2) * sizeof(XYZZMem<F>))) ||
         (rc = W.ones.reserve((n + 1) * 4)) || (rc = W.huge_slices.reserve(max_huge * HUGE_SLICES * sizeof(XYZZMem<F>))))
         return rc;
@@ -247,6 +258,11 @@ static int msm_stage_reduce(MsmWs &W, const MsmPlan &p, int w_lo, int w_hi, bool
     }
     constexpr int WS_THREADS = 256;                                // 64 quads per window
     size_t ws_smem = (WS_THREADS / 4) * sizeof(XYZZMem<F>);
+    if (with_ones) {
+        XYZZMem<F> *parts = W.partials.as<XYZZMem<F>>() + (size_t)p.windows * p.segs;
+        k_ones_fold<F, 128><<<ONES_GROUPS, 128, (128 / 4) * sizeof(XYZZMem<F>), st>>>(parts, parts + ONES_PARTS);
+        LAUNCH_CHECK();
+    }
     k_window_sum<F, WS_THREADS><<<(w_hi - w_lo) + (with_ones ? 1 : 0), WS_THREADS, ws_smem, st>>>(
         W.partials.as<XYZZMem<F>>(), p, w_lo, w_hi, W.window_sums.as<XYZZMem<F>>());
     LAUNCH_CHECK();
@@ -335,7 +351,7 @@ static int msm_split_run(Engine &E, MsmWs &W, MsmWs &B, const MsmPlan &p, int sp
 
 // d_bases: native packed images (pack_bases output); d_out: arkworks GroupProjective image
 template <class C>
-int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st) {
+int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st, size_t n_eff) {
     using F = typename C::F;
     if (n == 0) {
         k_sum_jacobian<F><<<1, SUM_THREADS, 0, st>>>(nullptr, 0, reinterpret_cast<JacobianMem<F> *>(d_out));
@@ -343,7 +359,7 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
         return B200_OK;
     }
     if (n > (size_t)1 << 26) return fail(B200_ERR_ARG, "n = %zu exceeds the 2^26 per-call limit", n);
-    MsmPlan p = make_plan<C>(n);
+    MsmPlan p = n_eff ? make_plan_eff<C>(n, n_eff) : make_plan<C>(n);
     MsmWs &W = E.ws[0];
     int rc;
     if ((rc = msm_reserve<C>(W, p, n))) return rc;
@@ -361,7 +377,7 @@ int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, 
 // ready (optional): ready[i] is recorded (on any stream) once job i's inputs are in place; the
 // sort of job i waits for it.  Used by the host-pointer API to overlap H2D copies with compute.
 template <class C>
-int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st, const cudaEvent_t *ready) {
+int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st, const cudaEvent_t *ready, const size_t *n_eff) {
     using F = typename C::F;
     int rc;
     std::vector<MsmPlan> plans(count);
@@ -370,7 +386,7 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
         if (!jobs[i].d_out_jacobian || (jobs[i].n && (!jobs[i].d_bases_packed || !jobs[i].d_scalars)))
             return fail(B200_ERR_ARG, "null pointer in job %zu", i);
         if (jobs[i].n == 0) continue;
-        plans[i] = make_plan<C>(jobs[i].n);
+        plans[i] = n_eff ? make_plan_eff<C>(jobs[i].n, n_eff[i]) : make_plan<C>(jobs[i].n);
     }
     size_t live = 0;                                               // workspace sets alternate over the non-empty jobs
     for (size_t i = 0; i < count; i++)
@@ -492,11 +508,40 @@ int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scal
     return msm_native<C>(E, E.native_bases.p, d_scalars, n, d_out, st);
 }
 
+// how many of the n scalars are neither 0 nor 1 (synchronises `st`: call it before queueing the work it plans)
+template <class C>
+int scalar_census(Engine &E, const void *d_scalars, size_t n, size_t *n_eff, cudaStream_t st) {
+    *n_eff = n;
+    if (n == 0) return B200_OK;
+    int rc = E.census.reserve(16);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(E.census.p, 0, 16, st));
+    k_scalar_census<C::SCALAR_WORDS><<<std::min(ceil_div(n, 256), E.sm_count * 8), 256, 0, st>>>(
+        reinterpret_cast<const uint32_t *>(d_scalars), (uint32_t)n, E.census.as<uint32_t>());
+    LAUNCH_CHECK();
+    uint32_t h[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, E.census.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *n_eff = h[2];
+    return B200_OK;
+}
+
 template <class C>
 int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st) {
     using F = typename C::F;
     k_sum_jacobian<F><<<1, SUM_THREADS, 0, st>>>(reinterpret_cast<const JacobianMem<F> *>(pts), (uint32_t)count,
                                        reinterpret_cast<JacobianMem<F> *>(out));
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
+// out[b] = sum_{i < count} pts[i * batch + b] for b < batch
+template <class C>
+int sum_jacobian_batch(const void *pts, size_t count, size_t batch, void *out, cudaStream_t st) {
+    using F = typename C::F;
+    if (batch == 0) return B200_OK;
+    k_sum_jacobian<F><<<(unsigned)batch, SUM_THREADS, 0, st>>>(reinterpret_cast<const JacobianMem<F> *>(pts), (uint32_t)count,
+                                                     reinterpret_cast<JacobianMem<F> *>(out), (uint32_t)batch);
     LAUNCH_CHECK();
     return B200_OK;
 }
@@ -577,9 +622,11 @@ int field_op(int op, const void *a, const void *b, size_t n, void *out, cudaStre
 #define B200_INSTANTIATE(C)                                                                                       \
     template int msm_device<C>(Engine &, const void *, size_t, const void *, size_t, void *, cudaStream_t);       \
     template int pack_bases<C>(const void *, size_t, size_t, void *, cudaStream_t);                               \
-    template int msm_native<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);               \
-    template int msm_batch<C>(Engine &, const b200_msm_job *, size_t, cudaStream_t, const cudaEvent_t *);         \
+    template int msm_native<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t, size_t);       \
+    template int msm_batch<C>(Engine &, const b200_msm_job *, size_t, cudaStream_t, const cudaEvent_t *, const size_t *); \
+    template int scalar_census<C>(Engine &, const void *, size_t, size_t *, cudaStream_t);                         \
     template int sum_jacobian<C>(const void *, size_t, void *, cudaStream_t);                                     \
+    template int sum_jacobian_batch<C>(const void *, size_t, size_t, void *, cudaStream_t);                       \
     template int fixed_base_mul<C>(Engine &, const void *, const void *, size_t, void *, cudaStream_t);           \
     template int msm_chunks_begin<C>(Engine &, size_t, size_t, cudaStream_t);                                     \
     template int msm_chunks_add<C>(Engine &, const void *, const void *, size_t, cudaEvent_t, int, void *);       \

@@ -213,7 +213,7 @@ void engine_teardown(Engine &En) {
                           &w.window_sums, &w.ones, &w.huge_slices, &w.aff_a, &w.aff_b})
             b->release();
     for (b200::Buffer *b : {&E->h2d_bases, &E->native_bases, &E->scalars, &E->result,
-                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->gather, &E->v_sum, &E->v_pairs1, &E->v_pairs2, &E->v_offsets, &E->v_flags, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->g16_part, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
+                      &E->miller, &E->g2_packed, &E->h2d_g2, &E->gather, &E->v_sum, &E->v_pairs1, &E->v_pairs2, &E->v_offsets, &E->v_flags, &E->v_g1jac, &E->v_g2jac, &E->v_g1aff, &E->v_g2aff, &E->g16_h, &E->g16_tmp, &E->g16_part, &E->census, &E->bh_table, &E->hash_ws, &E->sqrt_tables})
         b->release();
     for (NttDomain &d : E->ntt)
         for (b200::Buffer *b : {&d.consts, &d.pw, &d.tw}) b->release();
@@ -532,6 +532,16 @@ int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void
     REQUIRE_ENGINE();
     cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
     return DISPATCH_CURVE(curve, sum_jacobian, d_points, count, d_out, st);
+}
+
+int b200_sum_jacobian_batch_device(int curve, const void *d_points, size_t count, size_t batch, void *d_out, void *stream) {
+    CurveInfo ci;
+    if (!curve_info(curve, ci)) return fail(B200_ERR_ARG, "unknown curve id %d", curve);
+    if (batch && (!d_out || (count && !d_points))) return fail(B200_ERR_ARG, "null pointer");
+    if (batch > 65535) return fail(B200_ERR_ARG, "batch too large");
+    REQUIRE_ENGINE();
+    cudaStream_t st = stream ? (cudaStream_t)stream : E.stream;
+    return DISPATCH_CURVE(curve, sum_jacobian_batch, d_points, count, batch, d_out, st);
 }
 
 // host-pointer form: `count` contiguous arkworks GroupProjective images in host memory -> their sum (host memory).

@@ -115,7 +115,7 @@ struct Engine {
     // NTT domains: [0] BLS12-377 Fr, [1] BW6-761 Fr (= BLS12-377 Fq)
     NttDomain ntt[2];
     // Groth16 prover composite (inst_groth16.cu): quotient coefficients h, partial MSM results
-    Buffer g16_h, g16_tmp, g16_part;
+    Buffer g16_h, g16_tmp, g16_part, census;
     // batch-verification composites (inst_verify.cu)
     Buffer v_g1jac, v_g2jac, v_g1aff, v_g2aff, v_sum, v_pairs1, v_pairs2, v_offsets, v_flags;
     // hash-to-G1 (inst_hash.cu): affine multiples of the Bowe-Hopwood generators (built at first use), per-call staging
@@ -135,14 +135,17 @@ inline int ceil_div(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 
 // per-curve entry points; each is instantiated in its own translation unit (inst_*.cu)
 template <class C> int msm_device(Engine &E, const void *d_bases, size_t stride, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
-template <class C> int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st);
-template <class C> int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st, const cudaEvent_t *ready = nullptr);
+template <class C> int msm_native(Engine &E, const void *d_bases, const void *d_scalars, size_t n, void *d_out, cudaStream_t st, size_t n_eff = 0);
+template <class C> int scalar_census(Engine &E, const void *d_scalars, size_t n, size_t *n_eff, cudaStream_t st);
+template <class C> int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st, const cudaEvent_t *ready = nullptr,
+                                 const size_t *n_eff = nullptr);
 template <class C> int msm_chunks_begin(Engine &E, size_t n_total, size_t chunk_max, cudaStream_t st);
 template <class C> int msm_chunks_add(Engine &E, const void *d_bases_packed, const void *d_scalars, size_t cnt, cudaEvent_t ready, int last,
                                       void *d_out);
 template <class C> int msm_chunks_finish(Engine &E, void *d_out, cudaStream_t st);
 template <class C> int pack_bases(const void *src_dev, size_t stride, size_t n, void *dst, cudaStream_t st);
 template <class C> int sum_jacobian(const void *pts, size_t count, void *out, cudaStream_t st);
+template <class C> int sum_jacobian_batch(const void *pts, size_t count, size_t batch, void *out, cudaStream_t st);
 template <class C> int fixed_base_mul(Engine &E, const void *base, const void *scalars, size_t n, void *out, cudaStream_t st);
 template <class C> int point_runs(Engine &E, const void *base, const void *scalars, size_t runs, size_t run, void *out, cudaStream_t st);
 template <class C> int batch_to_affine(const void *jac, size_t n, void *out, cudaStream_t st);

@@ -65,6 +65,19 @@ static int groth16_partial_t(Engine &E, int field, const b200_groth16_pk *pk, co
     int rc;
     if ((rc = E.g16_h.reserve(n * sizeof(M)))) return rc;
     char *tmp = reinterpret_cast<char *>(d_partials);
+    const char *assign0 = reinterpret_cast<const char *>(d_assignment);
+    size_t a_lo, a_hi, l_lo, l_hi, h_lo, h_hi;
+    shard_range(num_assign, shard, shards, &a_lo, &a_hi);
+    shard_range(num_aux, shard, shards, &l_lo, &l_hi);
+    shard_range(n - 1, shard, shards, &h_lo, &h_hi);
+    // a witness is mostly bits: count the scalars that actually reach the buckets (neither 0 nor 1) so the a / l / b MSMs
+    // get windows sized for them, not for the length of the assignment (the bucket reduce is paid per bucket: at domain 2^22
+    // it cost each of these MSMs 17 ms for 50 k dense scalars).  One tiny kernel + a 16-byte read per array, before the
+    // witness map is queued so the read waits for nothing.
+    size_t eff_a = a_hi - a_lo, eff_l = l_hi - l_lo;
+    if ((rc = scalar_census<G1>(E, assign0 + a_lo * sizeof(M), a_hi - a_lo, &eff_a, st)) ||
+        (rc = scalar_census<G1>(E, assign0 + (num_assign - num_aux + l_lo) * sizeof(M), l_hi - l_lo, &eff_l, st)))
+        return rc;
     if ((rc = witness_map(E, field, d_a, d_b, d_c, (int)log_n, E.g16_h.p, st))) return rc;
     k_into_repr<FR><<<ceil_div(n, 256), 256, 0, st>>>(E.g16_h.as<M>(), (uint32_t)n);
     LAUNCH_CHECK();
@@ -73,10 +86,6 @@ static int groth16_partial_t(Engine &E, int field, const b200_groth16_pk *pk, co
     const char *aq = reinterpret_cast<const char *>(pk->a_query) + sizeof(AffineMem<F1>);
     const char *bq = reinterpret_cast<const char *>(pk->b_g2_query) + sizeof(AffineMem<F2>);
     const char *lq = reinterpret_cast<const char *>(pk->l_query), *hq = reinterpret_cast<const char *>(pk->h_query);
-    size_t a_lo, a_hi, l_lo, l_hi, h_lo, h_hi;
-    shard_range(num_assign, shard, shards, &a_lo, &a_hi);
-    shard_range(num_aux, shard, shards, &l_lo, &l_hi);
-    shard_range(n - 1, shard, shards, &h_lo, &h_hi);
     // the three G1 MSMs as one pipelined batch (sort / accumulate / tail of consecutive MSMs overlap),
     // then the G2 MSM (same batch when G1 and G2 share the coordinate field, i.e. BW6-761)
     const b200_msm_job jobs[4] = {
@@ -84,11 +93,13 @@ static int groth16_partial_t(Engine &E, int field, const b200_groth16_pk *pk, co
         {lq + l_lo * sizeof(AffineMem<F1>), aux + l_lo * sizeof(M), l_hi - l_lo, tmp + J1},
         {hq + h_lo * sizeof(AffineMem<F1>), E.g16_h.as<char>() + h_lo * sizeof(M), h_hi - h_lo, tmp + 2 * J1},
         {bq + a_lo * sizeof(AffineMem<F2>), assign + a_lo * sizeof(M), a_hi - a_lo, tmp + 3 * J1}};
+    const size_t n_eff[4] = {eff_a, eff_l, h_hi - h_lo, eff_a};
     if constexpr (std::is_same<G1, G2>::value) {
-        if ((rc = msm_batch<G1>(E, jobs, 4, st, nullptr))) return rc;
+        if ((rc = msm_batch<G1>(E, jobs, 4, st, nullptr, n_eff))) return rc;
     } else {
-        if ((rc = msm_batch<G1>(E, jobs, 3, st, nullptr))) return rc;
-        if ((rc = msm_native<G2>(E, jobs[3].d_bases_packed, jobs[3].d_scalars, jobs[3].n, tmp + 3 * J1, st))) return rc;
+        if ((rc = msm_batch<G1>(E, jobs, 3, st, nullptr, n_eff))) return rc;
+        if ((rc = msm_native<G2>(E, jobs[3].d_bases_packed, jobs[3].d_scalars, jobs[3].n, tmp + 3 * J1, st, std::max<size_t>(eff_a, 1))))
+            return rc;
     }
     ENGINE_MARK(st);
     return B200_OK;

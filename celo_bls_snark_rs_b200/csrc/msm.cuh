@@ -552,8 +552,39 @@ __global__ void __launch_bounds__(THREADS) k_huge_buckets(const AffineMem<F> *__
     if (threadIdx.x == 0) slices[(size_t)b * HUGE_SLICES + blockIdx.y] = acc.store();
 }
 
-// unit scalars: ONES_PARTS strided partial sums of the listed bases (weight 1, added after Horner)
-constexpr uint32_t ONES_PARTS = 8192;
+// how many scalars are 0, 1, or neither: a Groth16 witness is mostly bits (crates/epoch-snark/src/api/prover.rs:78), and the
+// window width should follow the scalars that actually reach the buckets (out[0] zeros, out[1] ones, out[2] the rest)
+template <int SW>
+__global__ void __launch_bounds__(256) k_scalar_census(const uint32_t *__restrict__ scalars, uint32_t n, uint32_t *__restrict__ out) {
+    uint32_t zeros = 0, ones = 0, rest = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t *s = scalars + (size_t)i * SW;
+        uint32_t hi = 0;
+#pragma unroll
+        for (int k = 1; k < SW; k++) hi |= __ldg(s + k);
+        const uint32_t lo = __ldg(s);
+        const bool z = (hi | lo) == 0, o = hi == 0 && lo == 1;
+        zeros += z;
+        ones += o;
+        rest += !(z || o);
+    }
+    for (int off = 16; off; off >>= 1) {
+        zeros += __shfl_down_sync(0xffffffffu, zeros, off);
+        ones += __shfl_down_sync(0xffffffffu, ones, off);
+        rest += __shfl_down_sync(0xffffffffu, rest, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (zeros) atomicAdd(out, zeros);
+        if (ones) atomicAdd(out + 1, ones);
+        if (rest) atomicAdd(out + 2, rest);
+    }
+}
+
+// unit scalars: ONES_PARTS strided partial sums of the listed bases (weight 1, added after Horner), folded to ONES_GROUPS
+// sums by k_ones_fold before the window-sum kernel adds those up (a witness holds millions of ones: 8192 parts meant
+// chains of 150 dependent additions and a 8192-term sum on one block -- 8.7 ms per BW6-761 MSM, now about 1 ms)
+constexpr uint32_t ONES_PARTS = 32768;
+constexpr uint32_t ONES_GROUPS = 256;
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_ones_accumulate(const AffineMem<F> *__restrict__ bases,
                                                              const uint32_t *__restrict__ ones, int resume,
@@ -630,8 +661,8 @@ __global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__rest
     // blocks 0 .. (w_hi - w_lo) - 1: the segment partials of window w_lo + block; one block more: the unit-scalar partials
     const bool ones_block = blockIdx.x == (uint32_t)(w_hi - w_lo);
     const uint32_t window = ones_block ? (uint32_t)p.windows : (uint32_t)w_lo + blockIdx.x;
-    const XYZZMem<F> *src = partials + (size_t)window * p.segs;
-    const uint32_t count = ones_block ? ONES_PARTS : p.segs;
+    const XYZZMem<F> *src = partials + (size_t)window * p.segs + (ones_block ? ONES_PARTS : 0u);   // the folded unit-scalar sums
+    const uint32_t count = ones_block ? ONES_GROUPS : p.segs;
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t i = quad; i < count; i += QUADS) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(src + i)));
     if (Q.q == 0) sm[quad] = acc.store();
@@ -644,6 +675,30 @@ __global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__rest
         __syncthreads();
     }
     if (threadIdx.x == 0) window_sums[window] = acc.store();
+}
+
+// block g: folded[g] = sum of parts[g * (ONES_PARTS / ONES_GROUPS) ...) (quads + shared-memory tree, as k_window_sum)
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_ones_fold(const XYZZMem<F> *__restrict__ parts, XYZZMem<F> *__restrict__ folded) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XYZZMem<F> *sm = reinterpret_cast<XYZZMem<F> *>(smem_raw);
+    constexpr int QUADS = THREADS / 4;
+    constexpr uint32_t PER = ONES_PARTS / ONES_GROUPS;
+    const Quad Q;
+    const int quad = threadIdx.x >> 2;
+    const XYZZMem<F> *src = parts + (size_t)blockIdx.x * PER;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = quad; i < PER; i += QUADS) quad_add(Q, acc, XYZZ<F>::load(ldg_mem(src + i)));
+    if (Q.q == 0) sm[quad] = acc.store();
+    __syncthreads();
+    for (int s = QUADS / 2; s > 0; s >>= 1) {
+        if (quad < s) {
+            quad_add(Q, acc, XYZZ<F>::load(sm[quad + s]));
+            if (Q.q == 0) sm[quad] = acc.store();
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) folded[blockIdx.x] = acc.store();
 }
 
 // one quad: Horner over the windows, high to low; result leaves as an arkworks GroupProjective
@@ -691,13 +746,17 @@ __global__ void __launch_bounds__(THREADS) k_pack_bases(const uint32_t *__restri
 constexpr int SUM_THREADS = 128;
 template <class F>
 __global__ void __launch_bounds__(SUM_THREADS) k_sum_jacobian(const JacobianMem<F> *__restrict__ pts, uint32_t count,
-                                                              JacobianMem<F> *__restrict__ out) {
+                                                              JacobianMem<F> *__restrict__ out, uint32_t stride = 1) {
     __shared__ JacobianMem<F> part[SUM_THREADS];
     const int t = threadIdx.x;
+    // block b: out[b] = sum_i pts[i * stride + b]  (one block: the plain sum; a grid of `stride` blocks: the combine of a
+    // whole batch of sharded MSMs after ONE all-gather, rank-major records of `stride` partials each)
+    pts += blockIdx.x;
+    out += blockIdx.x;
     Jacobian<F> total = Jacobian<F>::inf();
     launder(total);
     for (uint32_t i = t; i < count; i += SUM_THREADS) {
-        total.add(Jacobian<F>::from_ark(pts[i]));
+        total.add(Jacobian<F>::from_ark(pts[(size_t)i * stride]));
         launder(total);
     }
     part[t] = total.to_ark();

@@ -28,7 +28,7 @@ PACKED_STRIDE = {k: 2 * v for k, v in COORD_BYTES.items()}
 EXPORTS = [
     "b200_init", "b200_init_devices", "b200_device_count", "b200_msm_sharded", "b200_multi_pairing_bls12_377_sharded", "b200_shutdown", "b200_last_error", "b200_msm", "b200_msm_bls12_377_g1", "b200_msm_bls12_377_g2",
     "b200_msm_bw6_761_g1", "b200_msm_bw6_761_g2", "b200_msm_device", "b200_pack_bases_device", "b200_msm_prepared_device",
-    "b200_sum_jacobian_device", "b200_sum_jacobian", "b200_scalar_mul", "b200_fixed_base_mul_device", "b200_point_runs_device", "b200_batch_to_affine_device", "b200_sync",
+    "b200_sum_jacobian_device", "b200_sum_jacobian_batch_device", "b200_sum_jacobian", "b200_scalar_mul", "b200_fixed_base_mul_device", "b200_point_runs_device", "b200_batch_to_affine_device", "b200_sync",
     "b200_msm_plan", "b200_launch_count", "b200_profile_enable", "b200_profile_read",
     "b200_field_op_device", "b200_multi_pairing_bls12_377", "b200_miller_product_bls12_377_device",
     "b200_final_exp_bls12_377_device", "b200_batch_verify_hashes", "b200_batch_verify_strict_hash", "b200_batch_verify_strict_many",
@@ -123,6 +123,7 @@ def load() -> ctypes.CDLL:
     lib.b200_msm_prepared_device.argtypes = [i32, vp, vp, sz, vp, vp]
     lib.b200_sum_jacobian_device.argtypes = [i32, vp, sz, vp, vp]
     lib.b200_sum_jacobian.argtypes = [i32, vp, sz, vp]
+    lib.b200_sum_jacobian_batch_device.argtypes = [i32, vp, sz, sz, vp, vp]
     lib.b200_fixed_base_mul_device.argtypes = [i32, vp, vp, sz, vp, vp]
     lib.b200_point_runs_device.argtypes = [i32, vp, vp, sz, sz, vp, vp]
     lib.b200_batch_to_affine_device.argtypes = [i32, vp, sz, vp, vp]
@@ -285,6 +286,11 @@ def pack_bases_device(curve: int, src: int, stride: int, n: int, src_on_device: 
 
 def sum_jacobian_device(curve: int, d_points: int, count: int, d_out: int, stream: int = 0):
     _check(load().b200_sum_jacobian_device(curve, d_points, count, d_out, stream or None))
+
+
+def sum_jacobian_batch_device(curve: int, d_points: int, count: int, batch: int, d_out: int, stream: int = 0):
+    """d_out[b] = sum_i d_points[i * batch + b]: combines a batch of sharded MSMs after ONE all-gather."""
+    _check(load().b200_sum_jacobian_batch_device(curve, d_points, count, batch, d_out, stream or None))
 
 
 def fixed_base_mul_device(curve: int, d_base: int, d_scalars: int, n: int, d_out: int, stream: int = 0):

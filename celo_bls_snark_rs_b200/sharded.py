@@ -82,9 +82,11 @@ class ShardedMsm:
                                         for i, (b, s, n) in enumerate(jobs)], stream)
         if self.world == 1:
             return self._partials[:k]
-        for i in range(k):
-            dist.all_gather_into_tensor(self._gathered[i], self._partials[i], group=self.group)
-            E.sum_jacobian_device(self.curve, self._gathered[i].data_ptr(), self.world, self._results[i].data_ptr(), stream)
+        # ONE all-gather for the whole batch (rank-major records of k partial points each) and one combine launch
+        # (block b adds the `world` partials of MSM b); round 1 issued k gathers and k sums after the batch
+        flat = self._gathered.view(-1)[:self.world * k * jb]
+        dist.all_gather_into_tensor(flat, self._partials[:k].reshape(-1), group=self.group)
+        E.sum_jacobian_batch_device(self.curve, flat.data_ptr(), self.world, k, self._results.data_ptr(), stream)
         return self._results[:k]
 
 

@@ -118,6 +118,10 @@ int b200_msm_batch_device(int curve, const b200_msm_job *jobs, size_t count, voi
 /* out = sum of `count` Jacobian points (device pointers).  Used to combine per-GPU
  * partial MSM results after the all-gather. */
 int b200_sum_jacobian_device(int curve, const void *d_points, size_t count, void *d_out_jacobian, void *stream);
+/* d_out[b] = sum_{i < count} d_points[i * batch + b] for b < batch: the combine of a whole BATCH of sharded MSMs after one
+ * all-gather of rank-major records of `batch` partial points each (one launch instead of `batch`). */
+int b200_sum_jacobian_batch_device(int curve, const void *d_points, size_t count, size_t batch, void *d_out_jacobian,
+                                   void *stream);
 /* Host-pointer form: `count` contiguous GroupProjective images -> their sum; replaces the folds of
  * PublicKey::aggregate / Signature::aggregate (crates/bls-crypto/src/bls/public.rs:34, signature.rs:52). */
 int b200_sum_jacobian(int curve, const void *points, size_t count, void *out_jacobian);
