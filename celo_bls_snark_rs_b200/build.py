@@ -49,8 +49,17 @@ def _compile(unit: str, force: bool, verbose: bool) -> str:
     return obj
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, crosschecks: bool = False) -> str:
+    """crosschecks: also compile the cross-check kernels (one-thread-per-pair pairing, batched-affine accumulation, the
+    one-quad Horner ...) that the B200_* environment switches select; the shipped library leaves them out."""
     os.makedirs(OBJ, exist_ok=True)
+    marker = os.path.join(OBJ, "crosschecks.flag")
+    had = os.path.exists(marker)
+    if crosschecks != had:
+        force = True
+        (open(marker, "w").close() if crosschecks else os.remove(marker))
+    if crosschecks and "-DB200_WITH_CROSSCHECKS" not in FLAGS:
+        FLAGS.append("-DB200_WITH_CROSSCHECKS")
     with ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
         objs = list(ex.map(lambda u: _compile(u, force, verbose), UNITS))
     if force or _stale(LIB, objs):
@@ -60,4 +69,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, crosschecks="--crosschecks" in sys.argv))

@@ -250,12 +250,39 @@ struct Coop<Fp2<Fp<P>>> {
 constexpr int COOP_THREADS = 128;
 
 template <class F>
-struct CoopSm {
+struct alignas(16) CoopSm {
     static constexpr int W = Coop<F>::WORDS;
     uint32_t pt[4][W];                               // the running point: x, y, zz, zzz
-    uint32_t in[4][W];                               // the addend
+    uint32_t in[4][W];                               // the addend (16-byte aligned: the TMA bulk copy lands here)
     uint32_t t[8][W];                                // round outputs
+    unsigned long long bar;                          // mbarrier of the bulk copies
 };
+
+// ---- TMA (bulk asynchronous copy) staging of a point into shared memory ---------------------------------------
+// One elected thread arms the mbarrier with the byte count and issues ONE cp.async.bulk for the whole 192 / 384-byte
+// XYZZ record; the copy engine moves it while the block is still doubling, and every thread waits on the barrier's phase
+// when the addend is needed.  (SASS: UBLKCP + SYNCS, profiles/r2_sass_tma_coop.txt.)
+B200_DEV uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+B200_DEV void tma_bar_init(unsigned long long *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+B200_DEV void tma_load(void *smem_dst, const void *gmem_src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of the slot are done (barrier before)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+B200_DEV void tma_wait(unsigned long long *bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(phase)
+                     : "memory");
+    }
+}
 
 template <class F>
 struct CoopPoint {
@@ -385,6 +412,15 @@ struct CoopPoint {
         for (int i = threadIdx.x; i < 4 * W; i += blockDim.x) dst[i / W][i % W] = src ? __ldg(s + i) : 0u;
         __syncthreads();
     }
+    // the same through the copy engine: issue (one thread) ... later ... wait (all threads)
+    B200_DEV static void fetch_issue(CoopSm<F> &sm, const XYZZMem<F> *src) {
+        __syncthreads();                             // everyone is done with the previous addend
+        if (threadIdx.x == 0) tma_load(sm.in, src, (uint32_t)sizeof(XYZZMem<F>), &sm.bar);
+    }
+    B200_DEV static void fetch_wait(CoopSm<F> &sm, uint32_t &phase) {
+        tma_wait(&sm.bar, phase);
+        phase ^= 1u;
+    }
 };
 
 // ---- the Horner combine --------------------------------------------------------------------------------
@@ -402,10 +438,16 @@ __global__ void __launch_bounds__(COOP_THREADS) k_window_combine_coop(const XYZZ
     constexpr int W = C::WORDS;
     __shared__ CoopSm<F> sm;
     const typename C::Ctx c = C::Ctx::make();
-    CP::fetch(sm.pt, nullptr);
+    static_assert(sizeof(XYZZMem<F>) % 16 == 0 && (4 * W * 4) % 16 == 0, "bulk copies move 16-byte multiples to 16-byte aligned slots");
+    if (threadIdx.x == 0) tma_bar_init(&sm.bar);
+    CP::fetch(sm.pt, nullptr);                       // (contains the barrier that publishes the mbarrier)
+    uint32_t phase = 0;
+    // window sum w is staged by the copy engine while the c doublings that precede its addition run
+    if (w_hi > w_lo) CP::fetch_issue(sm, window_sums + (w_hi - 1));
     for (int w = w_hi - 1; w >= w_lo; w--) {
-        CP::fetch(sm.in, window_sums + w);
+        CP::fetch_wait(sm, phase);
         CP::add(c, sm);
+        if (w > w_lo) CP::fetch_issue(sm, window_sums + (w - 1));
         const int doublings = w > w_lo ? c_bits : shift;
         for (int k = 0; k < doublings; k++) CP::dbl(c, sm);
     }

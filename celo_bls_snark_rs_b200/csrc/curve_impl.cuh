@@ -6,9 +6,18 @@
 namespace b200 {
 
 template <class C> struct CurveTraits;
-template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128; static constexpr bool AFFINE = true; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false; };
-template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false; };
+// AFFINE: the curve also has the experimental batched-affine accumulate kernels (compiled only with B200_WITH_CROSSCHECKS);
+// SHARED_MUL: the accumulate kernel multiplies through one out-of-line product body; COOP_COMBINE: the Horner combine runs
+// on four warps with one limb per lane (coop.cuh) -- 2.5x faster for the 24-limb field and for Fq2, no faster for the
+// 12-limb field (0.9 against 0.85 ms) where it only costs the neighbouring MSMs of a pipelined batch more issue slots
+#ifdef B200_WITH_CROSSCHECKS
+constexpr bool B200_AFFINE_BUILD = true;
+#else
+constexpr bool B200_AFFINE_BUILD = false;
+#endif
+template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true; };
+template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
 // keeping enough buckets in flight to fill 148 SMs.
@@ -129,6 +138,7 @@ static int msm_reserve(MsmWs &W, const MsmPlan &p, size_t n) {
 
 template <class C>
 static int msm_stage_sort(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_scalars, size_t n, cudaStream_t st, int split = 0) {
+    NvtxRange range("msm.sort");
     size_t total = (size_t)p.windows * p.nb;
     uint32_t tiles = (uint32_t)ceil_div(total, SCAN_TILE);
     const uint32_t *sc = reinterpret_cast<const uint32_t *>(d_scalars);
@@ -175,6 +185,7 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
                                 MsmWs *Bp = nullptr, int resume = 0, int split = 0, int group = -1) {
     using F = typename C::F;
     using T = CurveTraits<C>;
+    NvtxRange range("msm.accumulate");
     MsmWs &B = Bp ? *Bp : W;
     const size_t all = (size_t)p.windows * p.nb, total_b = (size_t)split * p.nb, total_a = all - total_b;
     const size_t total = group < 0 ? all : (group ? total_b : total_a);
@@ -208,7 +219,7 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
     // 12-limb curves: the accumulate kernel with ONE out-of-line product body (12 KB of code instead of 117 KB)
     // is 1.8 % faster under the pipelined batch (7.48 against 7.61 ms); B200_MSM_SHAREDMUL=0 selects the inlined one
     static const bool shared_mul = !(getenv("B200_MSM_SHAREDMUL") && !atoi(getenv("B200_MSM_SHAREDMUL")));
-    if (!affine && shared_mul && T::AFFINE)
+    if (!affine && shared_mul && T::SHARED_MUL)
         k_bucket_accumulate_shared<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
             <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
                 bases, W.sorted.as<uint32_t>(), offsets, order, (uint32_t)total, p.big, resume,
@@ -272,12 +283,14 @@ static int msm_stage_reduce(MsmWs &W, const MsmPlan &p, int w_lo, int w_hi, bool
 template <class C>
 static int msm_stage_tail(MsmWs &W, const MsmPlan &p, void *d_out, cudaStream_t st) {
     using F = typename C::F;
+    NvtxRange range("msm.tail");
     int rc = msm_stage_reduce<C>(W, p, 0, p.windows, true, st);
     if (rc) return rc;
-    // Horner over the windows: four warps share every point operation (coop.cuh); B200_COMBINE_QUAD=1 selects the
-    // one-quad kernel it replaced (cross-check)
-    static const bool quad_combine = getenv("B200_COMBINE_QUAD") && atoi(getenv("B200_COMBINE_QUAD"));
-    if (quad_combine)
+    // Horner over the windows: one quad (12-limb field) or four warps sharing every point operation (coop.cuh);
+    // B200_COMBINE = quad | coop overrides the per-curve choice (experiments)
+    static const char *force = getenv("B200_COMBINE");
+    const bool coop = force ? force[0] == 'c' : CurveTraits<C>::COOP_COMBINE;
+    if (!coop)
         k_window_combine<F><<<1, 32, 0, st>>>(W.window_sums.as<XYZZMem<F>>(), p, reinterpret_cast<JacobianMem<F> *>(d_out));
     else
         k_window_combine_coop<F><<<1, COOP_THREADS, 0, st>>>(W.window_sums.as<XYZZMem<F>>(), 0, p.windows, p.c, 0,

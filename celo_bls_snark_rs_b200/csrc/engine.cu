@@ -348,8 +348,23 @@ static int msm_host(Engine &E, int curve, const void *bases, size_t stride, cons
         }
         return DISPATCH_CURVE(curve, msm_device, E, d_bases, stride, E.scalars.p, n, res, st);
     }
-    const int chunks = (int)std::min<size_t>(Engine::MAX_CHUNKS, std::max<size_t>(2, n / HOST_CHUNK_PAIRS));
-    const size_t chunk_max = (n + chunks - 1) / chunks + 1;
+    // chunk bounds: about 2^18 pairs each, but the first two are a quarter and a half of that -- the accumulation can only
+    // start once the first chunk has crossed PCIe and been sorted, so a short first chunk trims the exposed latency
+    size_t bound[Engine::MAX_CHUNKS + 1];
+    int chunks = 0;
+    {
+        const size_t body = std::max<size_t>(HOST_CHUNK_PAIRS, (n + Engine::MAX_CHUNKS - 3) / (Engine::MAX_CHUNKS - 2));
+        size_t at = 0;
+        bound[0] = 0;
+        for (size_t want : {HOST_CHUNK_PAIRS / 4, HOST_CHUNK_PAIRS / 2}) {
+            if (n - at > want + HOST_CHUNK_PAIRS / 2) bound[++chunks] = (at += want);
+        }
+        while (n - at > body + body / 4 && chunks < Engine::MAX_CHUNKS - 1) bound[++chunks] = (at += body);
+        bound[++chunks] = n;
+    }
+    size_t chunk_max = 0;
+    for (int c = 0; c < chunks; c++) chunk_max = std::max(chunk_max, bound[c + 1] - bound[c]);
+    chunk_max += 1;
     const size_t rec = stride + ci.scalar_bytes;
     const bool pinned = host_is_pinned(bases) && host_is_pinned(scalars);
     if (!pinned && E.pinned_cap < chunk_max * rec) {          // staging slots: grow-only
@@ -378,7 +393,7 @@ static int msm_host(Engine &E, int curve, const void *bases, size_t stride, cons
             workers.emplace_back([&, t]() {
                 for (int c = 0; c < chunks; c++) {
                     while (free_upto.load(std::memory_order_acquire) <= c) std::this_thread::yield();
-                    const size_t lo = n * c / chunks, cnt = n * (c + 1) / chunks - lo;
+                    const size_t lo = bound[c], cnt = bound[c + 1] - lo;
                     char *slot = reinterpret_cast<char *>(E.pinned[c & 1]);
                     const size_t bbytes = cnt * stride, sbytes = cnt * ci.scalar_bytes, total = bbytes + sbytes;
                     const size_t a = total * t / STAGE_THREADS, b = total * (t + 1) / STAGE_THREADS;   // this thread's byte range
@@ -398,7 +413,7 @@ static int msm_host(Engine &E, int curve, const void *bases, size_t stride, cons
     };
     rc = B200_OK;
     for (int c = 0; c < chunks && rc == B200_OK; c++) {
-        const size_t lo = n * c / chunks, cnt = n * (c + 1) / chunks - lo;
+        const size_t lo = bound[c], cnt = bound[c + 1] - lo;
         const char *src_b = hb + lo * stride, *src_s = hs + lo * ci.scalar_bytes;
         if (!pinned) {
             while (staged[c].load(std::memory_order_acquire) < STAGE_THREADS) std::this_thread::yield();

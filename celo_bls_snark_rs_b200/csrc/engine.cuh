@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/b200_bls.h"
 #include "../../include/bls_snark_sys_compat.h"
 #include "msm.cuh"
@@ -45,6 +47,15 @@ void count_launch();
         CUDA_TRY(cudaEventRecord(E.done, (st)));                                                         \
         E.has_pending = true;                                                                            \
     } while (0)
+
+// NVTX range around the host-side issue of a stage (header-only NVTX3: a no-op unless a profiler is attached); the
+// three stages of an MSM show up as msm.sort / msm.accumulate / msm.tail on the timeline
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct Buffer {
     void *p = nullptr;

@@ -4,23 +4,15 @@
 
 namespace b200 {
 
-// B200_PAIRING_THREAD=1 selects the one-thread-per-pair kernels of pairing.cuh (cross-check path)
-static bool thread_path() {
-    static const bool v = getenv("B200_PAIRING_THREAD") && atoi(getenv("B200_PAIRING_THREAD"));
-    return v;
-}
-
-// B200_FINAL_EXP_WARP=1 selects the one-warp final exponentiation (cross-check of the block-cooperative one)
-static bool warp_final_exp() {
-    static const bool v = getenv("B200_FINAL_EXP_WARP") && atoi(getenv("B200_FINAL_EXP_WARP"));
-    return v;
-}
-
-// B200_PAIRING_SINGLE=1: one pair per warp (k_w_miller_loop), the cross-check of the two-pair kernel
-static bool single_pair_warps() {
-    static const bool v = getenv("B200_PAIRING_SINGLE") && atoi(getenv("B200_PAIRING_SINGLE"));
-    return v;
-}
+// Cross-check kernels (one thread per pair, one pair per warp, one-warp final exponentiation) are compiled only with
+// -DB200_WITH_CROSSCHECKS (python -m celo_bls_snark_rs_b200.build --crosschecks); the shipped library holds the product
+// kernels alone.  With them compiled in: B200_PAIRING_THREAD=1, B200_PAIRING_SINGLE=1, B200_FINAL_EXP_WARP=1 select them.
+#ifdef B200_WITH_CROSSCHECKS
+static bool env_on(const char *name) { return getenv(name) && atoi(getenv(name)); }
+static bool thread_path() { static const bool v = env_on("B200_PAIRING_THREAD"); return v; }
+static bool warp_final_exp() { static const bool v = env_on("B200_FINAL_EXP_WARP"); return v; }
+static bool single_pair_warps() { static const bool v = env_on("B200_PAIRING_SINGLE"); return v; }
+#endif
 
 // Miller values of n pairs multiplied together -> d_out (one Fq12 image, before the final exponentiation)
 int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out, cudaStream_t st) {
@@ -37,17 +29,23 @@ int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, 
         g2 = reinterpret_cast<const AffineMem<PFq2> *>(g1 + 1);
         n = 1;
     }
+#ifdef B200_WITH_CROSSCHECKS
     if (thread_path()) {
         constexpr int TH = 64;
         k_miller_loop<TH><<<ceil_div(n, TH), TH, 0, st>>>(g1, g2, (uint32_t)n, vals);
         LAUNCH_CHECK();
         k_fq12_product<128><<<1, 128, 0, st>>>(vals, (uint32_t)n);
         LAUNCH_CHECK();
-    } else {
+    } else
+#endif
+    {
         uint32_t live = (uint32_t)n;                 // Miller values to fold
+#ifdef B200_WITH_CROSSCHECKS
         if (single_pair_warps()) {
             k_w_miller_loop<<<ceil_div(n, W_WARPS), 32 * W_WARPS, 0, st>>>(g1, g2, (uint32_t)n, vals);
-        } else {                                     // two pairs per warp share one Miller variable
+        } else
+#endif
+        {                                            // two pairs per warp share one Miller variable
             live = (uint32_t)((n + 1) / 2);
             k_w2_miller_loop<<<ceil_div(live, W_WARPS), 32 * W_WARPS, 0, st>>>(g1, g2, (uint32_t)n, vals);
         }
@@ -92,11 +90,14 @@ int final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_i
         k_fq12_product<128><<<1, 128, 0, st>>>(vals, (uint32_t)count);          // a handful of values (one per GPU)
         LAUNCH_CHECK();
     }
+#ifdef B200_WITH_CROSSCHECKS
     if (thread_path()) {
         k_final_exp<<<1, 32, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one);   // d_out may be NULL
     } else if (warp_final_exp()) {
         k_w_final_exp<<<1, 32, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one, vals + count);
-    } else {
+    } else
+#endif
+    {
         k_b_final_exp<<<1, B_THREADS, 0, st>>>(vals, reinterpret_cast<Fq12::Mem *>(d_out), d_is_one);
     }
     LAUNCH_CHECK();

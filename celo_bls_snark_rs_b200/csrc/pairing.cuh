@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(THREADS) k_fq12_product(Fq12::Mem *__restrict_
     }
 }
 
+#ifdef B200_WITH_CROSSCHECKS                        // cross-check kernels are not part of the shipped library (build.py --crosschecks)
 // Bls12::final_exponentiation (eprint 2016/130 table 1 chain), one thread
 __global__ void k_final_exp(const Fq12::Mem *__restrict__ in, Fq12::Mem *__restrict__ out, int *__restrict__ is_one) {
     if (blockIdx.x || threadIdx.x) return;
@@ -287,5 +288,6 @@ __global__ void k_final_exp(const Fq12::Mem *__restrict__ in, Fq12::Mem *__restr
     if (out) out[0] = f12_store(res);
     if (is_one) *is_one = f12_is_one(res) ? 1 : 0;
 }
+#endif
 
 }  // namespace b200

@@ -250,6 +250,7 @@ B200_DEV void w_line_to_power(const Fq2Slot *s, FqImg *B, int lane) {
 // ---- kernels ---------------------------------------------------------------------------------------
 constexpr int W_WARPS = 4;                           // warps (pairings) per block
 
+#ifdef B200_WITH_CROSSCHECKS
 // warp w: Miller value of pair w -> out[w] (tower image); infinite members give one
 __global__ void __launch_bounds__(32 * W_WARPS) k_w_miller_loop(const AffineMem<PFq> *__restrict__ g1,
                                                                 const AffineMem<PFq2> *__restrict__ g2, uint32_t n,
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(32 * W_WARPS) k_w_miller_loop(const AffineMem<
     }
     w_f12_store_global(S.f[fa], out + pair, lane);
 }
+#endif
 
 // ---- two pairs per warp, one shared f ----------------------------------------------------------------
 // prod_i f_i can be accumulated in ONE Miller variable: f <- f^2 * line_0 * line_1 per bit, so the
@@ -468,6 +470,7 @@ B200_DEV int w_exp_by_x(WarpScratch &S, FqImg *base /* separate 12-entry buffer 
     return cur;
 }
 
+#ifdef B200_WITH_CROSSCHECKS
 // one warp: Bls12::final_exponentiation (2016/130 table 1 chain) of vals[0]
 __global__ void __launch_bounds__(32) k_w_final_exp(const Fq12::Mem *__restrict__ in, Fq12::Mem *__restrict__ out,
                                                     int *__restrict__ is_one, Fq12::Mem *__restrict__ tmp /* 1 image */) {
@@ -532,6 +535,7 @@ __global__ void __launch_bounds__(32) k_w_final_exp(const Fq12::Mem *__restrict_
         if (lane == 0) *is_one = all == 0xffffffffu ? 1 : 0;
     }
 }
+#endif
 
 // ---- block-cooperative final exponentiation ---------------------------------------------------------
 // The final exponentiation is ONE Fq12 chain of ~350 dependent products: with one warp each product

@@ -26,7 +26,8 @@ def eng():
     return E
 
 
-@pytest.mark.parametrize("family,log_n,num_inputs", [("bls12_377", 6, 3), ("bw6_761", 6, 2), ("bls12_377", 9, 5), ("bw6_761", 8, 1)])
+@pytest.mark.parametrize("family,log_n,num_inputs", [("bls12_377", 6, 3), ("bw6_761", 6, 2), ("bls12_377", 9, 5), ("bw6_761", 8, 1),
+                                                     ("bw6_761", 16, 3), ("bls12_377", 16, 2)])
 def test_prover_arithmetic_matches_oracle_composition(eng, family, log_n, num_inputs):
     import torch
     fam_id, g1n, g2n, f = FAMILIES[family]
@@ -52,7 +53,10 @@ def test_prover_arithmetic_matches_oracle_composition(eng, family, log_n, num_in
     assert len(h_query) == n - 1 and len(l_query) == num_aux
 
     # ---- oracle composition ----
-    h = N.witness_map(f, a, b, c)
+    if log_n <= 10:
+        h = N.witness_map(f, a, b, c)
+    else:                                                 # the C port of the same chain (pinned against N.witness_map in the CPU suite)
+        h = f.from_mont_array(C.witness_map(f.id, f.to_mont_array(a), f.to_mont_array(b), f.to_mont_array(c), log_n, threads=8))
     sc = lambda vals: L1.scalars_array(vals)
     msm = lambda L, pts, vals: L.jacobian_to_affine(C.msm(L, L.affine_records(pts), sc(vals))) if vals else None
     a_acc = msm(L1, a_query[1:], assign)
