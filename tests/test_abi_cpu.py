@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     # the bls-snark-sys names re-exported for existing C / cgo consumers (include/bls_snark_sys_compat.h)
     compat = open(os.path.join(ROOT, "include", "bls_snark_sys_compat.h")).read()
     compat = re.sub(r"/\*.*?\*/", "", compat, flags=re.S)
-    names = sorted(set(re.findall(r"\bbool\s+([a-z_]+)\s*\(", compat)))
+    names = sorted(set(re.findall(r"\bbool\s+([a-z_0-9]+)\s*\(", compat)))
     assert names == sorted(E.COMPAT_EXPORTS)
     for s in names:
         assert hasattr(lib, s), s
