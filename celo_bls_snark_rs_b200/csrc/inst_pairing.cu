@@ -14,6 +14,18 @@ static bool warp_final_exp() { static const bool v = env_on("B200_FINAL_EXP_WARP
 static bool single_pair_warps() { static const bool v = env_on("B200_PAIRING_SINGLE"); return v; }
 #endif
 
+// `warps` warps of the two-pairs-per-warp Miller kernel; B200_MILLER_WARPS = 1 | 2 | 4 warps per block (default 2)
+static void launch_w2_miller(const AffineMem<PFq> *g1, const AffineMem<PFq2> *g2, uint32_t n, uint32_t warps, Fq12::Mem *vals,
+                             cudaStream_t st) {
+    static const int ww = getenv("B200_MILLER_WARPS") ? atoi(getenv("B200_MILLER_WARPS")) : 2;
+    if (ww == 4)
+        k_w2_miller_loop<4><<<ceil_div(warps, 4), 128, 0, st>>>(g1, g2, n, vals);
+    else if (ww == 1)
+        k_w2_miller_loop<1><<<warps, 32, 0, st>>>(g1, g2, n, vals);
+    else
+        k_w2_miller_loop<2><<<ceil_div(warps, 2), 64, 0, st>>>(g1, g2, n, vals);
+}
+
 // Miller values of n pairs multiplied together -> d_out (one Fq12 image, before the final exponentiation)
 int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, size_t n, void *d_out, cudaStream_t st) {
     static_assert(sizeof(Fq12::Mem) == 576, "arkworks Fq12 image is 576 bytes");
@@ -47,7 +59,7 @@ int miller_product(Engine &E, const void *d_g1_packed, const void *d_g2_packed, 
 #endif
         {                                            // two pairs per warp share one Miller variable
             live = (uint32_t)((n + 1) / 2);
-            k_w2_miller_loop<<<ceil_div(live, W_WARPS), 32 * W_WARPS, 0, st>>>(g1, g2, (uint32_t)n, vals);
+            launch_w2_miller(g1, g2, (uint32_t)n, live, vals, st);
         }
         LAUNCH_CHECK();
         // fold: live -> <= 4 * SMs -> <= 32 -> 1 partial products
@@ -70,9 +82,8 @@ int pairing_checks_2(Engine &E, const void *d_g1_packed, const void *d_g2_packed
     int rc = E.miller.reserve(count * sizeof(Fq12::Mem));
     if (rc) return rc;
     Fq12::Mem *vals = E.miller.as<Fq12::Mem>();
-    k_w2_miller_loop<<<ceil_div(count, W_WARPS), 32 * W_WARPS, 0, st>>>(reinterpret_cast<const AffineMem<PFq> *>(d_g1_packed),
-                                                                          reinterpret_cast<const AffineMem<PFq2> *>(d_g2_packed),
-                                                                          (uint32_t)(2 * count), vals);
+    launch_w2_miller(reinterpret_cast<const AffineMem<PFq> *>(d_g1_packed), reinterpret_cast<const AffineMem<PFq2> *>(d_g2_packed),
+                     (uint32_t)(2 * count), (uint32_t)count, vals, st);
     LAUNCH_CHECK();
     k_b_final_exp<<<(unsigned)count, B_THREADS, 0, st>>>(vals, nullptr, d_flags);
     LAUNCH_CHECK();

@@ -389,12 +389,16 @@ B200_DEV void w_init_line_state(Fq2Slot *s, const Affine<PFq> &p, const Affine<P
 
 // warp w: out[w] = Miller value of pair 2w  *  Miller value of pair 2w + 1 (tower image);
 // pairs with an infinite member (and the missing partner of an odd n) contribute one
-__global__ void __launch_bounds__(32 * W_WARPS) k_w2_miller_loop(const AffineMem<PFq> *__restrict__ g1,
-                                                                 const AffineMem<PFq2> *__restrict__ g2, uint32_t n,
-                                                                 Fq12::Mem *__restrict__ out) {
-    __shared__ WarpScratch2 scratch[W_WARPS];
+// WW warps per block: the warps are independent, so the block size only decides how evenly 2049 warps (config 2) spread
+// over 148 SMs -- 513 blocks of 4 leave some SMs with 4 blocks and some with 3 (the kernel ends with the fullest SM),
+// 1025 blocks of 2 put 13 or 14 warps on every SM
+template <int WW>
+__global__ void __launch_bounds__(32 * WW) k_w2_miller_loop(const AffineMem<PFq> *__restrict__ g1,
+                                                            const AffineMem<PFq2> *__restrict__ g2, uint32_t n,
+                                                            Fq12::Mem *__restrict__ out) {
+    __shared__ WarpScratch2 scratch[WW];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t w = blockIdx.x * W_WARPS + wib;
+    const uint32_t w = blockIdx.x * WW + wib;
     if (2 * w >= n) return;                          // whole warps leave together
     WarpScratch2 &S = scratch[wib];
     int live = 0;                                    // finite pairs placed in slot sets 0 .. live-1
