@@ -805,6 +805,35 @@ int b200_deserialize_points(int kind, const void *bytes, size_t n, int check_sub
 void b200_blake2s_personal(const uint8_t *data, size_t len, const uint8_t *personal8, uint8_t *out32) {
     blake2s_personal(data, len, personal8, out32);
 }
+void b200_blake2s_param(const uint8_t *data, size_t len, int digest_len, int fanout, int depth, uint32_t leaf_len, uint64_t node_offset,
+                        int inner_len, const uint8_t *personal8, uint8_t *out) {
+    blake2s_param(data, len, digest_len, fanout, depth, leaf_len, node_offset, inner_len, personal8, out);
+}
+int b200_encode_epoch_block(int cip22, uint16_t index, uint8_t round, const uint8_t *epoch_entropy, const uint8_t *parent_entropy,
+                            uint32_t maximum_non_signers, size_t maximum_validators, const uint8_t *keys96, size_t nkeys,
+                            uint8_t **out_inner, size_t *out_inner_len, uint8_t **out_extra, size_t *out_extra_len) {
+    if (!out_inner || !out_inner_len || (nkeys && !keys96) || (cip22 && (!out_extra || !out_extra_len))) return fail(B200_ERR_ARG, "null pointer");
+    std::vector<uint8_t> inner, extra;
+    epoch_block_encode(cip22, index, round, epoch_entropy, parent_entropy, maximum_non_signers, maximum_validators, keys96, nkeys, &inner,
+                       &extra);
+    auto leak = [](const std::vector<uint8_t> &v) {
+        uint8_t *p = (uint8_t *)malloc(v.size() ? v.size() : 1);
+        if (p && !v.empty()) memcpy(p, v.data(), v.size());
+        return p;
+    };
+    *out_inner = leak(inner);
+    *out_inner_len = inner.size();
+    if (!*out_inner) return fail(B200_ERR_ARG, "out of memory");
+    if (cip22) {
+        *out_extra = leak(extra);
+        *out_extra_len = extra.size();
+        if (!*out_extra) {
+            free(*out_inner);
+            return fail(B200_ERR_ARG, "out of memory");
+        }
+    }
+    return B200_OK;
+}
 
 int b200_verify_epochs(const uint8_t *vk, size_t vk_len, const uint8_t *proof, size_t proof_len, const void *first_epoch,
                        const void *last_epoch, int *out_ok) {

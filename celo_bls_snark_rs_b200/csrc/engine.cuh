@@ -193,6 +193,11 @@ int epoch_verify(Engine &E, const uint8_t *vk, size_t vk_len, const uint8_t *pro
 int epoch_public_inputs(Engine &E, const EpochBlockFFI &first, const EpochBlockFFI &last, std::vector<uint64_t> *inputs, int *ok,
                         std::string *why);
 void blake2s_personal(const uint8_t *data, size_t len, const uint8_t personal[8], uint8_t out[32]);
+void blake2s_param(const uint8_t *data, size_t len, int digest_len, int fanout, int depth, uint32_t leaf_len, uint64_t node_offset,
+                   int inner_len, const uint8_t personal[8], uint8_t *out);
+void epoch_block_encode(int cip22, uint16_t index, uint8_t round, const uint8_t *epoch_entropy, const uint8_t *parent_entropy,
+                        uint32_t maximum_non_signers, size_t maximum_validators, const uint8_t *keys96, size_t nkeys,
+                        std::vector<uint8_t> *inner, std::vector<uint8_t> *extra);
 // batched hash-to-G1 (inst_hash.cu)
 int hash_to_g1(Engine &E, int hasher, int flags, const uint8_t *domain, size_t domain_len, const b200_hash_input *inputs, size_t n,
                void *out, uint32_t *out_attempts);

@@ -68,10 +68,16 @@ void blake2s_compress(uint32_t h[8], const uint8_t block[64], uint64_t t, bool l
 }
 }  // namespace
 
-void blake2s_personal(const uint8_t *data, size_t len, const uint8_t personal[8], uint8_t out[32]) {
+// full parameter block (RFC 7693 section 2.5, sequential or tree parameters): what DirectHasher's XOF needs
+// (crates/bls-crypto/src/hashers/direct.rs:41-79: fanout 0, depth 0, leaf 32, inner 32, node offset i | digest length << 32)
+void blake2s_param(const uint8_t *data, size_t len, int digest_len, int fanout, int depth, uint32_t leaf_len, uint64_t node_offset,
+                   int inner_len, const uint8_t personal[8], uint8_t *out) {
     uint32_t h[8];
     for (int i = 0; i < 8; i++) h[i] = BLAKE2S_IV[i];
-    h[0] ^= 0x01010020u;                                 // digest 32, no key, fanout 1, depth 1
+    h[0] ^= (uint32_t)digest_len | ((uint32_t)fanout << 16) | ((uint32_t)depth << 24);
+    h[1] ^= leaf_len;
+    h[2] ^= (uint32_t)node_offset;
+    h[3] ^= (uint32_t)((node_offset >> 32) & 0xffffu) | ((uint32_t)inner_len << 24);       // node depth 0
     h[6] ^= (uint32_t)personal[0] | ((uint32_t)personal[1] << 8) | ((uint32_t)personal[2] << 16) | ((uint32_t)personal[3] << 24);
     h[7] ^= (uint32_t)personal[4] | ((uint32_t)personal[5] << 8) | ((uint32_t)personal[6] << 16) | ((uint32_t)personal[7] << 24);
     uint8_t block[64];
@@ -83,8 +89,10 @@ void blake2s_personal(const uint8_t *data, size_t len, const uint8_t personal[8]
     memset(block, 0, 64);
     if (len - off) memcpy(block, data + off, len - off);
     blake2s_compress(h, block, len, true);
-    for (int i = 0; i < 8; i++)
-        for (int k = 0; k < 4; k++) out[4 * i + k] = (uint8_t)(h[i] >> (8 * k));
+    for (int i = 0; i < digest_len; i++) out[i] = (uint8_t)(h[i >> 2] >> (8 * (i & 3)));
+}
+void blake2s_personal(const uint8_t *data, size_t len, const uint8_t personal[8], uint8_t out[32]) {
+    blake2s_param(data, len, 32, 1, 1, 0, 0, 0, personal, out);                            // digest 32, no key, fanout 1, depth 1
 }
 
 // ---- CIP22 bit encodings (host) ------------------------------------------------------------------------
@@ -148,6 +156,44 @@ std::vector<uint64_t> pack_376(const Bits &bits) {
     return out;
 }
 }  // namespace
+
+// bits (big-endian string) -> little-endian bytes (bls-gadgets utils.rs:2-21 bits_be_to_bytes_le)
+static std::vector<uint8_t> bits_be_to_bytes_le(const Bits &bits) {
+    std::vector<uint8_t> bytes((bits.size() + 7) / 8, 0);
+    const size_t n = bits.size();
+    for (size_t i = 0; i < n; i++)
+        if (bits[n - 1 - i]) bytes[i >> 3] |= (uint8_t)(1u << (i & 7));
+    return bytes;
+}
+// EpochBlock::encode_to_bytes (pre-Donut) and ::encode_inner_to_bytes_cip22 (crates/epoch-snark/src/epoch_block.rs:106-114,
+// 152-171, 191-211) from the keys' compressed encodings (96 bytes each: the wire's sign flag is encode_public_key's y bit).
+void epoch_block_encode(int cip22, uint16_t index, uint8_t round, const uint8_t *epoch_entropy, const uint8_t *parent_entropy,
+                        uint32_t maximum_non_signers, size_t maximum_validators, const uint8_t *keys96, size_t nkeys,
+                        std::vector<uint8_t> *inner, std::vector<uint8_t> *extra) {
+    Bits bits, xbits;
+    auto push_keys = [&]() {
+        for (size_t i = 0; i < nkeys; i++) push_public_key(bits, keys96 + 96 * i, (keys96[96 * i + 95] >> 7) & 1u);
+    };
+    if (!cip22) {
+        push_le_int(bits, index, 2);
+        push_le_int(bits, maximum_non_signers, 4);
+        push_keys();
+        *inner = bits_be_to_bytes_le(bits);
+        return;
+    }
+    push_le_int(xbits, index, 2);
+    push_le_int(xbits, round, 1);
+    push_le_int(xbits, maximum_non_signers, 4);
+    for (const uint8_t *entropy : {epoch_entropy, parent_entropy}) {
+        if (entropy) push_le_bytes(bits, entropy, 16);
+        else bits.insert(bits.end(), 128, 0);
+    }
+    push_keys();
+    for (size_t i = nkeys; i < maximum_validators; i++)
+        push_public_key(bits, reinterpret_cast<const uint8_t *>(G2_GENERATOR_X_CANONICAL), G2_GENERATOR_Y_OVER_HALF != 0);
+    *inner = bits_be_to_bytes_le(bits);
+    *extra = bits_be_to_bytes_le(xbits);
+}
 
 // ---- device-side decoding ------------------------------------------------------------------------------
 // kind: 0 = BLS12-377 G2, 1 = BW6-761 G1, 2 = BW6-761 G2.  d_src: n x 96 bytes; d_out: n packed affine records;

@@ -2,7 +2,8 @@
 // seam "B2"): private keys and signing, the hash_* byte helpers, the uncompressed encodings, key subtraction, init.
 //
 //   crates/bls-snark-sys/src/signatures.rs:19-91     generate_private_key, private_key_to_public_key, sign_message, sign_pop
-//   crates/bls-snark-sys/src/signatures.rs:93-242    hash_direct, hash_direct_with_attempt, hash_composite, hash_crh, hash_composite_cip22
+//   crates/bls-snark-sys/src/signatures.rs:93-242    hash_direct, hash_direct_with_attempt, hash_composite, hash_crh, hash_direct_first_step, hash_composite_cip22
+//   crates/bls-snark-sys/src/snark/epoch_block.rs:16-106 encode_epoch_block_to_bytes, encode_epoch_block_to_bytes_cip22
 //   crates/bls-snark-sys/src/signatures.rs:454-483   aggregate_public_keys_subtract
 //   crates/bls-snark-sys/src/serialization.rs:13-105 (de)serialize_private_key, deserialize_public_key_cached, serialize_*_uncompressed
 //   crates/bls-snark-sys/src/serialization.rs:224-234 destroy_private_key          crates/bls-snark-sys/src/lib.rs:29-34 init
@@ -10,7 +11,7 @@
 // Handles are the Rust types' memory images, as in sys_compat.cu: PrivateKey = Fr (32 bytes, the Montgomery residue).
 // Host code here is byte and integer work only (Montgomery <-> canonical conversions of single field elements for the
 // wire formats, negating a coordinate); hashing, scalar multiplications and sums run on the device.
-// Not exported (3 of the reference's 36): hash_direct_first_step and the two encode_epoch_block_to_bytes helpers.
+// With these every one of the reference's 36 exports exists under its own name.
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -373,6 +374,66 @@ bool hash_crh(const uint8_t *in_message, int in_message_len, int hash_bytes, uin
     std::vector<uint8_t> v(48, 0);
     if (b200_hash_to_g1(B200_HASHER_COMPOSITE, B200_HASH_CRH_ONLY, SIG_DOMAIN, 8, &in, 1, v.data(), nullptr) != B200_OK) return engine_failed(fn);
     return hand_out(fn, v, out_hash, out_len);
+}
+
+// DirectHasher.hash(SIG_DOMAIN, message, hash_bytes) = xof(crh(message)) (crates/bls-crypto/src/hashers/direct.rs:23-79,
+// signatures.rs:191-212): pure byte work -- two or more Blake2s calls on the host, no field element involved
+bool hash_direct_first_step(const uint8_t *in_message, int in_message_len, int hash_bytes, uint8_t **out_hash, int *out_len) {
+    const char *fn = "hash_direct_first_step";
+    if (!out_hash || !out_len || in_message_len < 0 || (in_message_len && !in_message) || hash_bytes < 0 || hash_bytes > 0xffff)
+        return failed(fn, "bad argument");
+    const uint64_t len_tag = (uint64_t)(uint16_t)hash_bytes << 32;             // xof_digest_length_to_node_offset
+    uint8_t crh[32];
+    b200_blake2s_param(in_message, (size_t)in_message_len, 32, 1, 1, 0, len_tag, 0, SIG_DOMAIN, crh);
+    std::vector<uint8_t> v((size_t)hash_bytes, 0);
+    const int blocks = (hash_bytes + 31) / 32;
+    for (int i = 0; i < blocks; i++) {
+        const int part = (i == blocks - 1 && hash_bytes % 32) ? hash_bytes % 32 : 32;
+        b200_blake2s_param(crh, 32, part, 0, 0, 32, (uint64_t)i | len_tag, 32, SIG_DOMAIN, v.data() + 32 * i);
+    }
+    return hand_out(fn, v, out_hash, out_len);
+}
+
+// ---- epoch-block byte encodings (snark/epoch_block.rs:16-106): keys compressed on the device in one pass, bit shuffling on the host ----
+static bool encode_block(const char *fn, int cip22, uint16_t index, uint8_t round, const uint8_t *epoch_entropy, const uint8_t *parent_entropy,
+                         uint32_t maximum_non_signers, size_t maximum_validators, const PublicKey *const *keys, int nkeys, uint8_t **out_bytes,
+                         int *out_len, uint8_t **out_extra, int *out_extra_len) {
+    if (!out_bytes || !out_len || nkeys < 0 || (nkeys && !keys) || (cip22 && (!out_extra || !out_extra_len))) return failed(fn, "null pointer");
+    std::vector<uint8_t> images((size_t)nkeys * PK_BYTES), keys96((size_t)nkeys * 96);
+    for (int i = 0; i < nkeys; i++) {
+        if (!keys[i]) return failed(fn, "null handle");
+        memcpy(&images[(size_t)i * PK_BYTES], keys[i], PK_BYTES);
+    }
+    if (nkeys) {
+        if (b200_ensure_init() != B200_OK) return engine_failed(fn);
+        if (b200_serialize_points(B200_POINTS_BLS12_377_G2, images.data(), (size_t)nkeys, keys96.data()) != B200_OK) return engine_failed(fn);
+    }
+    uint8_t *inner = nullptr, *extra = nullptr;
+    size_t inner_len = 0, extra_len = 0;
+    if (b200_encode_epoch_block(cip22, index, round, epoch_entropy, parent_entropy, maximum_non_signers, maximum_validators, keys96.data(),
+                                (size_t)nkeys, &inner, &inner_len, cip22 ? &extra : nullptr, cip22 ? &extra_len : nullptr) != B200_OK)
+        return engine_failed(fn);
+    *out_bytes = inner;
+    *out_len = (int)inner_len;
+    if (cip22) {
+        *out_extra = extra;
+        *out_extra_len = (int)extra_len;
+    }
+    return true;
+}
+bool encode_epoch_block_to_bytes_cip22(unsigned short in_epoch_index, unsigned char in_round_number, const uint8_t *in_epoch_entropy,
+                                       const uint8_t *in_parent_entropy, unsigned int in_maximum_non_signers, unsigned int in_maximum_validators,
+                                       const PublicKey *const *in_added_public_keys, int in_added_public_keys_len, uint8_t **out_bytes,
+                                       int *out_len, uint8_t **out_extra_data_bytes, int *out_extra_data_len) {
+    return encode_block("encode_epoch_block_to_bytes_cip22", 1, in_epoch_index, in_round_number, in_epoch_entropy, in_parent_entropy,
+                        in_maximum_non_signers, in_maximum_validators, in_added_public_keys, in_added_public_keys_len, out_bytes, out_len,
+                        out_extra_data_bytes, out_extra_data_len);
+}
+bool encode_epoch_block_to_bytes(unsigned short in_epoch_index, unsigned int in_maximum_non_signers, const PublicKey *const *in_added_public_keys,
+                                 int in_added_public_keys_len, uint8_t **out_bytes, int *out_len) {
+    return encode_block("encode_epoch_block_to_bytes", 0, in_epoch_index, 0, nullptr, nullptr, in_maximum_non_signers,
+                        (size_t)(in_added_public_keys_len > 0 ? in_added_public_keys_len : 0), in_added_public_keys, in_added_public_keys_len,
+                        out_bytes, out_len, nullptr, nullptr);
 }
 
 // ---- encodings ----

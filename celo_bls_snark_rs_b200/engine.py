@@ -35,7 +35,7 @@ EXPORTS = [
     "b200_ntt_device", "b200_witness_map_device", "b200_groth16_prove_device", "b200_groth16_prove_partial_device", "b200_groth16_assemble_device", "b200_msm_batch_device",
     "b200_multi_pairing_bw6_761", "b200_miller_values_bw6_761_device", "b200_final_exp_bw6_761_device",
     "b200_groth16_verify_bw6_761", "b200_deserialize_points", "b200_verify_epochs", "b200_epoch_public_inputs",
-    "b200_blake2s_personal", "b200_hash_to_g1", "b200_serialize_points", "b200_ensure_init", "b200_bound_device",
+    "b200_blake2s_personal", "b200_blake2s_param", "b200_encode_epoch_block", "b200_hash_to_g1", "b200_serialize_points", "b200_ensure_init", "b200_bound_device",
 ]
 # the reference's own symbols re-exported by the library (include/bls_snark_sys_compat.h)
 COMPAT_EXPORTS = ["verify", "deserialize_public_key", "deserialize_signature", "serialize_public_key", "serialize_signature",
@@ -44,7 +44,8 @@ COMPAT_EXPORTS = ["verify", "deserialize_public_key", "deserialize_signature", "
                   "compress_pubkey", "init", "generate_private_key", "deserialize_private_key", "serialize_private_key",
                   "destroy_private_key", "private_key_to_public_key", "sign_message", "sign_pop", "hash_direct",
                   "hash_direct_with_attempt", "hash_composite", "hash_composite_cip22", "hash_crh", "deserialize_public_key_cached",
-                  "serialize_public_key_uncompressed", "serialize_signature_uncompressed", "aggregate_public_keys_subtract"]
+                  "serialize_public_key_uncompressed", "serialize_signature_uncompressed", "aggregate_public_keys_subtract",
+                  "hash_direct_first_step", "encode_epoch_block_to_bytes", "encode_epoch_block_to_bytes_cip22"]
 
 
 class Groth16Pk(ctypes.Structure):
@@ -164,7 +165,11 @@ def load() -> ctypes.CDLL:
                        ("hash_composite", [vp, ci, vp, ci, pp, pci]), ("hash_composite_cip22", [vp, ci, vp, ci, pp, pci, pu8]),
                        ("hash_crh", [vp, ci, ci, pp, pci]), ("deserialize_public_key_cached", [vp, ci, pp]),
                        ("serialize_public_key_uncompressed", [vp, pp, pci]), ("serialize_signature_uncompressed", [vp, pp, pci]),
-                       ("aggregate_public_keys_subtract", [vp, pp, ci, pp]), ("init", [])):
+                       ("aggregate_public_keys_subtract", [vp, pp, ci, pp]), ("init", []),
+                       ("hash_direct_first_step", [vp, ci, ci, pp, pci]),
+                       ("encode_epoch_block_to_bytes", [ctypes.c_ushort, ctypes.c_uint, pp, ci, pp, pci]),
+                       ("encode_epoch_block_to_bytes_cip22", [ctypes.c_ushort, ctypes.c_ubyte, vp, vp, ctypes.c_uint, ctypes.c_uint, pp, ci,
+                                                              pp, pci, pp, pci])):
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = args, cb
     for name, args in (("deserialize_public_key", [vp, ci, pp]), ("deserialize_signature", [vp, ci, pp]),

@@ -347,6 +347,18 @@ int b200_epoch_public_inputs(const void *first_epoch, const void *last_epoch, ui
 /* Host helper of the verifier (no GPU): Blake2s, 32-byte digest, 8-byte personalisation
  * (crates/epoch-snark/src/epoch_block.rs:226-236 hashes the encoded blocks with "ULforout"). */
 void b200_blake2s_personal(const uint8_t *data, size_t len, const uint8_t *personal8, uint8_t *out32);
+/* The same with the full parameter block (digest length, fanout, depth, leaf length, node offset, inner length): the
+ * DirectHasher's CRH / XOF parameters (crates/bls-crypto/src/hashers/direct.rs:23-79). */
+void b200_blake2s_param(const uint8_t *data, size_t len, int digest_len, int fanout, int depth, uint32_t leaf_len, uint64_t node_offset,
+                        int inner_len, const uint8_t *personal8, uint8_t *out);
+/* Host helper (no GPU): EpochBlock::encode_to_bytes (cip22 = 0; round, entropies and maximum_validators unused) or
+ * ::encode_inner_to_bytes_cip22 (cip22 = 1; entropies may be NULL, keys padded with the G2 generator up to
+ * maximum_validators) from the keys' 96-byte compressed encodings.
+ *   crates/epoch-snark/src/epoch_block.rs:106-114, 152-171, 191-211; crates/epoch-snark/src/encoding.rs:23-80
+ * out_inner / out_extra: malloc'd, the caller frees; out_extra may be NULL when cip22 = 0. */
+int b200_encode_epoch_block(int cip22, uint16_t index, uint8_t round, const uint8_t *epoch_entropy, const uint8_t *parent_entropy,
+                            uint32_t maximum_non_signers, size_t maximum_validators, const uint8_t *keys96, size_t nkeys,
+                            uint8_t **out_inner, size_t *out_inner_len, uint8_t **out_extra, size_t *out_extra_len);
 
 /* Element-wise arithmetic in the coordinate field of `curve` (Fq, Fq2 or Fq761; Montgomery
  * form, device pointers): op 0 add, 1 sub, 2 mul, 3 square(a), 4 inverse(a), 5 neg(a),

@@ -107,6 +107,16 @@ bool hash_composite(const uint8_t *in_message, int in_message_len, const uint8_t
 bool hash_composite_cip22(const uint8_t *in_message, int in_message_len, const uint8_t *in_extra_data, int in_extra_data_len,
                           uint8_t **out_hash, int *out_len, uint8_t *attempt_counter);
 bool hash_crh(const uint8_t *in_message, int in_message_len, int hash_bytes, uint8_t **out_hash, int *out_len);
+/* signatures.rs:191-212: DirectHasher.hash(SIG_DOMAIN, message, hash_bytes) = XOF(CRH(message)), hash_bytes bytes */
+bool hash_direct_first_step(const uint8_t *in_message, int in_message_len, int hash_bytes, uint8_t **out_hash, int *out_len);
+/* snark/epoch_block.rs:16-106: EpochBlock::encode_inner_to_bytes_cip22 (inner bytes + extra-data bytes; entropies are 16 bytes
+ * or NULL; keys padded with the G2 generator up to in_maximum_validators) and the pre-Donut EpochBlock::encode_to_bytes */
+bool encode_epoch_block_to_bytes_cip22(unsigned short in_epoch_index, unsigned char in_round_number, const uint8_t *in_epoch_entropy,
+                                       const uint8_t *in_parent_entropy, unsigned int in_maximum_non_signers, unsigned int in_maximum_validators,
+                                       const PublicKey *const *in_added_public_keys, int in_added_public_keys_len, uint8_t **out_bytes,
+                                       int *out_len, uint8_t **out_extra_data_bytes, int *out_extra_data_len);
+bool encode_epoch_block_to_bytes(unsigned short in_epoch_index, unsigned int in_maximum_non_signers, const PublicKey *const *in_added_public_keys,
+                                 int in_added_public_keys_len, uint8_t **out_bytes, int *out_len);
 /* serialization.rs:44-61, 72-105: the cached decoder hands out the same key; serialize_uncompressed = canonical x | y
  * (192 / 96 bytes), infinity flag in bit 6 of the last byte */
 bool deserialize_public_key_cached(const uint8_t *in_public_key_bytes, int in_public_key_bytes_len, PublicKey **out_public_key);

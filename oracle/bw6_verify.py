@@ -189,6 +189,31 @@ class EpochBlock:
             bits += encode_public_key(O.G2_GEN)
         return bits
 
+    def encode_to_bits(self):
+        """epoch_block.rs:106-114 (the pre-Donut encoding: index, maximum_non_signers, keys)."""
+        bits = _le_bits(self.index, 2) + _le_bits(self.maximum_non_signers, 4)
+        for pk in self.pubkeys:
+            bits += encode_public_key(pk)
+        return bits
+
+    def encode_to_bytes(self):
+        """epoch_block.rs:191-193."""
+        return bits_be_to_bytes_le(self.encode_to_bits())
+
+    def encode_first_epoch_to_bytes_cip22(self):
+        """epoch_block.rs:184-188."""
+        return bits_be_to_bytes_le(self.encode_to_bits_cip22(True))
+
+    def encode_inner_to_bytes_cip22(self):
+        """epoch_block.rs:152-171, 205-211: (inner bytes, extra-data bytes)."""
+        extra = _le_bits(self.index, 2) + _le_bits(self.round, 1) + _le_bits(self.maximum_non_signers, 4)
+        bits = self._entropy_bits(self.epoch_entropy) + self._entropy_bits(self.parent_entropy)
+        for pk in self.pubkeys:
+            bits += encode_public_key(pk)
+        for _ in range(max(0, self.maximum_validators - len(self.pubkeys))):
+            bits += encode_public_key(O.G2_GEN)
+        return bits_be_to_bytes_le(bits), bits_be_to_bytes_le(extra)
+
     def blake2_first_epoch_cip22(self):
         return hash_to_bits(bits_be_to_bytes_le(self.encode_to_bits_cip22(True)))
 

@@ -47,6 +47,12 @@ vec = {
                                "hex": const_str(snark, "ENTROPY_LAST_PUBKEYS")},
     "epoch_block_encoding_with_entropy": {"cite": "crates/epoch-snark/src/epoch_block.rs:243",
                                           "hex": const_str(epoch, "EXPECTED_ENCODING_WITH_ENTROPY")},
+    "epoch_block_encoding_with_entropy_padded": {"cite": "crates/epoch-snark/src/epoch_block.rs:244",
+                                                 "hex": const_str(epoch, "EXPECTED_ENCODING_WITH_ENTROPY_PADDED")},
+    "epoch_block_encoding_without_entropy": {"cite": "crates/epoch-snark/src/epoch_block.rs:245",
+                                             "hex": const_str(epoch, "EXPECTED_ENCODING_WITHOUT_ENTROPY")},
+    "epoch_block_encoding_before_donut": {"cite": "crates/epoch-snark/src/epoch_block.rs:246",
+                                          "hex": const_str(epoch, "EXPECTED_ENCODING_BEFORE_DONUT")},
 }
 
 

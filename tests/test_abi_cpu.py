@@ -84,3 +84,37 @@ def test_plan_is_sane():
     assert nb == 1 << (c - 1) and w * c >= 254
     c, w, nb = E.msm_plan(E.BW6_761_G1, 1 << 22)
     assert w * c >= 378
+
+
+def test_byte_helper_exports_on_host():
+    """hash_direct_first_step and b200_encode_epoch_block are host byte work (no GPU): checked here against the oracle's
+    DirectHasher and against the reference's own encoding KATs (crates/epoch-snark/src/epoch_block.rs:243-320)."""
+    import ctypes
+    import json
+    from oracle import hash_to_curve as H
+    from oracle import oracle as O
+    lib = E.load()
+    for msg, n in ((b"", 32), (b"abc", 64), (bytes(range(200)), 96), (b"x" * 65, 33), (b"y", 1), (b"z" * 64, 0)):
+        ptr, ln = ctypes.c_void_p(), ctypes.c_int()
+        assert lib.hash_direct_first_step(msg, len(msg), n, ctypes.byref(ptr), ctypes.byref(ln))
+        assert ctypes.string_at(ptr, ln.value) == H.direct_hash(b"ULforxof", msg, n)
+        assert lib.free_vec(ptr, ln.value)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))
+    key = O.serialize_compressed(O.G2, O.G2_GEN)
+    lib.b200_encode_epoch_block.argtypes = [ctypes.c_int, ctypes.c_uint16, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32,
+                                            ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p),
+                                            ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]
+    inner, n_in, extra, n_ex = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_void_p(), ctypes.c_size_t()
+    assert lib.b200_encode_epoch_block(0, 120, 0, None, None, 3, 10, key * 10, 10, ctypes.byref(inner), ctypes.byref(n_in), None, None) == 0
+    assert ctypes.string_at(inner, n_in.value).hex() == gold["epoch_block_encoding_before_donut"]["hex"]
+    lib.free_vec(inner, n_in.value)
+    # the inner CIP22 encoding is both entropies + keys + padding: the first-epoch KAT minus its 16 + 32 leading bits, checked
+    # bit for bit against the oracle class that reproduces all four KATs (tests/test_oracle_golden.py)
+    from oracle import bw6_verify as V
+    for ee, pe, maxv in ((bytes([255] * 16), bytes([254] * 16), 10), (None, bytes([7] * 16), 12), (None, None, 10)):
+        assert lib.b200_encode_epoch_block(1, 120, 5, ee, pe, 3, maxv, key * 10, 10, ctypes.byref(inner), ctypes.byref(n_in),
+                                           ctypes.byref(extra), ctypes.byref(n_ex)) == 0
+        want_inner, want_extra = V.EpochBlock(120, 5, ee, pe, 3, maxv, [O.G2_GEN] * 10).encode_inner_to_bytes_cip22()
+        assert ctypes.string_at(inner, n_in.value) == want_inner and ctypes.string_at(extra, n_ex.value) == want_extra
+        lib.free_vec(inner, n_in.value)
+        lib.free_vec(extra, n_ex.value)

@@ -69,6 +69,23 @@ def test_epoch_block_encoding_reproduced_from_oracle_g2_generator():
     assert _bits_be_to_bytes_le(bits).hex() == GOLD["epoch_block_encoding_with_entropy"]["hex"]
 
 
+def test_epoch_block_encodings_of_the_oracle_class():
+    """The four encoding KATs of crates/epoch-snark/src/epoch_block.rs:243-320 through oracle/bw6_verify.EpochBlock
+    (the class the GPU tests of encode_epoch_block_to_bytes[_cip22] compare with)."""
+    from oracle import bw6_verify as V
+    keys = [O.G2_GEN] * 10
+    e255, e254 = bytes([255] * 16), bytes([254] * 16)
+    assert V.EpochBlock(120, 5, e255, e254, 3, 10, keys).encode_first_epoch_to_bytes_cip22().hex() == \
+        GOLD["epoch_block_encoding_with_entropy"]["hex"]
+    assert V.EpochBlock(120, 5, None, None, 3, 10, keys).encode_first_epoch_to_bytes_cip22().hex() == \
+        GOLD["epoch_block_encoding_without_entropy"]["hex"]
+    assert V.EpochBlock(120, 5, e255, e254, 3, 11, keys).encode_first_epoch_to_bytes_cip22().hex() == \
+        GOLD["epoch_block_encoding_with_entropy_padded"]["hex"]
+    assert V.EpochBlock(120, 10, None, None, 3, 10, keys).encode_to_bytes().hex() == GOLD["epoch_block_encoding_before_donut"]["hex"]
+    inner, extra = V.EpochBlock(120, 5, e255, e254, 3, 11, keys).encode_inner_to_bytes_cip22()
+    assert len(inner) == (256 + 11 * 755 + 7) // 8 and len(extra) == 7
+
+
 def test_ffi_pubkeys_decode_as_bls12_377_g2():
     # crates/bls-snark-sys/src/snark/mod.rs:56-58 : 4 + 4 compressed G2 keys of 96 bytes
     for key in ("bls12_377_first_pubkeys", "bls12_377_last_pubkeys"):

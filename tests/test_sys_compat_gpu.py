@@ -266,3 +266,42 @@ def test_hash_helpers_and_uncompressed_encodings(lib):
     assert _bytes_of(lib, "serialize_public_key", rest) == pk_bytes((sks[0] + sks[2]) % O.R)
     inf = _handle(lib, "deserialize_signature", O.serialize_compressed(O.G1, None))
     assert _out_bytes(lib, lambda p, n: lib.serialize_signature_uncompressed(inf, p, n)) == O.serialize_uncompressed(O.G1, None)
+
+
+def test_epoch_block_byte_exports(lib):
+    """encode_epoch_block_to_bytes / _cip22 (crates/bls-snark-sys/src/snark/epoch_block.rs:16-106) on key HANDLES: the keys are
+    normalised and compressed on the device, the bit strings assembled on the host.  The pre-Donut KAT of
+    crates/epoch-snark/src/epoch_block.rs:285-295 through the exported symbol, then random keys against the oracle class."""
+    import json
+    import os
+    from oracle import bw6_verify as V
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+    gen = [_handle(lib, "deserialize_public_key", O.serialize_compressed(O.G2, O.G2_GEN)) for _ in range(10)]
+    arr = (ctypes.c_void_p * 10)(*[h.value for h in gen])
+    got = _out_bytes(lib, lambda p, n: lib.encode_epoch_block_to_bytes(120, 3, arr, 10, p, n))
+    assert got.hex() == gold["epoch_block_encoding_before_donut"]["hex"]
+    rng = O.SplitMix64(77)
+    sks = [rng.below(O.R - 1) + 1 for _ in range(5)]
+    pts = [O.G2.pmul(O.G2_GEN, s) for s in sks]
+    hs = [_handle(lib, "deserialize_public_key", O.serialize_compressed(O.G2, p)) for p in pts]
+    # an aggregate is a non-normalised Jacobian image: the device has to normalise it
+    agg = ctypes.c_void_p()
+    arr5 = (ctypes.c_void_p * 5)(*[h.value for h in hs])
+    assert lib.aggregate_public_keys(arr5, 5, ctypes.byref(agg))
+    agg_pt = None
+    for p in pts:
+        agg_pt = O.G2.padd(agg_pt, p)
+    keys, key_pts = (ctypes.c_void_p * 6)(*([h.value for h in hs] + [agg.value])), pts + [agg_pt]
+    assert _out_bytes(lib, lambda p, n: lib.encode_epoch_block_to_bytes(7, 2, keys, 6, p, n)) == \
+        V.EpochBlock(7, 0, None, None, 2, 6, key_pts).encode_to_bytes()
+    for ee, pe, maxv in ((bytes(range(16)), bytes(range(16, 32)), 6), (None, bytes([9] * 16), 8), (bytes([1] * 16), None, 3)):
+        inner, n_in, extra, n_ex = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_void_p(), ctypes.c_int()
+        assert lib.encode_epoch_block_to_bytes_cip22(513, 9, ee, pe, 4, maxv, keys, 6, ctypes.byref(inner), ctypes.byref(n_in),
+                                                     ctypes.byref(extra), ctypes.byref(n_ex))
+        want_inner, want_extra = V.EpochBlock(513, 9, ee, pe, 4, maxv, key_pts).encode_inner_to_bytes_cip22()
+        assert ctypes.string_at(inner, n_in.value) == want_inner and ctypes.string_at(extra, n_ex.value) == want_extra
+        assert lib.free_vec(inner, n_in.value) and lib.free_vec(extra, n_ex.value)
+    # no keys at all: only the header (and the padding)
+    assert _out_bytes(lib, lambda p, n: lib.encode_epoch_block_to_bytes(1, 1, None, 0, p, n)) == V.EpochBlock(1, 0, None, None, 1, 0, []).encode_to_bytes()
+    msg = b"first step"
+    assert _out_bytes(lib, lambda p, n: lib.hash_direct_first_step(msg, len(msg), 96, p, n)) == H.direct_hash(SIG_DOMAIN, msg, 96)
