@@ -15,9 +15,9 @@ constexpr bool B200_AFFINE_BUILD = true;
 #else
 constexpr bool B200_AFFINE_BUILD = false;
 #endif
-template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true; };
-template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true; };
+template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
 // keeping enough buckets in flight to fill 148 SMs.
@@ -111,9 +111,48 @@ static bool msm_use_affine(const MsmPlan &p, size_t n, size_t *rec_a, size_t *re
     return (*rec_a + *rec_b) * sizeof(AffineMem<F>) <= AFFINE_SCRATCH_BUDGET && n / p.nb >= 8;
 }
 
+// ---- batched-affine tree (msm_afftree.cuh): how many levels, how many windows per pass ------------------------------
+// EXPERIMENTAL, compiled only with B200_WITH_CROSSCHECKS and off unless B200_MSM_AFFTREE = k (k levels): parity-green
+// (the 70 MSM parity tests pass with the tree on, both fields), MEASURED SLOWER on B200 (profiles/r2_experiments.md):
+// BLS12-377 G1 n = 2^20 8.28 ms without, 8.76 / 9.40 / 9.88 / 10.3 ms with 2 / 3 / 4 / 5 levels; BW6-761 47.2 -> 47.4 / 48.0.
+// levels: the tree halves a bucket `levels` times, the XYZZ finish adds what is left (mean population / 2^levels points).
+// Windows are taken in groups so that the two level buffers stay within AFT_SCRATCH_BUDGET.
+constexpr size_t AFT_SCRATCH_BUDGET = (size_t)6 << 30;
+struct AftPlan {
+    int levels = 0, group = 0;                      // windows per pass
+    size_t slots_a = 0, slots_b = 0;                // records of the odd / even level buffers
+};
+template <class C>
+static AftPlan aft_plan(const MsmPlan &p, size_t n) {
+    using F = typename C::F;
+    AftPlan a;
+    if (!CurveTraits<C>::AFFTREE) return a;
+    static const int forced = getenv("B200_MSM_AFFTREE") ? atoi(getenv("B200_MSM_AFFTREE")) : 0;
+    if (forced <= 0 || n / p.nb < 8) return a;
+    const int levels = std::min(forced, 10);
+    int group = p.windows;
+    for (;;) {
+        const size_t entries = n * (size_t)group, nbk = (size_t)group * p.nb;
+        a.slots_a = aft_slots(entries, nbk, 1);
+        a.slots_b = levels > 1 ? aft_slots(entries, nbk, 2) : 0;
+        if ((a.slots_a + a.slots_b) * sizeof(AffineMem<F>) <= AFT_SCRATCH_BUDGET || group == 1) break;
+        group = (group + 1) / 2;
+    }
+    if (n * (size_t)group >= ((size_t)1 << 31)) return AftPlan{};   // slot indices are 31 bits
+    a.levels = levels;
+    a.group = group;
+    return a;
+}
+
 template <class C>
 static int msm_reserve(MsmWs &W, const MsmPlan &p, size_t n) {
     using F = typename C::F;
+    {
+        const AftPlan a = aft_plan<C>(p, n);
+        int rc0;
+        if (a.levels && ((rc0 = W.aff_a.reserve(a.slots_a * sizeof(AffineMem<F>))) || (rc0 = W.aff_b.reserve(a.slots_b * sizeof(AffineMem<F>)))))
+            return rc0;
+    }
     {
         size_t ra, rb;
         int rc0;
@@ -219,7 +258,32 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
     // 12-limb curves: the accumulate kernel with ONE out-of-line product body (12 KB of code instead of 117 KB)
     // is 1.8 % faster under the pipelined batch (7.48 against 7.61 ms); B200_MSM_SHAREDMUL=0 selects the inlined one
     static const bool shared_mul = !(getenv("B200_MSM_SHAREDMUL") && !atoi(getenv("B200_MSM_SHAREDMUL")));
-    if (!affine && shared_mul && T::SHARED_MUL)
+    AftPlan aft{};
+    if constexpr (T::AFFTREE) {
+        if (group < 0 && !affine) aft = aft_plan<C>(p, n);
+    }
+    if constexpr (T::AFFTREE) if (aft.levels) {
+        // batched-affine tree, window group by window group (the level buffers are reused), then the XYZZ finish
+        const uint32_t *so = W.sorted.as<uint32_t>();
+        AffineMem<F> *buf[2] = {W.aff_a.as<AffineMem<F>>(), W.aff_b.as<AffineMem<F>>()};
+        for (int w0 = 0; w0 < p.windows; w0 += aft.group) {
+            const int gw = std::min(aft.group, p.windows - w0);
+            const uint32_t b0 = (uint32_t)w0 * p.nb, nbk = (uint32_t)gw * p.nb;
+            const size_t entries = n * (size_t)gw;
+            for (int L = 0; L < aft.levels; L++) {
+                const size_t slots = aft_slots(entries, nbk, L + 1);
+                const unsigned blocks = (unsigned)ceil_div(ceil_div(slots, (size_t)AFT_B), (size_t)T::AFT_THREADS);
+                k_affine_level<F, T::AFT_THREADS, T::AFT_MIN_BLOCKS, T::AFT_PREFETCH><<<blocks, T::AFT_THREADS, 0, st>>>(
+                    bases, so, offsets, b0, nbk, p.big, L, L ? buf[(L - 1) & 1] : nullptr, buf[L & 1], (uint32_t)slots);
+                LAUNCH_CHECK();
+            }
+            k_bucket_finish<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS><<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
+                buf[(aft.levels - 1) & 1], offsets, order, (uint32_t)total, b0, nbk, p.big, aft.levels, resume, B.buckets.as<XYZZMem<F>>());
+            LAUNCH_CHECK();
+        }
+    }
+    if (aft.levels) {
+    } else if (!affine && shared_mul && T::SHARED_MUL)
         k_bucket_accumulate_shared<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
             <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
                 bases, W.sorted.as<uint32_t>(), offsets, order, (uint32_t)total, p.big, resume,

@@ -960,3 +960,5 @@ __global__ void __launch_bounds__(64) k_field_op(int op, const typename F::Mem *
 }
 
 }  // namespace b200
+
+#include "msm_afftree.cuh"
