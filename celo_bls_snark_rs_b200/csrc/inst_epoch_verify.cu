@@ -195,6 +195,57 @@ void epoch_block_encode(int cip22, uint16_t index, uint8_t round, const uint8_t 
     *extra = bits_be_to_bytes_le(xbits);
 }
 
+// ---- subgroup membership, latency form ----------------------------------------------------------------------
+// r * P == O on ONE BLOCK PER POINT with the warp-cooperative point operations of coop.cuh (one limb per lane, the
+// independent products of a round on four warps): `verify` decodes ten BW6-761 points and eight BLS12-377 G2 keys, and
+// with one thread per point (codec.cuh k_subgroup_check) every call paid one thread's chain of 376 doublings of
+// 761-bit points -- 16 ms of the 37 ms entry point.  Same double-and-add, same exceptional cases (CoopPoint::add is
+// exact), so the last addition lands on O exactly when the per-thread kernel's does.
+template <class F, class RP>
+__global__ void __launch_bounds__(COOP_THREADS) k_subgroup_check_coop(const AffineMem<F> *__restrict__ pts, uint32_t n,
+                                                                      int *__restrict__ status) {
+    using CP = CoopPoint<F>;
+    using C = Coop<F>;
+    constexpr int W = C::WORDS;
+    __shared__ CoopSm<F> sm;
+    const uint32_t i = blockIdx.x;
+    if (i >= n || status[i] != DECODE_OK) return;                  // uniform over the block
+    const typename C::Ctx c = C::Ctx::make();
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(pts + i);
+    for (int k = threadIdx.x; k < 2 * W; k += blockDim.x) sm.in[k / W][k % W] = __ldg(src + k);      // x | y
+    for (int k = threadIdx.x; k < 4 * W; k += blockDim.x) sm.pt[k / W][k % W] = 0u;                  // infinity
+    if ((threadIdx.x >> 5) == 0) {
+        C::one(c).store(c, sm.in[2]);
+        C::one(c).store(c, sm.in[3]);
+    }
+    __syncthreads();
+    CP::add(c, sm);
+#pragma unroll 1
+    for (int b = RP::BITS - 2; b >= 0; b--) {
+        CP::dbl(c, sm);
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < RP::N; k++) word = (k == (b >> 5)) ? RP::mod(k) : word;
+        if ((word >> (b & 31)) & 1u) CP::add(c, sm);
+    }
+    __syncthreads();
+    const C zz = C::load(c, sm.pt[2]);
+    if (!C::is_zero(c, zz) && threadIdx.x == 0) status[i] = DECODE_NOT_IN_SUBGROUP;
+}
+// one block per point while all blocks are resident at once (latency: one chain); beyond that the per-thread kernel's
+// throughput wins
+constexpr size_t SUBGROUP_COOP_MAX = 1184;
+template <class F, class RP>
+static int subgroup_check(const void *d_pts, size_t n, int *d_status, cudaStream_t st) {
+    static const bool force_thread = getenv("B200_SUBGROUP_THREAD") != nullptr;
+    if (n <= SUBGROUP_COOP_MAX && !force_thread)
+        k_subgroup_check_coop<F, RP><<<(unsigned)n, COOP_THREADS, 0, st>>>(reinterpret_cast<const AffineMem<F> *>(d_pts), (uint32_t)n, d_status);
+    else
+        k_subgroup_check<F, RP><<<(unsigned)ceil_div(n, 64), 64, 0, st>>>(reinterpret_cast<const AffineMem<F> *>(d_pts), (uint32_t)n, d_status);
+    LAUNCH_CHECK();
+    return B200_OK;
+}
+
 // ---- device-side decoding ------------------------------------------------------------------------------
 // kind: 0 = BLS12-377 G2, 1 = BW6-761 G1, 2 = BW6-761 G2.  d_src: n x 96 bytes; d_out: n packed affine records;
 // d_status: n ints (DECODE_*).  Subgroup membership is checked when `subgroup` is set.
@@ -205,26 +256,20 @@ int decode_points(int kind, const void *d_src, size_t n, int subgroup, void *d_o
         k_g2_377_decompress<<<blocks, 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)n,
                                                    reinterpret_cast<AffineMem<CFq2> *>(d_out), d_status);
         LAUNCH_CHECK();
-        if (subgroup) {
-            k_subgroup_check<CFq2, Fr253Params><<<blocks, 64, 0, st>>>(reinterpret_cast<const AffineMem<CFq2> *>(d_out), (uint32_t)n, d_status);
-            LAUNCH_CHECK();
-        }
+        int rc;
+        if (subgroup && (rc = subgroup_check<CFq2, Fr253Params>(d_out, n, d_status, st))) return rc;
     } else if (kind == 1 || kind == 2) {
         k_bw6_decompress<<<blocks, 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)n, 0u, kind == 2 ? (uint32_t)n : 0u,
                                                 reinterpret_cast<AffineMem<Fq761> *>(d_out), d_status);
         LAUNCH_CHECK();
-        if (subgroup) {
-            k_subgroup_check<Fq761, Fq377Params><<<blocks, 64, 0, st>>>(reinterpret_cast<const AffineMem<Fq761> *>(d_out), (uint32_t)n, d_status);
-            LAUNCH_CHECK();
-        }
+        int rc;
+        if (subgroup && (rc = subgroup_check<Fq761, Fq377Params>(d_out, n, d_status, st))) return rc;
     } else if (kind == 3) {
         k_g1_377_decompress<<<blocks, 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)n,
                                                    reinterpret_cast<AffineMem<CFq> *>(d_out), d_status);
         LAUNCH_CHECK();
-        if (subgroup) {
-            k_subgroup_check<CFq, Fr253Params><<<blocks, 64, 0, st>>>(reinterpret_cast<const AffineMem<CFq> *>(d_out), (uint32_t)n, d_status);
-            LAUNCH_CHECK();
-        }
+        int rc;
+        if (subgroup && (rc = subgroup_check<CFq, Fr253Params>(d_out, n, d_status, st))) return rc;
     } else {
         return fail(B200_ERR_ARG, "unknown point kind %d", kind);
     }
@@ -382,9 +427,7 @@ int epoch_verify(Engine &E, const uint8_t *vk, size_t vk_len, const uint8_t *pro
     k_bw6_decompress<<<ceil_div(nbw, 64), 64, 0, st>>>(reinterpret_cast<const uint32_t *>(d_src), (uint32_t)nbw, 4u, 8u,
                                                        reinterpret_cast<AffineMem<Fq761> *>(d_pts), d_status);
     LAUNCH_CHECK();
-    k_subgroup_check<Fq761, Fq377Params><<<ceil_div(nbw, 64), 64, 0, st>>>(reinterpret_cast<const AffineMem<Fq761> *>(d_pts), (uint32_t)nbw,
-                                                                          d_status);
-    LAUNCH_CHECK();
+    if ((rc = subgroup_check<Fq761, Fq377Params>(d_pts, nbw, d_status, st))) return rc;
     CUDA_TRY(cudaStreamWaitEvent(st, E.ev_join, 0));
     std::vector<int> status(nbw);
     CUDA_TRY(cudaMemcpyAsync(status.data(), d_status, nbw * sizeof(int), cudaMemcpyDeviceToHost, st));
