@@ -440,6 +440,136 @@ __global__ void __launch_bounds__(32 * WW) k_w2_miller_loop(const AffineMem<PFq>
     w_f12_store_global(S.f[fa], out + w, lane);
 }
 
+// ---- two pairs per BLOCK: the latency form of the same loop ----------------------------------------------------------
+// k_w2_miller_loop gives a check (two pairs) one warp: every Fq12 operation is 3-4 field products deep per lane and the
+// G2 line steps wait behind them -- 27 us per bit, 1.7 ms for the 2-pair check of verify_signature.  Here a block of six
+// warps shares it: warp 5 walks the G2 points (w_doubling_step2 / w_addition_step, unchanged) ONE BIT AHEAD and leaves the
+// sparse line elements in a double-buffered slot, warps 0-4 (160 threads) keep the Miller variable -- f^2 is 78 products
+// on 78 threads, a sparse line product 72 on 72, each ONE field product deep, summed by 24 threads -- and the two groups
+// meet once per bit.  The pipe work is the same as the warp kernel's (fewer idle lanes, if anything), spread over six
+// times the warps.  Values are identical: the same field operations on the same operands, multiplied in another order.
+constexpr int B2_F_THREADS = 160, B2_THREADS = 192;
+struct alignas(16) Block2Scratch {
+    FqImg f[12];                                     // the Miller variable, power basis
+    FqImg P[144];                                    // coefficient products, P[e * 12 + i]
+    FqImg line[2][4][12];                            // [bit parity][pair 0 / pair 1 doubling, pair 0 / pair 1 addition][exponent]
+    Fq2Slot s[2][W_SLOTS];                           // line state of the two pairs
+};
+B200_DEV void b2_f_bar() { asm volatile("bar.sync 1, 160;" ::: "memory"); }
+__device__ const uint8_t B2_LINE_EXP[6] = {0, 1, 3, 6, 7, 9};
+// sum of the products of output exponent e: lanes (e, h) of warp 0; h = 1 takes the wrapped terms (i + j >= 12, times -5)
+B200_DEV void b2_store_sums(FqImg *O, const PFq &part, int t) {
+    PFq other = part.shfl(0xffffffffu, (t + 12) & 31);
+    if (t < 12) w_st(O[t], part - (other.dbl().dbl() + other));
+}
+// f <- f^2: unordered pairs {i <= j}, thread t < 78 takes one
+B200_DEV void b2_f12_sqr(FqImg *F, FqImg *P, int t) {
+    if (t < 78) {
+        int i = 0, r = t;                            // row i holds the pairs (i, i .. 11): 12 - i of them
+        while (r >= 12 - i) {
+            r -= 12 - i;
+            i++;
+        }
+        const int j = i + r;
+        int e = i + j;
+        e -= e >= 12 ? 12 : 0;
+        PFq prod = w_ld(F[i]) * w_ld(F[j]);
+        if (i != j) prod = prod.dbl();
+        w_st(P[e * 12 + i], prod);
+    }
+    b2_f_bar();
+    if (t < 32) {
+        const int e = t % 12, h = t / 12;
+        PFq part = PFq::zero();
+        if (t < 24) {
+#pragma unroll 1
+            for (int i = 0; i < 12; i++) {
+                int j = e - i;
+                j += j < 0 ? 12 : 0;
+                if (i <= j && ((i + j >= 12) ? 1 : 0) == h) part = part + w_ld(P[e * 12 + i]);
+            }
+        }
+        b2_store_sums(F, part, t);
+    }
+    b2_f_bar();
+}
+// f <- f * line (exponents 0, 1, 3, 6, 7, 9 of L): thread t < 72 takes one product
+B200_DEV void b2_f12_mul_line(FqImg *F, const FqImg *L, FqImg *P, int t) {
+    if (t < 72) {
+        const int i = t / 6, j = B2_LINE_EXP[t % 6];
+        int e = i + j;
+        e -= e >= 12 ? 12 : 0;
+        w_st(P[e * 12 + i], w_ld(F[i]) * w_ld(L[j]));
+    }
+    b2_f_bar();
+    if (t < 32) {
+        const int e = t % 12, h = t / 12;
+        PFq part = PFq::zero();
+        if (t < 24) {
+#pragma unroll 1
+            for (int k = 0; k < 6; k++) {
+                const int j = B2_LINE_EXP[k];
+                int i = e - j;
+                i += i < 0 ? 12 : 0;
+                if (((i + j >= 12) ? 1 : 0) == h) part = part + w_ld(P[e * 12 + i]);
+            }
+        }
+        b2_store_sums(F, part, t);
+    }
+    b2_f_bar();
+}
+
+// block b: out[b] = Miller value of pair 2b  *  Miller value of pair 2b + 1 (tower image), as k_w2_miller_loop's warp b
+__global__ void __launch_bounds__(B2_THREADS) k_b2_miller_loop(const AffineMem<PFq> *__restrict__ g1, const AffineMem<PFq2> *__restrict__ g2,
+                                                               uint32_t n, Fq12::Mem *__restrict__ out) {
+    __shared__ Block2Scratch S;
+    const int t = threadIdx.x, lane = t & 31;
+    const bool line_warp = t >= B2_F_THREADS;
+    const uint32_t w = blockIdx.x;
+    if (2 * w >= n) return;
+    int live = 0;                                    // finite pairs placed in slot sets 0 .. live-1 (block-uniform)
+    for (uint32_t pair = 2 * w; pair < min(n, 2 * w + 2); pair++) {
+        Affine<PFq> p = Affine<PFq>::from_ark(ldg_mem(g1 + pair));
+        Affine<PFq2> q = Affine<PFq2>::from_ark(ldg_mem(g2 + pair));
+        if (p.is_inf() || q.is_inf()) continue;
+        if (t == B2_F_THREADS) w_init_line_state(S.s[live], p, q);
+        live++;
+    }
+    if (t < 12) w_st(S.f[t], t == 0 ? PFq::one() : PFq::zero());
+    __syncthreads();
+    if (live) {
+        const bool two = live == 2;
+        // lines of bit b: doubling lines in slots 0 / 1, addition lines (bit set) in slots 2 / 3
+        auto lines_of_bit = [&](int b, int par) {
+            w_doubling_step2(S.s[0], S.s[1], two, lane);
+            for (int k = 0; k < live; k++) w_line_to_power(S.s[k], S.line[par][k], lane);
+            if ((PAIRING_X >> b) & 1ull) {
+                for (int k = 0; k < live; k++) {
+                    w_addition_step(S.s[k], lane);
+                    w_line_to_power(S.s[k], S.line[par][2 + k], lane);
+                }
+            }
+        };
+        if (line_warp) lines_of_bit(62, 0);
+        __syncthreads();
+        int par = 0;
+#pragma unroll 1
+        for (int b = 62; b >= 0; b--) {
+            if (line_warp) {
+                if (b > 0) lines_of_bit(b - 1, par ^ 1);
+            } else {
+                if (b != 62) b2_f12_sqr(S.f, S.P, t);                 // f is still one before the first lines
+                for (int k = 0; k < live; k++) b2_f12_mul_line(S.f, S.line[par][k], S.P, t);
+                if ((PAIRING_X >> b) & 1ull)
+                    for (int k = 0; k < live; k++) b2_f12_mul_line(S.f, S.line[par][2 + k], S.P, t);
+            }
+            __syncthreads();
+            par ^= 1;
+        }
+    }
+    if (t < 12) reinterpret_cast<FqImg *>(out + w)[t] = S.f[tower_to_power(t)];
+}
+
 // warp w of the grid: vals[w] = prod_{i = w (mod stride)} vals[i]   (strided in-place partial products)
 __global__ void __launch_bounds__(32 * W_WARPS) k_w_fq12_strided_product(Fq12::Mem *__restrict__ vals, uint32_t n,
                                                                          uint32_t stride) {
