@@ -15,13 +15,14 @@ static bool single_pair_warps() { static const bool v = env_on("B200_PAIRING_SIN
 #endif
 
 // `warps` warps of the two-pairs-per-warp Miller kernel; B200_MILLER_WARPS = 1 | 2 | 4 warps per block (default 2)
-// Up to 592 warps' worth of pairs (one wave of four blocks per SM) take the block kernel -- one block of six warps per two
-// pairs, 2 pairs: 1.48 -> 0.73 ms, 1024 pairs: 1.81 -> 1.41 ms -- beyond that one warp per two pairs wins (2960 pairs: 3.14
-// against 3.31 ms, 4097: 4.15 against 4.47; profiles/r2_pairing_block.log).  B200_MILLER_BLOCK = k overrides the limit.
+// Up to 888 checks (one wave of six 128-thread blocks per SM) take the block kernel -- one block of four warps per two
+// pairs: 2 pairs 1.48 -> 0.64 ms, 1024 pairs 1.81 -> 1.43 ms, 1776 pairs 2.25 -> 2.04 ms -- beyond that one warp per two
+// pairs wins (2960 pairs: 3.15 against 3.24 ms, 4097: 4.22 against 4.46; profiles/r2_pairing_block.log).
+// B200_MILLER_BLOCK = k overrides the limit.
 static void launch_w2_miller(const AffineMem<PFq> *g1, const AffineMem<PFq2> *g2, uint32_t n, uint32_t warps, Fq12::Mem *vals,
                              cudaStream_t st) {
     static const int ww = getenv("B200_MILLER_WARPS") ? atoi(getenv("B200_MILLER_WARPS")) : 2;
-    static const long block_max = getenv("B200_MILLER_BLOCK") ? atol(getenv("B200_MILLER_BLOCK")) : 592;
+    static const long block_max = getenv("B200_MILLER_BLOCK") ? atol(getenv("B200_MILLER_BLOCK")) : 888;
     if ((long)warps <= block_max) {
         k_b2_miller_loop<<<warps, B2_THREADS, 0, st>>>(g1, g2, n, vals);
         return;

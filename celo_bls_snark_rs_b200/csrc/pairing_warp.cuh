@@ -442,80 +442,58 @@ __global__ void __launch_bounds__(32 * WW) k_w2_miller_loop(const AffineMem<PFq>
 
 // ---- two pairs per BLOCK: the latency form of the same loop ----------------------------------------------------------
 // k_w2_miller_loop gives a check (two pairs) one warp: every Fq12 operation is 3-4 field products deep per lane and the
-// G2 line steps wait behind them -- 27 us per bit, 1.7 ms for the 2-pair check of verify_signature.  Here a block of six
-// warps shares it: warp 5 walks the G2 points (w_doubling_step2 / w_addition_step, unchanged) ONE BIT AHEAD and leaves the
-// sparse line elements in a double-buffered slot, warps 0-4 (160 threads) keep the Miller variable -- f^2 is 78 products
-// on 78 threads, a sparse line product 72 on 72, each ONE field product deep, summed by 24 threads -- and the two groups
-// meet once per bit.  The pipe work is the same as the warp kernel's (fewer idle lanes, if anything), spread over six
-// times the warps.  Values are identical: the same field operations on the same operands, multiplied in another order.
-constexpr int B2_F_THREADS = 160, B2_THREADS = 192;
+// G2 line steps wait behind them -- 27 us per bit, 1.7 ms for the 2-pair check of verify_signature.  Here a block of four
+// warps shares it: warp 3 walks the G2 points (w_doubling_step2 / w_addition_step, unchanged) ONE BIT AHEAD and leaves the
+// sparse line elements in a double-buffered slot, warps 0-2 (96 threads) keep the Miller variable -- f^2 is 78 products,
+// a sparse line product 72, each ONE field product deep, eight lanes per output coefficient folded by shuffles -- and the
+// two groups meet once per bit.  The pipe work is the same as the warp kernel's, spread over four times the warps.  Values are identical: the same field operations on the same operands, multiplied in another order.
+constexpr int B2_F_THREADS = 96, B2_THREADS = 128;
 struct alignas(16) Block2Scratch {
     FqImg f[12];                                     // the Miller variable, power basis
-    FqImg P[144];                                    // coefficient products, P[e * 12 + i]
     FqImg line[2][4][12];                            // [bit parity][pair 0 / pair 1 doubling, pair 0 / pair 1 addition][exponent]
     Fq2Slot s[2][W_SLOTS];                           // line state of the two pairs
 };
-B200_DEV void b2_f_bar() { asm volatile("bar.sync 1, 160;" ::: "memory"); }
+B200_DEV void b2_f_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
 __device__ const uint8_t B2_LINE_EXP[6] = {0, 1, 3, 6, 7, 9};
-// sum of the products of output exponent e: lanes (e, h) of warp 0; h = 1 takes the wrapped terms (i + j >= 12, times -5)
-B200_DEV void b2_store_sums(FqImg *O, const PFq &part, int t) {
-    PFq other = part.shfl(0xffffffffu, (t + 12) & 31);
-    if (t < 12) w_st(O[t], part - (other.dbl().dbl() + other));
-}
-// f <- f^2: unordered pairs {i <= j}, thread t < 78 takes one
-B200_DEV void b2_f12_sqr(FqImg *F, FqImg *P, int t) {
-    if (t < 78) {
-        int i = 0, r = t;                            // row i holds the pairs (i, i .. 11): 12 - i of them
-        while (r >= 12 - i) {
-            r -= 12 - i;
-            i++;
-        }
-        const int j = i + r;
-        int e = i + j;
-        e -= e >= 12 ? 12 : 0;
-        PFq prod = w_ld(F[i]) * w_ld(F[j]);
-        if (i != j) prod = prod.dbl();
-        w_st(P[e * 12 + i], prod);
-    }
-    b2_f_bar();
-    if (t < 32) {
-        const int e = t % 12, h = t / 12;
-        PFq part = PFq::zero();
-        if (t < 24) {
+// Eight lanes per output exponent e (t = 8 e + m): lane m computes ONE term of c_e -- wrapped terms (i + j >= 12) already
+// times -5, w^12 = -5 -- and three xor-shuffle steps add the eight up; no product ever goes through shared memory.
+B200_DEV PFq b2_fold8(PFq term, bool wrap, int lane) {
+    if (wrap) term = (term.dbl().dbl() + term).neg();
 #pragma unroll 1
-            for (int i = 0; i < 12; i++) {
-                int j = e - i;
-                j += j < 0 ? 12 : 0;
-                if (i <= j && ((i + j >= 12) ? 1 : 0) == h) part = part + w_ld(P[e * 12 + i]);
-            }
-        }
-        b2_store_sums(F, part, t);
+    for (int o = 4; o >= 1; o >>= 1) term = term + term.shfl(0xffffffffu, lane ^ o);
+    return term;
+}
+// f <- f^2: the unordered pairs {i, j}, i + j = e (mod 12): 7 for even e, 6 for odd (enumeration of w_f12_sqr)
+B200_DEV void b2_f12_sqr(FqImg *F, int t) {
+    const int e = t >> 3, m = t & 7, half = e >> 1, count = 7 - (e & 1);
+    PFq term = PFq::zero();
+    bool wrap = false;
+    if (m < count) {
+        wrap = m > half;
+        const int i = wrap ? e + m - half : m, j = wrap ? 12 + half - m : e - m;
+        term = w_ld(F[i]) * w_ld(F[j]);
+        if (i != j) term = term.dbl();
     }
+    term = b2_fold8(term, wrap, t & 31);
+    b2_f_bar();                                      // every read of f is done
+    if (m == 0) w_st(F[e], term);
     b2_f_bar();
 }
-// f <- f * line (exponents 0, 1, 3, 6, 7, 9 of L): thread t < 72 takes one product
-B200_DEV void b2_f12_mul_line(FqImg *F, const FqImg *L, FqImg *P, int t) {
-    if (t < 72) {
-        const int i = t / 6, j = B2_LINE_EXP[t % 6];
-        int e = i + j;
-        e -= e >= 12 ? 12 : 0;
-        w_st(P[e * 12 + i], w_ld(F[i]) * w_ld(L[j]));
+// f <- f * line (exponents 0, 1, 3, 6, 7, 9 of L)
+B200_DEV void b2_f12_mul_line(FqImg *F, const FqImg *L, int t) {
+    const int e = t >> 3, m = t & 7;
+    PFq term = PFq::zero();
+    bool wrap = false;
+    if (m < 6) {
+        const int j = B2_LINE_EXP[m];
+        int i = e - j;
+        wrap = i < 0;
+        i += wrap ? 12 : 0;
+        term = w_ld(F[i]) * w_ld(L[j]);
     }
+    term = b2_fold8(term, wrap, t & 31);
     b2_f_bar();
-    if (t < 32) {
-        const int e = t % 12, h = t / 12;
-        PFq part = PFq::zero();
-        if (t < 24) {
-#pragma unroll 1
-            for (int k = 0; k < 6; k++) {
-                const int j = B2_LINE_EXP[k];
-                int i = e - j;
-                i += i < 0 ? 12 : 0;
-                if (((i + j >= 12) ? 1 : 0) == h) part = part + w_ld(P[e * 12 + i]);
-            }
-        }
-        b2_store_sums(F, part, t);
-    }
+    if (m == 0) w_st(F[e], term);
     b2_f_bar();
 }
 
@@ -558,10 +536,10 @@ __global__ void __launch_bounds__(B2_THREADS) k_b2_miller_loop(const AffineMem<P
             if (line_warp) {
                 if (b > 0) lines_of_bit(b - 1, par ^ 1);
             } else {
-                if (b != 62) b2_f12_sqr(S.f, S.P, t);                 // f is still one before the first lines
-                for (int k = 0; k < live; k++) b2_f12_mul_line(S.f, S.line[par][k], S.P, t);
+                if (b != 62) b2_f12_sqr(S.f, t);                 // f is still one before the first lines
+                for (int k = 0; k < live; k++) b2_f12_mul_line(S.f, S.line[par][k], t);
                 if ((PAIRING_X >> b) & 1ull)
-                    for (int k = 0; k < live; k++) b2_f12_mul_line(S.f, S.line[par][2 + k], S.P, t);
+                    for (int k = 0; k < live; k++) b2_f12_mul_line(S.f, S.line[par][2 + k], t);
             }
             __syncthreads();
             par ^= 1;
@@ -676,32 +654,28 @@ __global__ void __launch_bounds__(32) k_w_final_exp(const Fq12::Mem *__restrict_
 // is 6 sequential field products per lane.  Here a block of 160 threads gives every one of the 144
 // coefficient products a[i] * b[j] its own thread (one field-product latency per Fq12 product), the
 // 12 output coefficients are then summed from shared memory by 24 threads (positive / wrapped halves).
-constexpr int B_THREADS = 160;
+constexpr int B_THREADS = 192;
 struct alignas(16) BlockScratch {
     FqImg V[9][12];                                  // named values of the chain, power basis
-    FqImg P[144];                                    // coefficient products, P[e * 12 + i] = a[i] * b[(e - i) mod 12]
 };
 
-// O = A * B; all B_THREADS threads call; O may alias A and / or B
-B200_DEV void b_f12_mul(const FqImg *A, const FqImg *B, FqImg *O, FqImg *P, int t) {
-    if (t < 144) {
-        const int i = t / 12, j = t % 12;
-        int e = i + j;
-        e -= e >= 12 ? 12 : 0;
-        w_st(P[e * 12 + i], w_ld(A[i]) * w_ld(B[j]));
+// O = A * B; all B_THREADS threads call; O may alias A and / or B.  Sixteen lanes per output exponent e (t = 16 e + i,
+// twelve of them busy): lane i computes a_i b_((e - i) mod 12), wrapped terms times -5 (w^12 = -5), four xor-shuffle steps
+// add the group up -- one field product and four additions deep, nothing staged through shared memory.
+B200_DEV void b_f12_mul(const FqImg *A, const FqImg *B, FqImg *O, int t) {
+    const int e = t >> 4, i = t & 15;
+    PFq term = PFq::zero();
+    if (i < 12) {
+        int j = e - i;
+        const bool wrap = j < 0;
+        j += wrap ? 12 : 0;
+        term = w_ld(A[i]) * w_ld(B[j]);
+        if (wrap) term = (term.dbl().dbl() + term).neg();
     }
-    __syncthreads();
-    if (t < 32) {                                    // warp 0: lanes (e, h); h = 1 sums the wrapped terms (i > e)
-        const int e = t % 12, h = t / 12;
-        PFq part = PFq::zero();
-        if (t < 24) {
-            const int lo = h ? e + 1 : 0, hi = h ? 12 : e + 1;
 #pragma unroll 1
-            for (int i = lo; i < hi; i++) part = part + w_ld(P[e * 12 + i]);
-        }
-        PFq other = part.shfl(0xffffffffu, (t + 12) & 31);
-        if (t < 12) w_st(O[e], part - (other.dbl().dbl() + other));          // w^12 = -5
-    }
+    for (int o = 8; o >= 1; o >>= 1) term = term + term.shfl(0xffffffffu, (t & 31) ^ o);
+    __syncthreads();                                 // every read of A / B is done
+    if (i == 0) w_st(O[e], term);
     __syncthreads();
 }
 B200_DEV void b_f12_frob(const FqImg *A, FqImg *O, int j, int t) {
@@ -720,12 +694,12 @@ B200_DEV void b_f12_copy(const FqImg *A, FqImg *O, int t) {
     __syncthreads();
 }
 // O = base^x (x = PAIRING_X), O != base
-B200_DEV void b_exp_by_x(const FqImg *base, FqImg *O, FqImg *P, int t) {
+B200_DEV void b_exp_by_x(const FqImg *base, FqImg *O, int t) {
     b_f12_copy(base, O, t);
 #pragma unroll 1
     for (int b = 62; b >= 0; b--) {
-        b_f12_mul(O, O, O, P, t);
-        if ((PAIRING_X >> b) & 1ull) b_f12_mul(O, base, O, P, t);
+        b_f12_mul(O, O, O, t);
+        if ((PAIRING_X >> b) & 1ull) b_f12_mul(O, base, O, t);
     }
 }
 
@@ -742,7 +716,6 @@ __global__ void __launch_bounds__(B_THREADS) k_b_final_exp(const Fq12::Mem *__re
     if (is_one) is_one += blockIdx.x;
     enum { R = 0, Y0, Y1, Y2, Y3, Y4, Y5, X, T };
     FqImg(*V)[12] = S.V;
-    FqImg *P = S.P;
     // f^(p^6 - 1) = conj(f) * f^-1 : the one inversion, on thread 0 with the per-thread tower
     if (t == 0) {
         Fq12 f = f12_load(in[0]);
@@ -756,33 +729,33 @@ __global__ void __launch_bounds__(B_THREADS) k_b_final_exp(const Fq12::Mem *__re
     if (t < 12) V[Y1][tower_to_power(t)] = reinterpret_cast<const FqImg *>(&inv_img)[t];   // f^-1
     __syncthreads();
     b_f12_conj(V[X], V[Y0], t);                      // conj(f)
-    b_f12_mul(V[Y0], V[Y1], V[R], P, t);             // r = conj(f) / f
+    b_f12_mul(V[Y0], V[Y1], V[R], t);             // r = conj(f) / f
     b_f12_frob(V[R], V[Y0], 2, t);
-    b_f12_mul(V[Y0], V[R], V[R], P, t);              // r = frob^2(r) * r          (easy part)
+    b_f12_mul(V[Y0], V[R], V[R], t);              // r = frob^2(r) * r          (easy part)
     // hard part
-    b_f12_mul(V[R], V[R], V[X], P, t);
+    b_f12_mul(V[R], V[R], V[X], t);
     b_f12_conj(V[X], V[Y0], t);                      // y0 = conj(r^2)
-    b_exp_by_x(V[R], V[Y5], P, t);                   // y5 = r^x
-    b_f12_mul(V[Y5], V[Y5], V[Y1], P, t);            // y1 = y5^2
-    b_f12_mul(V[Y0], V[Y5], V[Y3], P, t);            // y3 = y0 y5
-    b_exp_by_x(V[Y3], V[Y0], P, t);                  // y0 = y3^x
-    b_exp_by_x(V[Y0], V[Y2], P, t);                  // y2 = y0^x
-    b_exp_by_x(V[Y2], V[Y4], P, t);
-    b_f12_mul(V[Y4], V[Y1], V[Y4], P, t);            // y4 = y2^x y1
-    b_exp_by_x(V[Y4], V[Y1], P, t);                  // y1 = y4^x
+    b_exp_by_x(V[R], V[Y5], t);                   // y5 = r^x
+    b_f12_mul(V[Y5], V[Y5], V[Y1], t);            // y1 = y5^2
+    b_f12_mul(V[Y0], V[Y5], V[Y3], t);            // y3 = y0 y5
+    b_exp_by_x(V[Y3], V[Y0], t);                  // y0 = y3^x
+    b_exp_by_x(V[Y0], V[Y2], t);                  // y2 = y0^x
+    b_exp_by_x(V[Y2], V[Y4], t);
+    b_f12_mul(V[Y4], V[Y1], V[Y4], t);            // y4 = y2^x y1
+    b_exp_by_x(V[Y4], V[Y1], t);                  // y1 = y4^x
     b_f12_conj(V[Y3], V[Y3], t);                     // y3 = conj(y3)
-    b_f12_mul(V[Y1], V[Y3], V[Y1], P, t);
-    b_f12_mul(V[Y1], V[R], V[Y1], P, t);             // y1 = y1 y3 r
+    b_f12_mul(V[Y1], V[Y3], V[Y1], t);
+    b_f12_mul(V[Y1], V[R], V[Y1], t);             // y1 = y1 y3 r
     b_f12_conj(V[R], V[Y3], t);                      // y3 = conj(r)
-    b_f12_mul(V[Y0], V[R], V[X], P, t);
+    b_f12_mul(V[Y0], V[R], V[X], t);
     b_f12_frob(V[X], V[Y0], 3, t);                   // y0 = frob^3(y0 r)
-    b_f12_mul(V[Y4], V[Y3], V[X], P, t);
+    b_f12_mul(V[Y4], V[Y3], V[X], t);
     b_f12_frob(V[X], V[Y4], 1, t);                   // y4 = frob(y4 y3)
-    b_f12_mul(V[Y5], V[Y2], V[X], P, t);
+    b_f12_mul(V[Y5], V[Y2], V[X], t);
     b_f12_frob(V[X], V[Y5], 2, t);                   // y5 = frob^2(y5 y2)
-    b_f12_mul(V[Y5], V[Y0], V[X], P, t);
-    b_f12_mul(V[X], V[Y4], V[X], P, t);
-    b_f12_mul(V[X], V[Y1], V[X], P, t);              // result
+    b_f12_mul(V[Y5], V[Y0], V[X], t);
+    b_f12_mul(V[X], V[Y4], V[X], t);
+    b_f12_mul(V[X], V[Y1], V[X], t);              // result
     if (out && t < 12) reinterpret_cast<FqImg *>(out)[t] = V[X][tower_to_power(t)];
     if (is_one && t < 32) {
         bool ok = true;
