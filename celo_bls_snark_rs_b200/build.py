@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libb200bls.so")
 UNITS = ["engine.cu", "inst_g1_377.cu", "inst_g2_377.cu", "inst_761.cu", "inst_pairing.cu", "inst_bw6_pairing.cu", "inst_epoch_verify.cu", "inst_verify.cu", "inst_ntt.cu", "inst_groth16.cu", "inst_hash.cu", "sys_compat.cu", "sys_compat_keys.cu"]
 HEADERS = ["fp.cuh", "ec.cuh", "msm.cuh", "engine.cuh", "curve_impl.cuh", "params_gen.cuh", "pairing.cuh", "pairing_warp.cuh",
-           "pairing_params_gen.cuh", "ntt.cuh", "pairing_bw6.cuh", "codec.cuh", "coop.cuh", "pairing_bw6_params_gen.cuh", "msm_afftree.cuh",
+           "pairing_params_gen.cuh", "ntt.cuh", "pairing_bw6.cuh", "codec.cuh", "coop.cuh", "pairing_bw6_params_gen.cuh", "msm_afftree.cuh", "pairing_bw6_coop.cuh",
            os.path.join("..", "..", "include", "b200_bls.h"), os.path.join("..", "..", "include", "bls_snark_sys_compat.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -140,10 +140,15 @@ struct CoopOps {
     }
     B200_DEV static bool is_zero(const Ctx &c, uint32_t a) { return gballot(c, a != 0u) == 0u; }
 
-    // Montgomery product a b / R mod p
-    B200_DEV static uint32_t mul(const Ctx &c, uint32_t a, uint32_t b) {
-        const int g = c.g;
+    // Montgomery product a b / R mod p, in two halves so that a SUM of products can share one reduction:
+    // accumulate() adds the column sums of a b into s (pass 1), reduce() turns s into (sum) / R mod p (passes 2 and 3).
+    // Columns are 96 bits wide and a lane adds N products of 64 bits per accumulate(): hundreds of terms fit; the
+    // reduction needs sum < R p, i.e. K p < R for K terms -- K < 128 for both moduli (7 spare bits).
+    struct Acc {
         uint32_t l0 = 0, l1 = 0, l2 = 0, h0 = 0, h1 = 0, h2 = 0;
+    };
+    B200_DEV static void accumulate(const Ctx &c, Acc &s, uint32_t a, uint32_t b) {
+        const int g = c.g;
 #pragma unroll
         for (int j = 0; j < N; j++) {
             const uint32_t aj = __shfl_sync(COOP_FULL, a, j, GW);
@@ -151,11 +156,14 @@ struct CoopOps {
             k += k < 0 ? N : 0;
             const uint32_t bk = __shfl_sync(COOP_FULL, b, k, GW);
             const bool low = j <= g;
-            mad96(l0, l1, l2, low ? aj : 0u, bk);
-            mad96(h0, h1, h2, low ? 0u : aj, bk);
+            mad96(s.l0, s.l1, s.l2, low ? aj : 0u, bk);
+            mad96(s.h0, s.h1, s.h2, low ? 0u : aj, bk);
         }
+    }
+    B200_DEV static uint32_t reduce(const Ctx &c, const Acc &s) {
+        const int g = c.g;
         uint32_t t_lo, t_hi;
-        normalize(c, l0, l1, l2, h0, h1, h2, t_lo, t_hi);
+        normalize(c, s.l0, s.l1, s.l2, s.h0, s.h1, s.h2, t_lo, t_hi);
         uint32_t m0 = 0, m1 = 0, m2 = 0;
 #pragma unroll
         for (int j = 0; j < N; j++) {
@@ -166,7 +174,7 @@ struct CoopOps {
             mad96(m0, m1, m2, j <= g ? tj : 0u, qk);
         }
         const uint32_t m = normalize_low(c, m0, m1, m2);
-        l0 = t_lo, l1 = 0, l2 = 0, h0 = t_hi, h1 = 0, h2 = 0;
+        uint32_t l0 = t_lo, l1 = 0, l2 = 0, h0 = t_hi, h1 = 0, h2 = 0;
 #pragma unroll
         for (int j = 0; j < N; j++) {
             const uint32_t mj = __shfl_sync(COOP_FULL, m, j, GW);
@@ -180,6 +188,11 @@ struct CoopOps {
         uint32_t u_lo, u_hi;
         normalize(c, l0, l1, l2, h0, h1, h2, u_lo, u_hi);    // u_lo == 0 by construction
         return cond_sub(c, u_hi);
+    }
+    B200_DEV static uint32_t mul(const Ctx &c, uint32_t a, uint32_t b) {
+        Acc s;
+        accumulate(c, s, a, b);
+        return reduce(c, s);
     }
 };
 

@@ -3,6 +3,7 @@
 // (ark-groth16 verify_proof), reached from the C-ABI `verify` (crates/bls-snark-sys/src/snark/mod.rs:23-45).
 #include "curve_impl.cuh"
 #include "pairing_bw6.cuh"
+#include "pairing_bw6_coop.cuh"
 
 namespace b200 {
 
@@ -25,8 +26,15 @@ int bw6_miller_values(Engine &E, const void *d_g1_packed, const void *d_g2_packe
 int bw6_final_exp(Engine &E, const void *d_vals, size_t count, void *d_out, int *d_is_one, cudaStream_t st) {
     (void)E;
     if (count == 0) return fail(B200_ERR_ARG, "final exponentiation needs at least one value");
-    k_bw6_final_exp<<<1, BW6_THREADS, 0, st>>>(reinterpret_cast<const BImg *>(d_vals), (uint32_t)count,
-                                               reinterpret_cast<BImg *>(d_out), d_is_one);
+    // six warps, one output coefficient each, on the warp-cooperative field (pairing_bw6_coop.cuh);
+    // B200_BW6_THREAD_KERNELS=1 selects the one-product-per-thread kernels (cross-check)
+    static const bool thread_kernels = getenv("B200_BW6_THREAD_KERNELS") && atoi(getenv("B200_BW6_THREAD_KERNELS"));
+    if (thread_kernels)
+        k_bw6_final_exp<<<1, BW6_THREADS, 0, st>>>(reinterpret_cast<const BImg *>(d_vals), (uint32_t)count,
+                                                   reinterpret_cast<BImg *>(d_out), d_is_one);
+    else
+        k_bw6_final_exp_coop<<<1, BW6C_THREADS, 0, st>>>(reinterpret_cast<const BImg *>(d_vals), (uint32_t)count,
+                                                         reinterpret_cast<BImg *>(d_out), d_is_one);
     LAUNCH_CHECK();
     return B200_OK;
 }
