@@ -68,6 +68,14 @@ def main():
     ptr, n = ctypes.c_void_p(), ctypes.c_int()
     assert lib.serialize_signature(sg, ctypes.byref(ptr), ctypes.byref(n)) and ctypes.string_at(ptr, n.value) == sgb
     assert lib.free_vec(ptr, n.value) and lib.destroy_public_key(pk) and lib.destroy_signature(sg)
+    # the SNARK verifier entry point on the reference's known-answer instance: point decoding, the warp-cooperative subgroup
+    # checks, g_ic, the BW6-761 Miller loops and the warp-cooperative final exponentiation
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    from bw6_kat import GOLD
+    vk_b, proof_b = bytes.fromhex(GOLD["bw6_groth16_vk"]["hex"]), bytes.fromhex(GOLD["bw6_groth16_proof"]["hex"])
+    first = E.EpochBlock(0, 0, bytes([1] * 16), bytes([2] * 16), 1, 4, bytes.fromhex(GOLD["bls12_377_first_pubkeys"]["hex"]))
+    last = E.EpochBlock(2, 0, bytes([3] * 16), bytes([2] * 16), 1, 4, bytes.fromhex(GOLD["bls12_377_last_pubkeys"]["hex"]))
+    assert E.verify_epochs(vk_b, proof_b, first, last)
     print("sanitize smoke ok; launches =", E.launch_count())
     E.shutdown()
 
