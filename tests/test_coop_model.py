@@ -25,3 +25,19 @@ def test_coop_field_ops_match_integers(p, n):
             assert M.value_of(M.coop_mul(al, bl, pl, ql, n)) == a * b * rinv % p
             assert M.value_of(M.coop_add(al, bl, pl, n)) == (a + b) % p
             assert M.value_of(M.coop_sub(al, bl, pl, n)) == (a - b) % p
+
+
+@pytest.mark.parametrize("p,n", [(P377, 12), (Q761, 24)])
+def test_coop_dot_products_share_one_reduction(p, n):
+    """CoopOps::accumulate x K + CoopOps::reduce (the six-term coefficient sums of pairing_bw6_coop.cuh): worst-case
+    operands (p - 1 everywhere) stay inside the 96-bit columns and one conditional subtraction lands in [0, p)."""
+    R = 1 << (32 * n)
+    q = (-pow(p, -1, R)) % R
+    pl, ql = M.limbs_of(p, n), M.limbs_of(q, n)
+    rinv = pow(R, -1, p)
+    rng = random.Random(11 + n)
+    for k in (1, 2, 3, 6, 12):
+        for trial in range(6):
+            vals = [(p - 1, p - 1)] * k if trial == 0 else [(rng.randrange(p), rng.randrange(p)) for _ in range(k)]
+            got = M.coop_dot([(M.limbs_of(a, n), M.limbs_of(b, n)) for a, b in vals], pl, ql, n)
+            assert M.value_of(got) == sum(a * b for a, b in vals) * rinv % p

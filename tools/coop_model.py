@@ -106,6 +106,38 @@ def coop_mul(a, b, p, q, n):
     return cond_sub(u_hi, p, n)
 
 
+def coop_dot(pairs, p, q, n):
+    """sum of products sharing ONE reduction (csrc/coop.cuh CoopOps::accumulate x K, then CoopOps::reduce): the column
+    sums of every a * b go into the same accumulators.  Needs 96-bit columns (K n products of 64 bits per lane) and
+    K p < R; returns sum(a * b) / R mod p."""
+    lo, hi = [0] * n, [0] * n
+    for a, b in pairs:
+        for j in range(n):
+            for i in range(n):
+                if j <= i:
+                    lo[i] += a[j] * b[(i - j) % n]
+                else:
+                    hi[i] += a[j] * b[(i - j) % n]
+    assert all(x < (1 << 96) for x in lo + hi), "column accumulators are 96 bits wide"
+    t_lo, t_hi = normalize(lo, hi, n)
+    mc = [0] * n
+    for j in range(n):
+        for i in range(n):
+            if j <= i:
+                mc[i] += t_lo[j] * q[(i - j) % n]
+    m, _ = normalize(mc, [0] * n, n, low_only=True)
+    lo, hi = list(t_lo), list(t_hi)
+    for j in range(n):
+        for i in range(n):
+            if j <= i:
+                lo[i] += m[j] * p[(i - j) % n]
+            else:
+                hi[i] += m[j] * p[(i - j) % n]
+    u_lo, u_hi = normalize(lo, hi, n)
+    assert all(x == 0 for x in u_lo), "low half of T + m p must vanish"
+    return cond_sub(u_hi, p, n)
+
+
 def coop_add(a, b, p, n):
     gen = prop = 0
     s = [0] * n
