@@ -39,6 +39,15 @@ struct alignas(16) WarpScratch {                     // per-warp shared memory (
 enum : int { S_RX = 0, S_RY, S_RZ, S_QX, S_QY, S_PX, S_PY, S_TWOINV, S_TWISTB, S_L0, S_L1, S_L2, S_T0 /* = 12 .. 23 temps */ };
 
 B200_DEV PFq w_ld(const FqImg &m) { return PFq::load(m); }
+// Every field product of the warp kernels goes through ONE out-of-line body: with the ~600-instruction product inlined
+// in each helper (f12 product, squaring, the two Fq2 product rounds, Frobenius) the warps of an SM -- all in different
+// phases of their Miller loops -- ran out of instruction cache (ncu: 3.7 warps per issue stalled on "no instruction").
+// (SH = false: inlined, for the single-block latency kernels, where a call per product only adds to the chain.)
+template <bool SH = true>
+B200_DEV PFq w_mul(const PFq &a, const PFq &b) {
+    if constexpr (SH) return PFq::mul_outline(a, b);
+    else return a * b;
+}
 B200_DEV void w_st(FqImg &m, const PFq &v) { m = v.store(); }
 
 // tower image index m = 6I + 2J + K  <->  power-basis exponent e = 6K + 2J + I
@@ -59,7 +68,7 @@ __device__ __noinline__ void w_f12_mul(const FqImg *A, const FqImg *B, FqImg *O,
             int i = e - j;
             bool wrap = i < 0;
             i += wrap ? 12 : 0;
-            PFq prod = w_ld(A[i]) * w_ld(B[j]);
+            PFq prod = w_mul(w_ld(A[i]), w_ld(B[j]));
             if (wrap) accN = accN + prod;
             else accP = accP + prod;
         }
@@ -87,7 +96,7 @@ __device__ __noinline__ void w_f12_sqr(const FqImg *A, FqImg *O, int lane) {
                 const bool wrap = m > half;
                 const int i = wrap ? e + m - half : m;
                 const int j = wrap ? 12 + half - m : e - m;
-                PFq prod = w_ld(A[i]) * w_ld(A[j]);
+                PFq prod = w_mul(w_ld(A[i]), w_ld(A[j]));
                 if (i != j) prod = prod.dbl();
                 if (wrap) accN = accN + prod;
                 else accP = accP + prod;
@@ -105,7 +114,7 @@ constexpr uint64_t JPACK_LINE = 0x976310ull;         // exponents {0,1,3,6,7,9}:
 
 // coefficient-wise: O[e] = A[e] * gamma_j^e (Frobenius), or negate odd e (conjugation)
 B200_DEV void w_f12_frob(const FqImg *A, FqImg *O, int j, int lane) {
-    if (lane < 12) w_st(O[lane], w_ld(A[lane]) * pfq_const(PAIRING_GAMMA[j - 1][lane]));
+    if (lane < 12) w_st(O[lane], w_mul(w_ld(A[lane]), pfq_const(PAIRING_GAMMA[j - 1][lane])));
     __syncwarp();
 }
 B200_DEV void w_f12_conj(const FqImg *A, FqImg *O, int lane) {
@@ -135,6 +144,7 @@ B200_DEV void w_f12_store_global(const FqImg *A, Fq12::Mem *g, int lane) {
 
 // ---- batches of Fq2 products / linear statements on the slots ----------------------------------
 // product k (lanes 4k .. 4k+3): slot[dst_k] = slot[x_k] * slot[y_k]; packs hold one byte per product
+template <bool SH = true>
 static __device__ __noinline__ void w_f2_mul(Fq2Slot *s, int nprod, uint64_t xpack, uint64_t ypack, uint64_t dpack, int lane) {
     const int k = lane >> 2, t = lane & 3;
     const bool live = k < nprod;
@@ -143,7 +153,7 @@ static __device__ __noinline__ void w_f2_mul(Fq2Slot *s, int nprod, uint64_t xpa
         const Fq2Slot &X = s[(xpack >> (8 * k)) & 0xff], &Y = s[(ypack >> (8 * k)) & 0xff];
         PFq a = w_ld((t & 1) ? X.c1 : X.c0);                       // t: 0 (c0,c0) 1 (c1,c1) 2 (c0,c1) 3 (c1,c0)
         PFq b = w_ld((t == 1 || t == 2) ? Y.c1 : Y.c0);
-        prod = a * b;
+        prod = w_mul<SH>(a, b);
     }
     PFq other = prod.shfl(0xffffffffu, lane ^ 1);
     __syncwarp();                                                  // operands read before any slot is overwritten
@@ -199,18 +209,19 @@ __device__ const uint32_t DBL_D1[] = {LST(L_TRI, T20, T20), LST(L_CPY, S_L2, T22
 __device__ const uint32_t DBL_D2[] = {LST(L_SUB, S_RY, T12, T20)};
 
 // doubling_step + line scaling by P (arkworks: coeffs (-h, 3j, i); c0 *= P.y, c1 *= P.x)
+template <bool SH = true>
 B200_DEV void w_doubling_step(Fq2Slot *s, int lane) {
     w_f2_lin(s, 1, DBL_A, lane);                                                    // T12 = ry + rz
-    w_f2_mul(s, 5, PK(S_RX, S_RY, S_RZ, T12, S_RX), PK(S_RY, S_RY, S_RZ, T12, S_RX),
+    w_f2_mul<SH>(s, 5, PK(S_RX, S_RY, S_RZ, T12, S_RX), PK(S_RY, S_RY, S_RZ, T12, S_RX),
              PK(T13, T14, T15, T16, T17), lane);                                    // rx ry | b | c | (ry+rz)^2 | j
     w_f2_lin(s, 1, DBL_B, lane);                                                    // T18 = 3c
-    w_f2_mul(s, 2, PK(S_TWISTB, T13), PK(T18, S_TWOINV), PK(T19, T13), lane);       // e = b' 3c | a = rx ry / 2
+    w_f2_mul<SH>(s, 2, PK(S_TWISTB, T13), PK(T18, S_TWOINV), PK(T19, T13), lane);       // e = b' 3c | a = rx ry / 2
     w_f2_lin(s, 4, DBL_C1, lane);                                                   // f | b + c | i | 3j
     w_f2_lin(s, 3, DBL_C2, lane);                                                   // b + f | b - f | h
     w_f2_lin(s, 1, DBL_C3, lane);                                                   // -h
-    w_f2_mul(s, 6, PK(T12, T19, T13, T14, T21, T23), PK(S_TWOINV, T19, T18, T16, S_PY, S_PX),
+    w_f2_mul<SH>(s, 6, PK(T12, T19, T13, T14, T21, T23), PK(S_TWOINV, T19, T18, T16, S_PY, S_PX),
              PK(T12, T20, S_RX, S_RZ, S_L0, S_L1), lane);                           // g | e^2 | rx' | rz' | l0 | l1
-    w_f2_mul(s, 1, PK(T12), PK(T12), PK(T12), lane);                                // g^2
+    w_f2_mul<SH>(s, 1, PK(T12), PK(T12), PK(T12), lane);                                // g^2
     w_f2_lin(s, 2, DBL_D1, lane);                                                   // 3 e^2 | l2 = i
     w_f2_lin(s, 1, DBL_D2, lane);                                                   // ry' = g^2 - 3 e^2
 }
@@ -222,18 +233,19 @@ __device__ const uint32_t ADD_D[] = {LST(L_SUB, T12, T20, T23)};
 __device__ const uint32_t ADD_E[] = {LST(L_SUB, S_RY, T13, T16), LST(L_SUB, S_L2, T17, T19), LST(L_NEG, T21, T14)};
 
 // addition_step + line scaling (coeffs (lambda, -theta, j))
+template <bool SH = true>
 B200_DEV void w_addition_step(Fq2Slot *s, int lane) {
-    w_f2_mul(s, 2, PK(S_QY, S_QX), PK(S_RZ, S_RZ), PK(T12, T13), lane);             // qy rz | qx rz
+    w_f2_mul<SH>(s, 2, PK(S_QY, S_QX), PK(S_RZ, S_RZ), PK(T12, T13), lane);             // qy rz | qx rz
     w_f2_lin(s, 2, ADD_A, lane);                                                    // theta = T14 | lambda = T15
-    w_f2_mul(s, 2, PK(T14, T15), PK(T14, T15), PK(T16, T17), lane);                 // c = theta^2 | d = lambda^2
-    w_f2_mul(s, 3, PK(T15, S_RZ, S_RX), PK(T17, T16, T17), PK(T18, T19, T20), lane);  // e | f | g
+    w_f2_mul<SH>(s, 2, PK(T14, T15), PK(T14, T15), PK(T16, T17), lane);                 // c = theta^2 | d = lambda^2
+    w_f2_mul<SH>(s, 3, PK(T15, S_RZ, S_RX), PK(T17, T16, T17), PK(T18, T19, T20), lane);  // e | f | g
     w_f2_lin(s, 2, ADD_B, lane);                                                    // e + f | 2g
     w_f2_lin(s, 1, ADD_C, lane);                                                    // h = T23
     w_f2_lin(s, 1, ADD_D, lane);                                                    // g - h = T12
-    w_f2_mul(s, 6, PK(T15, T14, T18, S_RZ, T14, T15), PK(T23, T12, S_RY, T18, S_QX, S_QY),
+    w_f2_mul<SH>(s, 6, PK(T15, T14, T18, S_RZ, T14, T15), PK(T23, T12, S_RY, T18, S_QX, S_QY),
              PK(S_RX, T13, T16, S_RZ, T17, T19), lane);   // rx' | theta (g-h) | e ry | rz' | theta qx | lambda qy
     w_f2_lin(s, 3, ADD_E, lane);                                                    // ry' | l2 = j | -theta
-    w_f2_mul(s, 2, PK(T15, T21), PK(S_PY, S_PX), PK(S_L0, S_L1), lane);             // l0 = lambda py | l1 = -theta px
+    w_f2_mul<SH>(s, 2, PK(T15, T21), PK(S_PY, S_PX), PK(S_L0, S_L1), lane);             // l0 = lambda py | l1 = -theta px
 }
 
 // line (l0, l1, l2) -> sparse power-basis element: exponents 0,6 <- l0 ; 1,7 <- l1 ; 3,9 <- l2
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(32 * W_WARPS) k_w_miller_loop(const AffineMem<
 // steps run side by side in the same product rounds (<= 4 Fq2 products per pair and round, 4 lanes
 // each).  Slot sets s0 / s1 hold the two pairs' line state; `two` is false when the warp has only
 // one finite pair.
+template <bool SH = true>
 static __device__ __noinline__ void w_f2_mul2(Fq2Slot *s0, Fq2Slot *s1, bool two, int nprod, uint32_t xpack,
                                               uint32_t ypack, uint32_t dpack, int lane) {
     const int k = lane >> 2, t = lane & 3;
@@ -315,7 +328,7 @@ static __device__ __noinline__ void w_f2_mul2(Fq2Slot *s0, Fq2Slot *s1, bool two
         const Fq2Slot &X = s[(xpack >> (8 * kk)) & 0xff], &Y = s[(ypack >> (8 * kk)) & 0xff];
         PFq a = w_ld((t & 1) ? X.c1 : X.c0);                       // t: 0 (c0,c0) 1 (c1,c1) 2 (c0,c1) 3 (c1,c0)
         PFq b = w_ld((t == 1 || t == 2) ? Y.c1 : Y.c0);
-        prod = a * b;
+        prod = w_mul<SH>(a, b);
     }
     PFq other = prod.shfl(0xffffffffu, lane ^ 1);
     __syncwarp();
@@ -356,16 +369,17 @@ __host__ __device__ constexpr uint32_t PK4(int a0 = 0, int a1 = 0, int a2 = 0, i
     return (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16) | ((uint32_t)a3 << 24);
 }
 // w_doubling_step for both slot sets at once (same statements, product rounds regrouped to <= 4)
+template <bool SH = true>
 B200_DEV void w_doubling_step2(Fq2Slot *s0, Fq2Slot *s1, bool two, int lane) {
     w_f2_lin2(s0, s1, two, 1, DBL_A, lane);                                                   // T12 = ry + rz
-    w_f2_mul2(s0, s1, two, 4, PK4(S_RX, S_RY, S_RZ, T12), PK4(S_RY, S_RY, S_RZ, T12), PK4(T13, T14, T15, T16), lane);
+    w_f2_mul2<SH>(s0, s1, two, 4, PK4(S_RX, S_RY, S_RZ, T12), PK4(S_RY, S_RY, S_RZ, T12), PK4(T13, T14, T15, T16), lane);
     w_f2_lin2(s0, s1, two, 1, DBL_B, lane);                                                   // T18 = 3c
-    w_f2_mul2(s0, s1, two, 3, PK4(S_TWISTB, T13, S_RX), PK4(T18, S_TWOINV, S_RX), PK4(T19, T13, T17), lane);   // e | a | j
+    w_f2_mul2<SH>(s0, s1, two, 3, PK4(S_TWISTB, T13, S_RX), PK4(T18, S_TWOINV, S_RX), PK4(T19, T13, T17), lane);   // e | a | j
     w_f2_lin2(s0, s1, two, 4, DBL_C1, lane);
     w_f2_lin2(s0, s1, two, 3, DBL_C2, lane);
     w_f2_lin2(s0, s1, two, 1, DBL_C3, lane);
-    w_f2_mul2(s0, s1, two, 4, PK4(T12, T19, T13, T14), PK4(S_TWOINV, T19, T18, T16), PK4(T12, T20, S_RX, S_RZ), lane);   // g | e^2 | rx' | rz'
-    w_f2_mul2(s0, s1, two, 3, PK4(T12, T21, T23), PK4(T12, S_PY, S_PX), PK4(T12, S_L0, S_L1), lane);                     // g^2 | l0 | l1
+    w_f2_mul2<SH>(s0, s1, two, 4, PK4(T12, T19, T13, T14), PK4(S_TWOINV, T19, T18, T16), PK4(T12, T20, S_RX, S_RZ), lane);   // g | e^2 | rx' | rz'
+    w_f2_mul2<SH>(s0, s1, two, 3, PK4(T12, T21, T23), PK4(T12, S_PY, S_PX), PK4(T12, S_L0, S_L1), lane);                     // g^2 | l0 | l1
     w_f2_lin2(s0, s1, two, 2, DBL_D1, lane);
     w_f2_lin2(s0, s1, two, 1, DBL_D2, lane);
 }
@@ -519,11 +533,11 @@ __global__ void __launch_bounds__(B2_THREADS) k_b2_miller_loop(const AffineMem<P
         const bool two = live == 2;
         // lines of bit b: doubling lines in slots 0 / 1, addition lines (bit set) in slots 2 / 3
         auto lines_of_bit = [&](int b, int par) {
-            w_doubling_step2(S.s[0], S.s[1], two, lane);
+            w_doubling_step2<false>(S.s[0], S.s[1], two, lane);
             for (int k = 0; k < live; k++) w_line_to_power(S.s[k], S.line[par][k], lane);
             if ((PAIRING_X >> b) & 1ull) {
                 for (int k = 0; k < live; k++) {
-                    w_addition_step(S.s[k], lane);
+                    w_addition_step<false>(S.s[k], lane);
                     w_line_to_power(S.s[k], S.line[par][2 + k], lane);
                 }
             }
