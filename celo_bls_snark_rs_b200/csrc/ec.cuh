@@ -288,9 +288,30 @@ struct Quad {
     }
 };
 
+// Quad whose products go through the field's ONE out-of-line body (Fp::mul_outline; Fp2 products already do): for
+// kernels with many warps in different phases of long loops, where seven inlined ~600-instruction products per point
+// operation overflow the instruction cache (the many-small-MSMs kernel: 26 us per scalar bit either way until then).
+template <class F> struct OutlineMul {
+    B200_DEV static F mul(const F &a, const F &b) { return a * b; }
+};
+template <class P> struct OutlineMul<Fp<P>> {
+    B200_DEV static Fp<P> mul(const Fp<P> &a, const Fp<P> &b) { return Fp<P>::mul_outline(a, b); }
+};
+struct QuadShared : Quad {
+    template <class F>
+    B200_DEV void mul4(const F &a0, const F &b0, const F &a1, const F &b1, const F &a2, const F &b2, const F &a3,
+                       const F &b3, F &p0, F &p1, F &p2, F &p3) const {
+        F p = OutlineMul<F>::mul(F::sel4(q, a0, a1, a2, a3), F::sel4(q, b0, b1, b2, b3));
+        p0 = p.shfl(mask, base);
+        p1 = p.shfl(mask, base + 1);
+        p2 = p.shfl(mask, base + 2);
+        p3 = p.shfl(mask, base + 3);
+    }
+};
+
 // dbl-2008-s-1 in 3 rounds.  All lanes of the quad must call with identical arguments.
-template <class F>
-B200_DEV void quad_dbl(const Quad &Q, XYZZ<F> &a) {
+template <class F, class QT>
+B200_DEV void quad_dbl(const QT &Q, XYZZ<F> &a) {
     if (a.is_inf()) return;
     F u = a.y.dbl();
     F v, xx, d0, d1;
@@ -308,8 +329,8 @@ B200_DEV void quad_dbl(const Quad &Q, XYZZ<F> &a) {
 }
 
 // add-2008-s in 4 rounds (exceptional cases exact, as in XYZZ::add_outline).
-template <class F>
-B200_DEV void quad_add(const Quad &Q, XYZZ<F> &a, const XYZZ<F> &o) {
+template <class F, class QT>
+B200_DEV void quad_add(const QT &Q, XYZZ<F> &a, const XYZZ<F> &o) {
     if (o.is_inf()) return;
     if (a.is_inf()) {
         a = o;

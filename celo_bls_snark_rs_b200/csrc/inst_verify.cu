@@ -144,14 +144,14 @@ int batch_verify_strict_many(Engine &E, const b200_strict_batch *batches, size_t
     if ((rc = batch_to_affine<G1_377>(g1j, total + count, g1a, st))) return rc;
     if ((rc = batch_to_affine<G2_377>(g2j, total, g2a, st))) return rc;
     CUDA_TRY(cudaMemcpy2DAsync(p1 + G1A, 2 * G1A, g1a + total * G1A, G1A, G1A, count, cudaMemcpyDeviceToDevice, st));
-    constexpr int TH = 64;
+    constexpr int TH = 128;                                       // 32 quads: one point each per pass
     CUDA_TRY(cudaEventRecord(E.ev_fork, st));
     CUDA_TRY(cudaStreamWaitEvent(side, E.ev_fork, 0));
-    k_small_msm<Fq377, 8, TH><<<(unsigned)count, TH, TH * sizeof(XYZZMem<Fq377>), st>>>(
+    k_small_msm_quad<Fq377, 8, TH><<<(unsigned)count, TH, (TH / 4) * sizeof(XYZZMem<Fq377>), st>>>(
         reinterpret_cast<const AffineMem<Fq377> *>(g1a), E.scalars.as<uint32_t>(), E.v_offsets.as<uint32_t>(), bits,
         reinterpret_cast<AffineMem<Fq377> *>(p1), 2, 0);
     LAUNCH_CHECK();
-    k_small_msm<Fp2<Fq377>, 8, TH><<<(unsigned)count, TH, TH * sizeof(XYZZMem<Fp2<Fq377>>), side>>>(
+    k_small_msm_quad<Fp2<Fq377>, 8, TH><<<(unsigned)count, TH, (TH / 4) * sizeof(XYZZMem<Fp2<Fq377>>), side>>>(
         reinterpret_cast<const AffineMem<Fp2<Fq377>> *>(g2a), E.scalars.as<uint32_t>(), E.v_offsets.as<uint32_t>(), bits,
         reinterpret_cast<AffineMem<Fp2<Fq377>> *>(p2), 2, 1);
     LAUNCH_CHECK();

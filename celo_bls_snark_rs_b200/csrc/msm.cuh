@@ -841,6 +841,51 @@ __global__ void __launch_bounds__(THREADS) k_small_msm(const AffineMem<F> *__res
     }
 }
 
+// The same with a QUAD per point (quad-cooperative doubling / addition, ec.cuh): a doubling is 3 product rounds instead of
+// 9 sequential products, so the chain of `bits` doublings that paces the launch is three times shorter -- 300 batches of
+// 20 keys over Fq2: 11.8 -> ~4 ms.  THREADS / 4 points per pass; the block sum is a quad tree in shared memory.
+template <class F, int SW, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_small_msm_quad(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ scalars,
+                                                            const uint32_t *__restrict__ offsets, int bits,
+                                                            AffineMem<F> *__restrict__ out, uint32_t out_stride, uint32_t out_slot) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XYZZMem<F> *sm = reinterpret_cast<XYZZMem<F> *>(smem_raw);
+    constexpr int QUADS = THREADS / 4;
+    const QuadShared Q;
+    const int quad = threadIdx.x >> 2;
+    const uint32_t lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t i = lo + quad; i < hi; i += QUADS) {
+        Affine<F> g = Affine<F>::from_ark(ldg_mem(bases + i));
+        if (g.is_inf()) continue;                    // uniform over the quad
+        const XYZZ<F> gp = {g.x, g.y, F::one(), F::one()};
+        XYZZ<F> r = XYZZ<F>::inf();
+        for (int b = bits - 1; b >= 0; b--) {
+            quad_dbl(Q, r);
+            if ((__ldg(scalars + (size_t)i * SW + (b >> 5)) >> (b & 31)) & 1u) quad_add(Q, r, gp);
+        }
+        quad_add(Q, acc, r);
+    }
+    if (Q.q == 0) sm[quad] = acc.store();
+    __syncthreads();
+    for (int s = QUADS / 2; s > 0; s >>= 1) {
+        if (quad < s) {
+            quad_add(Q, acc, XYZZ<F>::load(sm[quad + s]));
+            if (Q.q == 0) sm[quad] = acc.store();
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Affine<F> r = {F::zero(), F::zero()};
+        if (!acc.is_inf()) {
+            F iv = FieldInv<F>::inv(acc.zz * acc.zzz);
+            r.x = acc.x * (iv * acc.zzz);
+            r.y = acc.y * (iv * acc.zz);
+        }
+        out[(size_t)blockIdx.x * out_stride + out_slot] = r.to_ark();
+    }
+}
+
 // out[t * run + j] = (scalars[t] + j) * base for j < run: `run` consecutive multiples behind one double-and-add, so a
 // synthetic base array of 2^24 distinct points costs ~1 / run of k_fixed_base_mul (bench.py, configs 4 and 5)
 template <class F, int SW, int THREADS>
