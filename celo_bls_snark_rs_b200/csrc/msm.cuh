@@ -606,8 +606,8 @@ __global__ void __launch_bounds__(THREADS) k_ones_accumulate(const AffineMem<F> 
 
 // ---- bucket reduction (quad-cooperative: 4 lanes per point operation, see ec.cuh) -----------
 // k * p for small k (double-and-add, MSB first)
-template <class F>
-B200_DEV XYZZ<F> quad_small_mul(const Quad &Q, const XYZZ<F> &p, uint32_t k) {
+template <class F, class QT>
+B200_DEV XYZZ<F> quad_small_mul(const QT &Q, const XYZZ<F> &p, uint32_t k) {
     XYZZ<F> r = XYZZ<F>::inf();
     for (int b = 31 - __clz(k | 1u); b >= 0; b--) {
         quad_dbl(Q, r);
@@ -634,10 +634,10 @@ __global__ void __launch_bounds__(THREADS) k_huge_finish(const XYZZMem<F> *__res
 }
 
 // quad (w, seg): partial = sum_{j < L} (seg*L + j + 1) * B[w][seg*L + j]
-template <class F, int THREADS>
+template <class F, int THREADS, class QT = Quad>
 __global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__restrict__ buckets, MsmPlan p, int w_lo, int w_hi,
                                                            XYZZMem<F> *__restrict__ partials) {
-    const Quad Q;
+    const QT Q;
     uint32_t t = (blockIdx.x * THREADS + threadIdx.x) >> 2;
     uint32_t total = (uint32_t)(w_hi - w_lo) * p.segs;
     if (t >= total) return;                          // whole quads leave together (THREADS % 4 == 0)
