@@ -6,6 +6,13 @@
 namespace b200 {
 
 template <class C> struct CurveTraits;
+// ACC_SM: default accumulate kernel (0 registers only, 1 = X, Y of the accumulator and the cp.async-staged point in shared-memory
+// slots, 2 = the whole accumulator in slots) with ACC_SM_BLOCKS1 / ACC_SM_BLOCKS2 blocks of 128 threads per SM.  Measured
+// (profiles/r2_experiments.md): BLS12-377 G1 n = 2^20 8.27 -> 7.95 ms (1: 128 registers, 4 blocks), 7.94 (2: 96 registers, 5
+// blocks), 8.08 (2 with 6 blocks: spills); BW6-761 n = 2^22 150.0 -> 143.6 ms (1: 252 registers, no spills, 2 blocks), 147.0 (2).
+// ACC_SM_PIPE: the same choice inside the batch pipeline (3 = mode 1 with one block fewer per SM: with four blocks the sort and
+// tail kernels of the neighbouring MSMs find no room and a pipelined 2^20 MSM takes 8.32 ms instead of 7.19; BW6-761: 42.6 ms with
+// mode 1 against 44.4 with the register kernel).
 // AFFINE: the curve also has the experimental batched-affine accumulate kernels (compiled only with B200_WITH_CROSSCHECKS);
 // SHARED_MUL: the accumulate kernel multiplies through one out-of-line product body; COOP_COMBINE: the Horner combine runs
 // on four warps with one limb per lane (coop.cuh) -- 2.5x faster for the 24-limb field and for Fq2, no faster for the
@@ -15,9 +22,9 @@ constexpr bool B200_AFFINE_BUILD = true;
 #else
 constexpr bool B200_AFFINE_BUILD = false;
 #endif
-template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
-template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2, ACC_SM = 1, ACC_SM_PIPE = 3, ACC_SM_BLOCKS1 = 4, ACC_SM_BLOCKS2 = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 0, ACC_SM_PIPE = 0, ACC_SM_BLOCKS1 = 1, ACC_SM_BLOCKS2 = 1; static constexpr bool ACC_SM_BUILD = false; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
 // keeping enough buckets in flight to fill 148 SMs.
@@ -221,7 +228,7 @@ static int msm_stage_sort(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_s
 // separately; group = -1 takes everything in one launch (split must be 0), 0 / 1 one group (unit scalars ride with group 0)
 template <class C>
 static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const void *d_bases, size_t n, cudaStream_t st,
-                                MsmWs *Bp = nullptr, int resume = 0, int split = 0, int group = -1) {
+                                MsmWs *Bp = nullptr, int resume = 0, int split = 0, int group = -1, bool pipelined = false) {
     using F = typename C::F;
     using T = CurveTraits<C>;
     NvtxRange range("msm.accumulate");
@@ -282,7 +289,32 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
             LAUNCH_CHECK();
         }
     }
-    if (aft.levels) {
+    // Accumulator (partly) in shared memory, more blocks per SM (msm.cuh k_bucket_accumulate_sm).  B200_MSM_ACC_SM overrides
+    // the per-curve default: 0 register kernel; 1 X, Y and the staged point in slots; 2 the whole accumulator in slots
+    static const int acc_sm_env = getenv("B200_MSM_ACC_SM") ? atoi(getenv("B200_MSM_ACC_SM")) : -1;
+    // the batch pipeline (msm_batch) keeps sort / tail kernels of the neighbouring MSMs on the SMs beside this one
+    static const int acc_sm_pipe_env = getenv("B200_MSM_ACC_SM_PIPE") ? atoi(getenv("B200_MSM_ACC_SM_PIPE")) : -1;
+    const int acc_sm = pipelined ? (acc_sm_pipe_env >= 0 ? acc_sm_pipe_env : T::ACC_SM_PIPE) : (acc_sm_env >= 0 ? acc_sm_env : T::ACC_SM);
+    bool acc_sm_done = false;
+    if constexpr (T::ACC_SM_BUILD) {
+        if (!aft.levels && !affine && acc_sm) {
+            using SL = AccSlots<F, 128>;
+            using PP = typename F::Params;
+            const unsigned grid = (unsigned)ceil_div(total, 128);
+            auto go = [&](auto kern, int slots) -> int {
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::bytes(slots)));
+                kern<<<grid, 128, SL::bytes(slots), st>>>(bases, W.sorted.as<uint32_t>(), offsets, order, (uint32_t)total, p.big, resume,
+                                                          B.buckets.as<XYZZMem<F>>());
+                return B200_OK;
+            };
+            const int rc2 = acc_sm == 1   ? go(k_bucket_accumulate_sm<PP, 128, T::ACC_SM_BLOCKS1, false>, 4)
+                            : acc_sm == 3 ? go(k_bucket_accumulate_sm<PP, 128, T::ACC_SM_BLOCKS1 - 1, false>, 4)
+                                          : go(k_bucket_accumulate_sm<PP, 128, T::ACC_SM_BLOCKS2, true>, 6);
+            if (rc2) return rc2;
+            acc_sm_done = true;
+        }
+    }
+    if (aft.levels || acc_sm_done) {
     } else if (!affine && shared_mul && T::SHARED_MUL)
         k_bucket_accumulate_shared<F, T::ACC_THREADS, T::ACC_MIN_BLOCKS>
             <<<ceil_div(total, T::ACC_THREADS), T::ACC_THREADS, 0, st>>>(
@@ -487,7 +519,7 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
         CUDA_TRY(cudaEventRecord(E.ev_sorted[w], s_sort));
         CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_sorted[w], 0));
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_tail[w], 0));      // buckets of job k-2 consumed
-        if ((rc = msm_stage_accumulate<C>(E, W, plans[i], jobs[i].d_bases_packed, jobs[i].n, s_acc))) return rc;
+        if ((rc = msm_stage_accumulate<C>(E, W, plans[i], jobs[i].d_bases_packed, jobs[i].n, s_acc, nullptr, 0, 0, -1, true))) return rc;
         CUDA_TRY(cudaEventRecord(E.ev_acc[w], s_acc));
         CUDA_TRY(cudaStreamWaitEvent(s_tail, E.ev_acc[w], 0));
         if ((rc = msm_stage_tail<C>(W, plans[i], jobs[i].d_out_jacobian, s_tail))) return rc;

@@ -484,6 +484,152 @@ k_bucket_accumulate_shared(const AffineMem<F> *__restrict__ bases, const uint32_
     buckets[id] = acc.store();
 }
 
+// ---- bucket accumulation with half the accumulator in shared memory (round 2) -----------------------------------------
+// k_bucket_accumulate_shared is bound by the multiplier pipe at 85 % with THREE blocks per SM (168 registers: XYZZ
+// accumulator 48, current and prefetched point image 48, the temporaries of the mixed addition); the remaining stalls are
+// fixed-latency waits that only more warps can fill.  Here X and Y of the accumulator and the staged point live in
+// per-thread shared-memory slots (conflict-free 128-bit layout: chunk k of slot s of thread t at ((s * CH + k) * THREADS
+// + t) * 16), the next point is gathered global -> shared by cp.async (LDGSTS, no register staging) as soon as the current
+// one's two products have consumed it, and ZZ / ZZZ plus at most five temporaries stay in registers: <= 128 registers,
+// FOUR blocks per SM.  Same additions in the same order as the register kernel (bit-identical buckets).
+B200_DEV uint4 acc_lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+B200_DEV void acc_sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" : : "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <class F, int THREADS>
+struct AccSlots {
+    static constexpr int CH = F::N / 4;
+    static constexpr uint32_t STRIDE = THREADS * 16u, SLOT = CH * STRIDE;
+    enum : uint32_t { X = 0, Y = 1, PX = 2, PY = 3 };
+    static constexpr uint32_t bytes(int slots) { return (uint32_t)slots * SLOT; }
+    B200_DEV static F ld(uint32_t base, uint32_t slot) {
+        F r;
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const uint4 v = acc_lds128(base + slot * SLOT + k * STRIDE);
+            r.l[4 * k] = v.x, r.l[4 * k + 1] = v.y, r.l[4 * k + 2] = v.z, r.l[4 * k + 3] = v.w;
+        }
+        return r;
+    }
+    B200_DEV static void st(uint32_t base, uint32_t slot, const F &v) {
+#pragma unroll
+        for (int k = 0; k < CH; k++) acc_sts128(base + slot * SLOT + k * STRIDE, make_uint4(v.l[4 * k], v.l[4 * k + 1], v.l[4 * k + 2], v.l[4 * k + 3]));
+    }
+    // one packed affine record global -> slots PX, PY, asynchronously
+    B200_DEV static void fetch_point(uint32_t base, const AffineMem<F> *g) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g);
+#pragma unroll
+        for (int k = 0; k < 2 * CH; k++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" : : "r"(base + (PX + k / CH) * SLOT + (k % CH) * STRIDE), "l"(src + k) : "memory");
+        asm volatile("cp.async.commit_group;" : : : "memory");
+    }
+    B200_DEV static void wait_point() { asm volatile("cp.async.wait_group 0;" : : : "memory"); }
+};
+
+// ZS: ZZ and ZZZ live in slots too (six slots per thread), leaving only the temporaries of one addition in registers.
+template <class P, int THREADS, int MIN_BLOCKS, bool ZS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+k_bucket_accumulate_sm(const AffineMem<Fp<P>> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+                       const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
+                       uint32_t big, int resume, XYZZMem<Fp<P>> *__restrict__ buckets) {
+    using F = Fp<P>;
+    using S = AccSlots<F, THREADS>;
+    constexpr uint32_t SZZ = 4, SZZZ = 5;            // slots of ZZ / ZZZ when ZS
+    extern __shared__ uint4 acc_sm[];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(acc_sm) + threadIdx.x * 16u;
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    if (t >= total_buckets) return;
+    const uint32_t id = order[t];
+    uint32_t k = offsets[id];
+    const uint32_t end = offsets[id + 1];
+    if (end - k >= big) return;                      // left to k_big_buckets (one block per bucket)
+    if (resume && k == end) return;
+    F zz_r = F::zero(), zzz_r = F::zero();           // the register copies (ZS: unused)
+    bool empty = true;                               // the accumulator holds nothing yet
+    auto get_zz = [&]() { return ZS ? S::ld(base, SZZ) : zz_r; };
+    auto get_zzz = [&]() { return ZS ? S::ld(base, SZZZ) : zzz_r; };
+    auto set_z = [&](const F &a, const F &b) {
+        if (ZS) {
+            S::st(base, SZZ, a);
+            S::st(base, SZZZ, b);
+        } else {
+            zz_r = a;
+            zzz_r = b;
+        }
+    };
+    if (resume) {
+        const XYZZ<F> b = XYZZ<F>::load(buckets[id]);
+        S::st(base, S::X, b.x);
+        S::st(base, S::Y, b.y);
+        set_z(b.zz, b.zzz);
+        empty = b.zz.is_zero();
+    }
+    if (k < end) {
+        uint32_t e = __ldg(sorted + k);
+        uint32_t e_next = k + 1 < end ? __ldg(sorted + k + 1) : 0u;
+        S::fetch_point(base, bases + (e & 0x7fffffffu));
+        for (;;) {
+            ++k;
+            const bool more = k < end;
+            const uint32_t e_after = k + 1 < end ? __ldg(sorted + k + 1) : 0u;
+            S::wait_point();
+            F px = S::ld(base, S::PX), py = S::ld(base, S::PY);
+            const bool pt_inf = px.is_zero() && py.is_zero();
+            py = py.cneg(e >> 31);
+            if (pt_inf) {
+                if (more) S::fetch_point(base, bases + (e_next & 0x7fffffffu));
+            } else if (empty) {                       // first point of the bucket
+                S::st(base, S::X, px);
+                S::st(base, S::Y, py);
+                set_z(F::one(), F::one());
+                empty = false;
+                if (more) S::fetch_point(base, bases + (e_next & 0x7fffffffu));
+            } else {
+                // madd-2008-s, operands named as in XYZZ::madd
+                F p = F::mul_outline(px, get_zz()) - S::ld(base, S::X);
+                F r = F::mul_outline(py, get_zzz()) - S::ld(base, S::Y);
+                if (p.is_zero()) {                    // same x: P + P or P + (-P) (the point's slots are still intact)
+                    if (r.is_zero()) {
+                        const XYZZ<F> d = XYZZ<F>::dbl_affine(px, py);
+                        S::st(base, S::X, d.x);
+                        S::st(base, S::Y, d.y);
+                        set_z(d.zz, d.zzz);
+                    } else {
+                        empty = true;
+                    }
+                    if (more) S::fetch_point(base, bases + (e_next & 0x7fffffffu));
+                } else {
+                    if (more) S::fetch_point(base, bases + (e_next & 0x7fffffffu));     // lands under the eight products below
+                    const F pp = F::sqr_outline(p);
+                    const F ppp = F::mul_outline(p, pp);
+                    const F q = F::mul_outline(S::ld(base, S::X), pp);
+                    if (ZS) {
+                        S::st(base, SZZ, F::mul_outline(S::ld(base, SZZ), pp));
+                        S::st(base, SZZZ, F::mul_outline(S::ld(base, SZZZ), ppp));
+                    } else {
+                        zz_r = F::mul_outline(zz_r, pp);
+                        zzz_r = F::mul_outline(zzz_r, ppp);
+                    }
+                    const F x3 = F::sqr_outline(r) - ppp - q.dbl();
+                    S::st(base, S::X, x3);
+                    const F m1 = F::mul_outline(r, q - x3);
+                    S::st(base, S::Y, m1 - F::mul_outline(S::ld(base, S::Y), ppp));
+                }
+            }
+            if (!more) break;
+            e = e_next;
+            e_next = e_after;
+        }
+    }
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (!empty) acc = {S::ld(base, S::X), S::ld(base, S::Y), get_zz(), get_zzz()};
+    buckets[id] = acc.store();
+}
+
 // block-wide sum of XYZZ values held one per thread (smem tree); result valid in thread 0
 template <class F, int THREADS>
 B200_DEV XYZZ<F> block_sum(XYZZ<F> acc, XYZZMem<F> *sm) {
