@@ -497,13 +497,22 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
         if (jobs[i].n == 0) continue;
         plans[i] = n_eff ? make_plan_eff<C>(jobs[i].n, n_eff[i]) : make_plan<C>(jobs[i].n);
     }
-    size_t live = 0;                                               // workspace sets alternate over the non-empty jobs
+    // workspace sets rotate over the non-empty jobs.  THREE sets: the tail of job k (bucket reduce, window sums, Horner: 1.6 ms
+    // alone, several times that while the next accumulation owns the SMs) may lag two accumulations behind before job k + 3
+    // needs its buckets; with two sets every accumulation waited ~1 ms for the tail of the job two before it
+    // (B200_PIPE_SETS=2 restores that)
+    static const int sets = getenv("B200_PIPE_SETS") ? std::min(std::max(atoi(getenv("B200_PIPE_SETS")), 2), Engine::PIPE_SETS_MAX) : 3;
+    size_t live = 0;
     for (size_t i = 0; i < count; i++)
-        if (jobs[i].n && (rc = msm_reserve<C>(E.ws[live++ & 1], plans[i], jobs[i].n))) return rc;
+        if (jobs[i].n && (rc = msm_reserve<C>(E.ws[live++ % sets], plans[i], jobs[i].n))) return rc;
     ENGINE_ORDER(st);
-    cudaStream_t s_sort = E.pipe_stream[0], s_acc = E.pipe_stream[1], s_tail = E.pipe_stream[2];
+    cudaStream_t s_sort = E.pipe_stream[0], s_tail = E.pipe_stream[2];
+    // consecutive accumulations alternate between TWO streams (they touch different workspace sets): the blocks of job k + 1
+    // fill the SMs as job k's last blocks drain instead of waiting for the whole kernel to end (B200_PIPE_ACC_STREAMS=1: one stream)
+    static const bool two_acc = !(getenv("B200_PIPE_ACC_STREAMS") && atoi(getenv("B200_PIPE_ACC_STREAMS")) == 1);
+    cudaStream_t s_acc2[2] = {E.pipe_stream[1], two_acc ? E.split_stream : E.pipe_stream[1]};
     CUDA_TRY(cudaEventRecord(E.ev_fork, st));
-    for (cudaStream_t s : {s_sort, s_acc, s_tail}) CUDA_TRY(cudaStreamWaitEvent(s, E.ev_fork, 0));
+    for (cudaStream_t s : {s_sort, s_acc2[0], s_acc2[1], s_tail}) CUDA_TRY(cudaStreamWaitEvent(s, E.ev_fork, 0));
     size_t k = 0;
     for (size_t i = 0; i < count; i++) {
         if (jobs[i].n == 0) {
@@ -511,14 +520,15 @@ int msm_batch(Engine &E, const b200_msm_job *jobs, size_t count, cudaStream_t st
             LAUNCH_CHECK();
             continue;
         }
-        const int w = (int)(k & 1);
+        const int w = (int)(k % sets);
         MsmWs &W = E.ws[w];
+        cudaStream_t s_acc = s_acc2[k & 1];
         if (ready) CUDA_TRY(cudaStreamWaitEvent(s_sort, ready[i], 0));
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(s_sort, E.ev_acc[w], 0));      // sort buffers of job k-2 consumed
+        if (k >= (size_t)sets) CUDA_TRY(cudaStreamWaitEvent(s_sort, E.ev_acc[w], 0));      // sort buffers of the set's previous job consumed
         if ((rc = msm_stage_sort<C>(E, W, plans[i], jobs[i].d_scalars, jobs[i].n, s_sort))) return rc;
         CUDA_TRY(cudaEventRecord(E.ev_sorted[w], s_sort));
         CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_sorted[w], 0));
-        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_tail[w], 0));      // buckets of job k-2 consumed
+        if (k >= (size_t)sets) CUDA_TRY(cudaStreamWaitEvent(s_acc, E.ev_tail[w], 0));      // buckets of the set's previous job consumed
         if ((rc = msm_stage_accumulate<C>(E, W, plans[i], jobs[i].d_bases_packed, jobs[i].n, s_acc, nullptr, 0, 0, -1, true))) return rc;
         CUDA_TRY(cudaEventRecord(E.ev_acc[w], s_acc));
         CUDA_TRY(cudaStreamWaitEvent(s_tail, E.ev_acc[w], 0));

@@ -94,8 +94,13 @@ static int create_engine(int device, std::shared_ptr<Engine> &out) {
             const bool hi = (i == 0 && (mask & 1)) || (i == 2 && (mask & 2));
             CUDA_TRY(cudaStreamCreateWithPriority(&E->pipe_stream[i], cudaStreamNonBlocking, hi ? prio_hi : prio_lo));
         }
-        for (cudaEvent_t *ev : {&E->ev_fork, &E->ev_join, &E->ev_sorted[0], &E->ev_sorted[1], &E->ev_acc[0], &E->ev_acc[1],
-                                &E->ev_tail[0], &E->ev_tail[1]})
+        std::vector<cudaEvent_t *> evs = {&E->ev_fork, &E->ev_join};
+        for (int i = 0; i < Engine::PIPE_SETS_MAX; i++) {
+            evs.push_back(&E->ev_sorted[i]);
+            evs.push_back(&E->ev_acc[i]);
+            evs.push_back(&E->ev_tail[i]);
+        }
+        for (cudaEvent_t *ev : evs)
             CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         CUDA_TRY(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
         for (cudaEvent_t &ev : E->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -220,8 +225,13 @@ void engine_teardown(Engine &En) {
     for (auto &ev : E->prof_ev)
         if (ev) cudaEventDestroy(ev);
     if (E->done) cudaEventDestroy(E->done);
-    for (cudaEvent_t ev : {E->ev_fork, E->ev_join, E->ev_sorted[0], E->ev_sorted[1], E->ev_acc[0], E->ev_acc[1], E->ev_tail[0],
-                           E->ev_tail[1]})
+    std::vector<cudaEvent_t> evs = {E->ev_fork, E->ev_join};
+    for (int i = 0; i < Engine::PIPE_SETS_MAX; i++) {
+        evs.push_back(E->ev_sorted[i]);
+        evs.push_back(E->ev_acc[i]);
+        evs.push_back(E->ev_tail[i]);
+    }
+    for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
     for (cudaStream_t s : E->pipe_stream)
         if (s) cudaStreamDestroy(s);
@@ -1015,6 +1025,13 @@ int b200_profile_read(double *accumulate_ms, int *launches, uint64_t *pairs) {
         CUDA_TRY(cudaEventSynchronize(E.prof_ev[2 * i + 1]));
         float t = 0;
         CUDA_TRY(cudaEventElapsedTime(&t, E.prof_ev[2 * i], E.prof_ev[2 * i + 1]));
+        if (i > 0) {
+            // consecutive launches of a pipelined batch overlap at their ends (two accumulate streams): a launch is charged
+            // from the completion of the previous one, not from the moment it was queued behind it
+            float since_prev = 0;
+            if (cudaEventElapsedTime(&since_prev, E.prof_ev[2 * i - 1], E.prof_ev[2 * i + 1]) == cudaSuccess && since_prev > 0 && since_prev < t)
+                t = since_prev;
+        }
         ms += t;
     }
     if (accumulate_ms) *accumulate_ms = ms;

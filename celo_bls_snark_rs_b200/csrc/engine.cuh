@@ -98,10 +98,11 @@ struct Engine {
     bool has_pending = false;
     bool dead = false;               // torn down by b200_shutdown while another thread still held a reference
     std::mutex mu;
-    MsmWs ws[2];
+    static constexpr int PIPE_SETS_MAX = 4;
+    MsmWs ws[PIPE_SETS_MAX];         // [0], [1]: every path; the others: further sets of the batch pipeline (a tail may lag behind)
     // software pipeline of b200_msm_batch_device: sort / accumulate / tail streams and their hand-over events
     cudaStream_t pipe_stream[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sorted[2] = {}, ev_acc[2] = {}, ev_tail[2] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sorted[PIPE_SETS_MAX] = {}, ev_acc[PIPE_SETS_MAX] = {}, ev_tail[PIPE_SETS_MAX] = {};
     // host-pointer MSM: chunked H2D copies on their own stream, one `ready` event per chunk
     cudaStream_t copy_stream = nullptr;
     static constexpr int MAX_CHUNKS = 16;
