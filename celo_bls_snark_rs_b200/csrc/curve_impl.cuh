@@ -9,7 +9,8 @@ template <class C> struct CurveTraits;
 // ACC_SM: default accumulate kernel (0 registers only, 1 = X, Y of the accumulator and the cp.async-staged point in shared-memory
 // slots, 2 = the whole accumulator in slots) with ACC_SM_BLOCKS1 / ACC_SM_BLOCKS2 blocks of 128 threads per SM.  Measured
 // (profiles/r2_experiments.md): BLS12-377 G1 n = 2^20 8.27 -> 7.95 ms (1: 128 registers, 4 blocks), 7.94 (2: 96 registers, 5
-// blocks), 8.08 (2 with 6 blocks: spills); BW6-761 n = 2^22 150.0 -> 143.6 ms (1: 252 registers, no spills, 2 blocks), 147.0 (2).
+// blocks), 8.08 (2 with 6 blocks: spills); BW6-761 n = 2^22 150.0 -> 143.6 ms (1: 252 registers, no spills, 2 blocks), 147.0 (2);
+// BLS12-377 G2 n = 2^20 29.2 -> 26.6 ms (1), 27.4 (2).
 // ACC_SM_PIPE: the same choice inside the batch pipeline (3 = mode 1 with one block fewer per SM: with four blocks the sort and
 // tail kernels of the neighbouring MSMs find no room and a pipelined 2^20 MSM takes 8.32 ms instead of 7.19; BW6-761: 42.6 ms with
 // mode 1 against 44.4 with the register kernel).
@@ -23,7 +24,7 @@ constexpr bool B200_AFFINE_BUILD = true;
 constexpr bool B200_AFFINE_BUILD = false;
 #endif
 template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2, ACC_SM = 1, ACC_SM_PIPE = 3, ACC_SM_BLOCKS1 = 4, ACC_SM_BLOCKS2 = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 0, ACC_SM_PIPE = 0, ACC_SM_BLOCKS1 = 1, ACC_SM_BLOCKS2 = 1; static constexpr bool ACC_SM_BUILD = false; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
 template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
@@ -299,7 +300,7 @@ static int msm_stage_accumulate(Engine &E, MsmWs &W, const MsmPlan &p, const voi
     if constexpr (T::ACC_SM_BUILD) {
         if (!aft.levels && !affine && acc_sm) {
             using SL = AccSlots<F, 128>;
-            using PP = typename F::Params;
+            using PP = F;
             const unsigned grid = (unsigned)ceil_div(total, 128);
             auto go = [&](auto kern, int slots) -> int {
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::bytes(slots)));

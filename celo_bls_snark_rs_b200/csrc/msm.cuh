@@ -502,22 +502,24 @@ B200_DEV void acc_sts128(uint32_t addr, uint4 v) {
 }
 template <class F, int THREADS>
 struct AccSlots {
-    static constexpr int CH = F::N / 4;
+    using Mem = typename F::Mem;
+    static_assert(sizeof(Mem) % 16 == 0, "field images are whole 16-byte chunks");
+    static constexpr int CH = (int)(sizeof(Mem) / 16);
     static constexpr uint32_t STRIDE = THREADS * 16u, SLOT = CH * STRIDE;
     enum : uint32_t { X = 0, Y = 1, PX = 2, PY = 3 };
     static constexpr uint32_t bytes(int slots) { return (uint32_t)slots * SLOT; }
     B200_DEV static F ld(uint32_t base, uint32_t slot) {
-        F r;
+        Mem m;
+        uint4 *d = reinterpret_cast<uint4 *>(&m);
 #pragma unroll
-        for (int k = 0; k < CH; k++) {
-            const uint4 v = acc_lds128(base + slot * SLOT + k * STRIDE);
-            r.l[4 * k] = v.x, r.l[4 * k + 1] = v.y, r.l[4 * k + 2] = v.z, r.l[4 * k + 3] = v.w;
-        }
-        return r;
+        for (int k = 0; k < CH; k++) d[k] = acc_lds128(base + slot * SLOT + k * STRIDE);
+        return F::load(m);
     }
     B200_DEV static void st(uint32_t base, uint32_t slot, const F &v) {
+        const Mem m = v.store();
+        const uint4 *d = reinterpret_cast<const uint4 *>(&m);
 #pragma unroll
-        for (int k = 0; k < CH; k++) acc_sts128(base + slot * SLOT + k * STRIDE, make_uint4(v.l[4 * k], v.l[4 * k + 1], v.l[4 * k + 2], v.l[4 * k + 3]));
+        for (int k = 0; k < CH; k++) acc_sts128(base + slot * SLOT + k * STRIDE, d[k]);
     }
     // one packed affine record global -> slots PX, PY, asynchronously
     B200_DEV static void fetch_point(uint32_t base, const AffineMem<F> *g) {
@@ -531,12 +533,11 @@ struct AccSlots {
 };
 
 // ZS: ZZ and ZZZ live in slots too (six slots per thread), leaving only the temporaries of one addition in registers.
-template <class P, int THREADS, int MIN_BLOCKS, bool ZS>
+template <class F, int THREADS, int MIN_BLOCKS, bool ZS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-k_bucket_accumulate_sm(const AffineMem<Fp<P>> *__restrict__ bases, const uint32_t *__restrict__ sorted,
+k_bucket_accumulate_sm(const AffineMem<F> *__restrict__ bases, const uint32_t *__restrict__ sorted,
                        const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, uint32_t total_buckets,
-                       uint32_t big, int resume, XYZZMem<Fp<P>> *__restrict__ buckets) {
-    using F = Fp<P>;
+                       uint32_t big, int resume, XYZZMem<F> *__restrict__ buckets) {
     using S = AccSlots<F, THREADS>;
     constexpr uint32_t SZZ = 4, SZZZ = 5;            // slots of ZZ / ZZZ when ZS
     extern __shared__ uint4 acc_sm[];
