@@ -14,6 +14,9 @@ template <class C> struct CurveTraits;
 // ACC_SM_PIPE: the same choice inside the batch pipeline (3 = mode 1 with one block fewer per SM: with four blocks the sort and
 // tail kernels of the neighbouring MSMs find no room and a pipelined 2^20 MSM takes 8.32 ms instead of 7.19; BW6-761: 42.6 ms with
 // mode 1 against 44.4 with the register kernel).
+// REDUCE_THREAD_MIN: from this many bucket-reduce segments on, one thread per segment (k_bucket_reduce_thread) instead of one quad:
+// BW6-761 n = 2^22 143.7 -> 137.7 ms, 2^20 45.6 -> 43.9; BLS12-377 G1 n = 2^24 102.2 -> 100.5, 2^22 25.9 -> 25.6 (quads stay for the
+// 8704 segments of n = 2^20, a latency problem).
 // AFFINE: the curve also has the experimental batched-affine accumulate kernels (compiled only with B200_WITH_CROSSCHECKS);
 // SHARED_MUL: the accumulate kernel multiplies through one out-of-line product body; COOP_COMBINE: the Horner combine runs
 // on four warps with one limb per lane (coop.cuh) -- 2.5x faster for the 24-limb field and for Fq2, no faster for the
@@ -23,9 +26,9 @@ constexpr bool B200_AFFINE_BUILD = true;
 #else
 constexpr bool B200_AFFINE_BUILD = false;
 #endif
-template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2, ACC_SM = 1, ACC_SM_PIPE = 3, ACC_SM_BLOCKS1 = 4, ACC_SM_BLOCKS2 = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
-template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2, ACC_SM = 1, ACC_SM_PIPE = 3, ACC_SM_BLOCKS1 = 4, ACC_SM_BLOCKS2 = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr long REDUCE_THREAD_MIN = 24576; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 1L << 40; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 16384; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
 // keeping enough buckets in flight to fill 148 SMs.
@@ -360,8 +363,19 @@ static int msm_stage_reduce(MsmWs &W, const MsmPlan &p, int w_lo, int w_hi, bool
     using T = CurveTraits<C>;
     uint32_t red_threads = (uint32_t)(w_hi - w_lo) * p.segs * 4;   // one quad per segment
     if (red_threads) {
-        k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
-            W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi, W.partials.as<XYZZMem<F>>());
+        // quads (latency) below REDUCE_THREAD_MIN segments, one thread per segment (throughput) from there on;
+        // B200_REDUCE_THREAD_MIN overrides the per-curve limit (0: always threads)
+        static const long env_min = getenv("B200_REDUCE_THREAD_MIN") ? atol(getenv("B200_REDUCE_THREAD_MIN")) : -1;
+        const long thread_min = env_min >= 0 ? env_min : T::REDUCE_THREAD_MIN;
+        const uint32_t segments = red_threads / 4;
+        if ((long)segments >= thread_min) {
+            constexpr int TT = 64;
+            k_bucket_reduce_thread<F, TT><<<ceil_div(segments, TT), TT, 0, st>>>(W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi,
+                                                                             W.partials.as<XYZZMem<F>>());
+        } else {
+            k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
+                W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi, W.partials.as<XYZZMem<F>>());
+        }
         LAUNCH_CHECK();
     }
     constexpr int WS_THREADS = 256;                                // 64 quads per window

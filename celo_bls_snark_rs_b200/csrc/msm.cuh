@@ -800,6 +800,46 @@ __global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__r
     if (Q.q == 0) partials[t] = acc.store();
 }
 
+// The same partial, ONE THREAD per segment: the throughput form.  A quad gives a point operation the latency of 3-4 product
+// rounds, which is what the 8704 segments of a 2^20 BLS12-377 MSM need; but the 86 k segments of a BW6-761 MSM at n = 2^22
+// are nine waves of quads, and there the idle lanes of the short rounds, the shuffles and 7.5 KB of spills per thread cost
+// more than latency buys (24.7 ms for 10 ms of multiplier time).  Here every thread walks its segment with the out-of-line
+// XYZZ addition / doubling (exact in every exceptional case): no idle lanes, no shuffles.
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_bucket_reduce_thread(const XYZZMem<F> *__restrict__ buckets, MsmPlan p, int w_lo, int w_hi,
+                                                                  XYZZMem<F> *__restrict__ partials) {
+    uint32_t t = blockIdx.x * THREADS + threadIdx.x;
+    const uint32_t total = (uint32_t)(w_hi - w_lo) * p.segs;
+    if (t >= total) return;
+    t += (uint32_t)w_lo * p.segs;
+    const uint32_t w = t / p.segs, seg = t % p.segs;
+    const XYZZMem<F> *b = buckets + (size_t)w * p.nb + (size_t)seg * p.seg_len;
+    XYZZ<F> run = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
+#pragma unroll 1
+    for (int j = p.seg_len - 1; j >= 0; j--) {
+        run.add(XYZZ<F>::load(ldg_mem(b + j)));
+        launder(run);
+        acc.add(run);
+        launder(acc);
+    }
+    if (seg) {                                       // + (seg * seg_len) * run: double-and-add, MSB first
+        const uint32_t k = seg * (uint32_t)p.seg_len;
+        XYZZ<F> r = XYZZ<F>::inf();
+#pragma unroll 1
+        for (int bit = 31 - __clz(k | 1u); bit >= 0; bit--) {
+            r.dbl();
+            launder(r);
+            if ((k >> bit) & 1u) {
+                r.add(run);
+                launder(r);
+            }
+        }
+        acc.add(r);
+        launder(acc);
+    }
+    partials[t] = acc.store();
+}
+
 // block w: window_sums[w] = sum of the window's partials (THREADS / 4 quads, tree in smem)
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_window_sum(const XYZZMem<F> *__restrict__ partials, MsmPlan p, int w_lo, int w_hi,
