@@ -16,7 +16,7 @@ template <class C> struct CurveTraits;
 // mode 1 against 44.4 with the register kernel).
 // REDUCE_THREAD_MIN: from this many bucket-reduce segments on, one thread per segment (k_bucket_reduce_thread) instead of one quad:
 // BW6-761 n = 2^22 143.7 -> 137.7 ms, 2^20 45.6 -> 43.9; BLS12-377 G1 n = 2^24 102.2 -> 100.5, 2^22 25.9 -> 25.6 (quads stay for the
-// 8704 segments of n = 2^20, a latency problem).
+// 8704 segments of n = 2^20, a latency problem); BLS12-377 G2 n = 2^22 88.4 -> 85.0 ms, but 2^20 26.6 -> 28.0; BW6-761 2^18 14.2 -> 16.0.
 // AFFINE: the curve also has the experimental batched-affine accumulate kernels (compiled only with B200_WITH_CROSSCHECKS);
 // SHARED_MUL: the accumulate kernel multiplies through one out-of-line product body; COOP_COMBINE: the Horner combine runs
 // on four warps with one limb per lane (coop.cuh) -- 2.5x faster for the 24-limb field and for Fq2, no faster for the
@@ -27,7 +27,7 @@ constexpr bool B200_AFFINE_BUILD = true;
 constexpr bool B200_AFFINE_BUILD = false;
 #endif
 template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2, ACC_SM = 1, ACC_SM_PIPE = 3, ACC_SM_BLOCKS1 = 4, ACC_SM_BLOCKS2 = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr long REDUCE_THREAD_MIN = 24576; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 1L << 40; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 24576; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
 template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 16384; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
