@@ -183,7 +183,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = n * args.steps / dt / 1e6
     sample = f"n=2^{k} pairs per step (full workload is 2^{LOG2_N}), {args.steps} steps"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (377-bit Montgomery)", "data": "synthetic",
@@ -193,7 +193,7 @@ def run_reference(args):
                          "host_cores": cores, "window_tasks": tasks},
         "e2e": {"value": val, "unit": "Mpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ----------------------------------------------------------------------------------------
@@ -834,11 +834,29 @@ def run_b200(args):
     if ctx.rank == 0:
         line["configs"] = subs
         line["parity"] = bool(ok)
-        print(json.dumps(line))
+        emit(line)
     if ctx.world > 1:
         ctx.dist.destroy_process_group()
     if not ok:
         raise SystemExit("bench.py: PARITY FAILED (see the `parity` fields of the JSON line)")
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that whatever a native
+    library prints there (NCCL's version banner under NCCL_DEBUG=VERSION, which ignores NCCL_DEBUG_FILE) cannot precede it."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -855,6 +873,7 @@ def main():
     ap.add_argument("--prove-log2n", type=int, default=24, help="config 5: domain of the outer proof (inner: 4x smaller)")
     ap.add_argument("--prove-sample-log2n", type=int, default=12, help="config 5: domain of the parity / CPU sample")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
