@@ -17,6 +17,8 @@ template <class C> struct CurveTraits;
 // REDUCE_THREAD_MIN: from this many bucket-reduce segments on, one thread per segment (k_bucket_reduce_thread) instead of one quad:
 // BW6-761 n = 2^22 143.7 -> 137.7 ms, 2^20 45.6 -> 43.9; BLS12-377 G1 n = 2^24 102.2 -> 100.5, 2^22 25.9 -> 25.6 (quads stay for the
 // 8704 segments of n = 2^20, a latency problem); BLS12-377 G2 n = 2^22 88.4 -> 85.0 ms, but 2^20 26.6 -> 28.0; BW6-761 2^18 14.2 -> 16.0.
+// REDUCE_THREAD_BLOCKS: resident blocks per SM of that kernel's register-capped build, used when it saves a round of blocks (<= 1 %:
+// profiles/r2_experiments.md); 1: no capped build.
 // AFFINE: the curve also has the experimental batched-affine accumulate kernels (compiled only with B200_WITH_CROSSCHECKS);
 // SHARED_MUL: the accumulate kernel multiplies through one out-of-line product body; COOP_COMBINE: the Horner combine runs
 // on four warps with one limb per lane (coop.cuh) -- 2.5x faster for the 24-limb field and for Fq2, no faster for the
@@ -26,9 +28,9 @@ constexpr bool B200_AFFINE_BUILD = true;
 #else
 constexpr bool B200_AFFINE_BUILD = false;
 #endif
-template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2, ACC_SM = 1, ACC_SM_PIPE = 3, ACC_SM_BLOCKS1 = 4, ACC_SM_BLOCKS2 = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr long REDUCE_THREAD_MIN = 24576; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
-template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 24576; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
-template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 16384; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G1_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 3, RED_THREADS = 128, AFT_THREADS = 128, AFT_MIN_BLOCKS = 2, ACC_SM = 1, ACC_SM_PIPE = 3, ACC_SM_BLOCKS1 = 4, ACC_SM_BLOCKS2 = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr long REDUCE_THREAD_MIN = 24576; static constexpr int REDUCE_THREAD_BLOCKS = 8; static constexpr bool AFFINE = B200_AFFINE_BUILD, SHARED_MUL = true, COOP_COMBINE = false, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = true; };
+template <> struct CurveTraits<G2_377> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 24576; static constexpr int REDUCE_THREAD_BLOCKS = 1; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = false, AFT_PREFETCH = false; };
+template <> struct CurveTraits<G_761> { static constexpr int ACC_THREADS = 128, ACC_MIN_BLOCKS = 1, RED_THREADS = 64, AFT_THREADS = 128, AFT_MIN_BLOCKS = 1, ACC_SM = 1, ACC_SM_PIPE = 1, ACC_SM_BLOCKS1 = 2, ACC_SM_BLOCKS2 = 3; static constexpr long REDUCE_THREAD_MIN = 16384; static constexpr int REDUCE_THREAD_BLOCKS = 5; static constexpr bool ACC_SM_BUILD = true; static constexpr bool AFFINE = false, SHARED_MUL = false, COOP_COMBINE = true, AFFTREE = B200_AFFINE_BUILD, AFT_PREFETCH = false; };
 
 // Window plan: minimise (madds + bucket-reduce work) in field-multiplication units while
 // keeping enough buckets in flight to fill 148 SMs.
@@ -370,8 +372,32 @@ static int msm_stage_reduce(MsmWs &W, const MsmPlan &p, int w_lo, int w_hi, bool
         const uint32_t segments = red_threads / 4;
         if ((long)segments >= thread_min) {
             constexpr int TT = 64;
-            k_bucket_reduce_thread<F, TT><<<ceil_div(segments, TT), TT, 0, st>>>(W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi,
-                                                                             W.partials.as<XYZZMem<F>>());
+            // register cap (REDUCE_THREAD_BLOCKS resident blocks per SM) when it saves a round of blocks; B200_REDUCE_THREAD_CAP = 0 / 1
+            // forces it off / on (read at every call: tools compare both forms inside one process)
+            const char *cap_env = getenv("B200_REDUCE_THREAD_CAP");
+            bool cap = false;
+            if constexpr (T::REDUCE_THREAD_BLOCKS > 1) {
+                static const int uncapped_blocks = [] {
+                    int b = 1;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_bucket_reduce_thread<F, TT>, TT, 0) != cudaSuccess) b = 1;
+                    return std::max(1, b);
+                }();
+                static const int sm_count = [] {
+                    int d = 0, n = 148;
+                    if (cudaGetDevice(&d) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess) n = 148;
+                    return std::max(1, n);
+                }();
+                const size_t blocks = ceil_div(segments, TT), sms = (size_t)sm_count;
+                const size_t rounds_now = ceil_div(blocks, sms * (size_t)uncapped_blocks);
+                const size_t rounds_cap = ceil_div(blocks, sms * (size_t)T::REDUCE_THREAD_BLOCKS);
+                cap = cap_env ? atoi(cap_env) != 0 : rounds_cap < rounds_now;
+                if (cap)
+                    k_bucket_reduce_thread<F, TT, T::REDUCE_THREAD_BLOCKS><<<ceil_div(segments, TT), TT, 0, st>>>(
+                        W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi, W.partials.as<XYZZMem<F>>());
+            }
+            if (!cap)
+                k_bucket_reduce_thread<F, TT><<<ceil_div(segments, TT), TT, 0, st>>>(W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi,
+                                                                                 W.partials.as<XYZZMem<F>>());
         } else {
             k_bucket_reduce<F, T::RED_THREADS><<<ceil_div(red_threads, T::RED_THREADS), T::RED_THREADS, 0, st>>>(
                 W.buckets.as<XYZZMem<F>>(), p, w_lo, w_hi, W.partials.as<XYZZMem<F>>());

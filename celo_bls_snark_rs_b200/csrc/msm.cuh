@@ -805,9 +805,11 @@ __global__ void __launch_bounds__(THREADS) k_bucket_reduce(const XYZZMem<F> *__r
 // are nine waves of quads, and there the idle lanes of the short rounds, the shuffles and 7.5 KB of spills per thread cost
 // more than latency buys (24.7 ms for 10 ms of multiplier time).  Here every thread walks its segment with the out-of-line
 // XYZZ addition / doubling (exact in every exceptional case): no idle lanes, no shuffles.
-template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_bucket_reduce_thread(const XYZZMem<F> *__restrict__ buckets, MsmPlan p, int w_lo, int w_hi,
-                                                                  XYZZMem<F> *__restrict__ partials) {
+// MIN_BLOCKS > 1 caps the registers so that more blocks are resident: every thread does the same work, so the launch takes
+// ceil(blocks / resident slots) rounds and one more resident block per SM can save a whole round (curve_impl.cuh).
+template <class F, int THREADS, int MIN_BLOCKS = 0>                     // 0: no cap (ptxas treats it as unspecified)
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) k_bucket_reduce_thread(const XYZZMem<F> *__restrict__ buckets, MsmPlan p, int w_lo,
+                                                                              int w_hi, XYZZMem<F> *__restrict__ partials) {
     uint32_t t = blockIdx.x * THREADS + threadIdx.x;
     const uint32_t total = (uint32_t)(w_hi - w_lo) * p.segs;
     if (t >= total) return;

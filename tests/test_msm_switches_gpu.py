@@ -68,6 +68,7 @@ def run_child(job_path, env_extra):
 @pytest.mark.parametrize("env_extra", [
     {"B200_REDUCE_THREAD_MIN": "0"},                              # one thread per bucket-reduce segment everywhere
     {"B200_REDUCE_THREAD_MIN": "0", "B200_MSM_SEG": "16"},
+    {"B200_REDUCE_THREAD_MIN": "0", "B200_REDUCE_THREAD_CAP": "1"},   # ... with the register cap (more resident blocks)
     {"B200_MSM_ACC_SM": "0"},                                     # register-only accumulate kernel
     {"B200_MSM_ACC_SM": "2"},                                     # shared-memory slots at the higher occupancy
     {"B200_COMBINE": "quad"}, {"B200_COMBINE": "coop"},           # both Horner kernels on every curve
